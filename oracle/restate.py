@@ -1,0 +1,456 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement of DLMC-QUANT's fake-quant hot path.
+
+This file is the *oracle* of the repo: a self-contained restatement, in plain
+eager torch ops, of the arithmetic the reference performs in
+`dlmc/quantization/scalar/{utils.py, ops.py, modules/base.py, RootQ/, FSPTQuant/}`.
+It exists because `/root/reference` cannot travel to the GPU box.  Every function
+cites the reference file:line it follows and keeps the reference's operation
+ORDER (each torch op is one separately rounded IEEE fp32 op), because "bit-exact"
+for this path means exactly that order.  Gradients come from autograd over the
+same chain, which is how the reference itself obtains them.
+
+Pinning: `oracle/make_golden.py` runs the unmodified reference (through
+`oracle/ref_shim.py`) and this file on the same seeded inputs and stores the
+reference's outputs in `tests/golden/`; `tests/test_oracle_golden.py` re-checks
+this file against those fixtures wherever the tests run.  The reference has no
+tests or golden vectors of its own, so the fixtures minted
+from its live code are the pin.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import this module.  The product package never does.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+N_SWEEP = 80          # ops.py:52,177  `for i in range(80)`
+SWEEP_MIN_LOSS = 1000  # ops.py:48,176
+
+
+# --------------------------------------------------------------------------- #
+# scalar/utils.py
+# --------------------------------------------------------------------------- #
+def qrange(signed, n_bits):
+    """utils.py:14-22 - symmetric signed range (no -2^(n-1)), or [0, 2^n-1]."""
+    if signed:
+        hi = 2 ** (n_bits - 1) - 1
+        return -hi, hi
+    return 0, 2 ** n_bits - 1
+
+
+def codes_a1(x, scale, offset, lo, hi):
+    """utils.py:1-2 - round THEN clamp, +1e-7 on the divisor only."""
+    return ((x - offset) / (scale + 1e-7)).round().clamp(lo, hi)
+
+
+def dequant_a1(codes, scale, offset):
+    """utils.py:5-6 - uses the scale WITHOUT the epsilon."""
+    return codes * scale + offset
+
+
+def emulate_a1(x, scale, offset, lo, hi):
+    """utils.py:9-11."""
+    return dequant_a1(codes_a1(x, scale, offset, lo, hi), scale, offset)
+
+
+def grad_scale(s, g):
+    """utils.py:24-27 - value (s - s*g) + s*g, gradient scaled by g."""
+    sg = s * g
+    return (s - sg).detach() + sg
+
+
+def round_ste(v):
+    """utils.py:29-32."""
+    return (v.round() - v).detach() + v
+
+
+def floor_ste(v):
+    """utils.py:34-37."""
+    return (v.floor() - v).detach() + v
+
+
+def l2_loss(a, b):
+    """trainer/loss/loss.py:22-24 - sum over axis 1, mean over the rest."""
+    return ((a - b) ** 2).sum(axis=1).mean()
+
+
+# --------------------------------------------------------------------------- #
+# modules/base.py (QBase): A.2 "affine, float offset" form
+# --------------------------------------------------------------------------- #
+def lsq_g(numel, qmax):
+    """modules/base.py:96,131 - python double."""
+    return 1 / math.sqrt(numel * qmax)
+
+
+def fq_affine(x, scale, offset, lo, hi, g):
+    """modules/base.py:97,102 (activation) and :132-133 (weight).
+    clamp THEN round, no epsilon, scale passed through grad_scale first."""
+    s = grad_scale(scale, g)
+    return round_ste(((x - offset) / s).clamp(lo, hi)) * s + offset
+
+
+def fq_affine_codes(x, scale, offset, lo, hi, g):
+    """The integer codes inside fq_affine (fp32-valued integers)."""
+    s = grad_scale(scale, g)
+    return round_ste(((x - offset) / s).clamp(lo, hi))
+
+
+def fq_affine_fwd_bwd(x, scale, offset, lo, hi, g, dy):
+    """Forward + autograd backward of fq_affine -> (y, dx, dscale)."""
+    x = x.detach().clone().requires_grad_(True)
+    scale = scale.detach().clone().requires_grad_(True)
+    y = fq_affine(x, scale, offset, lo, hi, g)
+    dx, ds = torch.autograd.grad(y, (x, scale), dy)
+    return y.detach(), dx, ds
+
+
+def lsq_init_scale(x, qmax):
+    """modules/base.py:84,119 - LSQ initial scale 2*mean|x|/sqrt(qmax)."""
+    return 2 * x.detach().abs().mean() / math.sqrt(qmax)
+
+
+def fun_lsq_backward(w, scale, lo, hi, g, dy):
+    """modules/function.py:38-47 - FunLSQ.backward restated (strict < / > masks,
+    offset ignored) -> (dw, dscale[1])."""
+    q = w / scale
+    below = (q < lo).float()
+    above = (q > hi).float()
+    mid = torch.ones(w.shape, device=w.device) - below - above
+    ds = ((lo * below + hi * above + mid * (-q + q.round())) * dy).sum().unsqueeze(dim=0) * g
+    return mid * dy, ds
+
+
+# --------------------------------------------------------------------------- #
+# FSPTQuant/base.py: A.3 integer zero-point form, A.4 symmetric per-channel
+# --------------------------------------------------------------------------- #
+def fq_zp(x, scale, zp, lo, hi):
+    """FSPTQuant/base.py:108-109 - round, add zp, clamp; no epsilon."""
+    q = (round_ste(x / scale) + zp).clamp(lo, hi)
+    return (q - zp) * scale
+
+
+def fq_zp_codes(x, scale, zp, lo, hi):
+    return (round_ste(x / scale) + zp).clamp(lo, hi)
+
+
+def fq_zp_fwd_bwd(x, scale, zp, lo, hi, dy):
+    x = x.detach().clone().requires_grad_(True)
+    scale = scale.detach().clone().requires_grad_(True)
+    y = fq_zp(x, scale, zp, lo, hi)
+    dx, ds = torch.autograd.grad(y, (x, scale), dy)
+    return y.detach(), dx, ds
+
+
+def fq_sym(w, scale, lo, hi):
+    """FSPTQuant/base.py:149-152 - symmetric per-channel weight fake-quant."""
+    return round_ste(w / scale).clamp(lo, hi) * scale
+
+
+def fq_sym_codes(w, scale, lo, hi):
+    return round_ste(w / scale).clamp(lo, hi)
+
+
+def fq_sym_fwd_bwd(w, scale, lo, hi, dy):
+    w = w.detach().clone().requires_grad_(True)
+    scale = scale.detach().clone().requires_grad_(True)
+    y = fq_sym(w, scale, lo, hi)
+    dw, ds = torch.autograd.grad(y, (w, scale), dy)
+    return y.detach(), dw, ds
+
+
+ADAROUND_GAMMA, ADAROUND_ZETA = -0.1, 1.1   # FSPTQuant/base.py:62
+
+
+def adaround_soft_targets(alpha):
+    """FSPTQuant/base.py:78-79."""
+    return torch.clamp(torch.sigmoid(alpha) * (ADAROUND_ZETA - ADAROUND_GAMMA) + ADAROUND_GAMMA, 0, 1)
+
+
+def adaround_init_alpha(w, scale):
+    """FSPTQuant/base.py:73-76."""
+    w_floor = torch.floor(w.detach() / scale)
+    rest = w.detach() / scale - w_floor
+    return -torch.log((ADAROUND_ZETA - ADAROUND_GAMMA) / (rest - ADAROUND_GAMMA) - 1)
+
+
+def fq_adaround(w, scale, alpha, lo, hi, training):
+    """FSPTQuant/base.py:136-141,151-152 - floor has NO straight-through here."""
+    q = torch.floor(w / scale)
+    if training:
+        q = q + adaround_soft_targets(alpha)
+    else:
+        q = q + (alpha >= 0).float()
+    return q.clamp(lo, hi) * scale
+
+
+def fq_adaround_fwd_bwd(w, scale, alpha, lo, hi, dy):
+    w = w.detach().clone().requires_grad_(True)
+    scale = scale.detach().clone().requires_grad_(True)
+    alpha = alpha.detach().clone().requires_grad_(True)
+    y = fq_adaround(w, scale, alpha, lo, hi, True)
+    ds, da = torch.autograd.grad(y, (scale, alpha), dy)
+    return y.detach(), ds, da
+
+
+# --------------------------------------------------------------------------- #
+# RootQ/function.py + RootQ/base.py: A.5
+# --------------------------------------------------------------------------- #
+def rootq_clipping(x, upper, lower):
+    """RootQ/function.py:15-20 - relu trick, NOT clamp (loses low bits, inf->nan)."""
+    x = x + F.relu(lower - x)
+    x = x - F.relu(x - upper)
+    return x
+
+
+def rootq_phi(x, mi, alpha, delta):
+    """RootQ/function.py:22-32 - root-function estimator."""
+    alpha = alpha + F.relu(1e-4 - alpha)
+    alpha = alpha - F.relu(alpha - 1)
+    x = x - mi
+    sg = x / (torch.abs(x) + 1e-5)
+    k = 2 / delta
+    return torch.pow(k * abs(x) + 1e-5, alpha) * sg
+
+
+class _SignSTE(torch.autograd.Function):
+    """RootQ/function.py:5-12 - value sgn(x), gradient identity."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.sgn()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def rootq_dequant(sig, lower, delta, interval):
+    """RootQ/function.py:63-67."""
+    return ((sig + 1) / 2 + interval) * delta + lower
+
+
+def rootq_act_init(x, lo, hi):
+    """RootQ/base.py:80 - first-call activation scale."""
+    return (torch.max(x) - torch.min(x)) / (hi - lo)
+
+
+def rootq_wt_init(w, hi):
+    """RootQ/base.py:115-116 - first-call weight bounds (upper, lower)."""
+    up = 2 * w.detach().abs().mean() * math.sqrt(hi)
+    dn = -2 * w.detach().abs().mean() * math.sqrt(hi)
+    return up, dn
+
+
+def rootq_act(x, in_scale, run_scale, momentum, lo, hi, training):
+    """RootQ/base.py:92-111 -> (y, new_run_scale).  `run_scale` is not modified."""
+    if training:
+        g = 1 / math.sqrt(x.numel() * hi)
+        rs = run_scale.mul(1 - momentum).add(momentum * in_scale)
+        rs = g * rs + (1 - g) * rs.detach()
+        upper = rs * (hi - lo)
+        new_run = rs.data.detach().clone()
+    else:
+        rs = run_scale
+        upper = rs * (hi - lo)
+        new_run = run_scale.detach().clone()
+    xq = rootq_clipping(x, upper, 0)
+    interval = round_ste(xq / rs)
+    return interval * rs, new_run
+
+
+def rootq_act_fwd_bwd(x, in_scale, run_scale, momentum, lo, hi, dy):
+    x = x.detach().clone().requires_grad_(True)
+    in_scale = in_scale.detach().clone().requires_grad_(True)
+    y, new_run = rootq_act(x, in_scale, run_scale, momentum, lo, hi, True)
+    dx, ds = torch.autograd.grad(y, (x, in_scale), dy)
+    return y.detach(), new_run, dx, ds
+
+
+def rootq_wt(w, upper, lower, alpha, run_upper, run_lower, momentum, lo, hi, training):
+    """RootQ/base.py:131-155 -> (w_q, new_run_upper, new_run_lower)."""
+    if training:
+        g = 1 / math.sqrt(w.numel() * hi)
+        ru = run_upper.mul(1 - momentum).add(momentum * upper)
+        rl = run_lower.mul(1 - momentum).add(momentum * lower)
+        ru = g * ru + (1 - g) * ru.detach()
+        rl = g * rl + (1 - g) * rl.detach()
+        new_ru, new_rl = ru.data.clone(), rl.data.clone()
+    else:
+        ru, rl = run_upper, run_lower
+        new_ru, new_rl = run_upper.detach().clone(), run_lower.detach().clone()
+    c = rootq_clipping(w, ru, rl)
+    delta = (ru - rl) / (hi - lo)
+    interval = floor_ste((c - rl) / delta)
+    mi = (interval + 0.5) * delta + rl
+    p = rootq_phi(c, mi.detach(), alpha, delta)
+    sig = _SignSTE.apply(p)
+    return rootq_dequant(sig, rl, delta, interval), new_ru, new_rl
+
+
+def rootq_wt_fwd_bwd(w, upper, lower, alpha, run_upper, run_lower, momentum, lo, hi, dy):
+    w = w.detach().clone().requires_grad_(True)
+    upper = upper.detach().clone().requires_grad_(True)
+    lower = lower.detach().clone().requires_grad_(True)
+    alpha = alpha.detach().clone().requires_grad_(True)
+    y, nru, nrl = rootq_wt(w, upper, lower, alpha, run_upper, run_lower, momentum, lo, hi, True)
+    dw, du, dl, da = torch.autograd.grad(y, (w, upper, lower, alpha), dy)
+    return y.detach(), nru, nrl, dw, du, dl, da
+
+
+# --------------------------------------------------------------------------- #
+# scalar/ops.py: observers
+# --------------------------------------------------------------------------- #
+def _rows(t, ch_axis):
+    """ops.py:112-118 - channel-major 2-D view and the broadcast shape."""
+    shape = [1] * t.dim()
+    shape[ch_axis] = -1
+    return t.transpose(0, ch_axis).reshape(t.shape[ch_axis], -1), shape
+
+
+def obs_minmax_tensor(t, n_bits, signed, allow_offset=True):
+    """ops.py:20-34."""
+    if signed:
+        return t.abs().max() / ((2 ** (n_bits - 1)) - 1), torch.tensor(0)
+    lo = t.min()
+    if not allow_offset:
+        assert (lo >= 0).all()
+        lo = torch.tensor(0)
+    return (t.max() - lo) / ((2 ** n_bits) - 1), lo
+
+
+def obs_minmax_channel(t, n_bits, signed, ch_axis=0, allow_offset=True):
+    """ops.py:121-140."""
+    rows, shape = _rows(t, ch_axis)
+    if signed:
+        scale = rows.abs().max(dim=1)[0] / ((2 ** (n_bits - 1)) - 1)
+        offset = torch.zeros_like(scale)
+    else:
+        lo = rows.min(dim=1)[0]
+        if not allow_offset:
+            assert (lo >= 0).all()
+            lo[:] = 0.
+        scale = (rows.max(dim=1)[0] - lo) / ((2 ** n_bits) - 1)
+        offset = lo
+    return scale.reshape(shape), offset.reshape(shape)
+
+
+def obs_minmax_pixel(t, n_bits, signed, allow_offset=True):
+    """ops.py:142-167 - reduce over (Cout, Cin) per kernel position; the unsigned
+    branch takes abs() before min/max (reference quirk A.7-10, reproduced)."""
+    shape = [t.shape[2], t.shape[3]] if t.dim() == 4 else [t.shape[2]]
+    t3 = t.reshape([t.shape[0], t.shape[1], -1])
+    if signed:
+        amax = t3.abs().max(dim=0)[0].max(dim=0)[0]
+        scale = amax / ((2 ** (n_bits - 1)) - 1)
+        offset = torch.zeros_like(scale)
+    else:
+        lo = t3.abs().min(dim=0)[0].min(dim=0)[0]
+        hi = t3.abs().max(dim=0)[0].max(dim=0)[0]
+        if not allow_offset:
+            assert (lo >= 0).all()
+            lo[:] = 0.
+        scale = (hi - lo) / ((2 ** n_bits) - 1)
+        offset = lo
+    return scale.reshape(shape), offset.reshape(shape)
+
+
+def obs_l2loss_tensor(t, n_bits, signed, allow_offset=True, return_index=False):
+    """ops.py:36-68 - 80-point clip-ratio MSE sweep, per tensor.  Signed inputs take
+    the min/max answer (:37-40).  First strict minimum below 1000 wins (:48,62)."""
+    if signed:
+        out = t.abs().max() / ((2 ** (n_bits - 1)) - 1), torch.tensor(0)
+        return out + (-1,) if return_index else out
+    lo = t.min()
+    if not allow_offset:
+        assert (lo >= 0).all()
+        lo = torch.tensor(0)
+    hi = t.max()
+    qmax = (2 ** n_bits) - 1
+    best = SWEEP_MIN_LOSS
+    scale, offset, pick = hi / qmax, torch.tensor(0), -1
+    for i in range(N_SWEEP):
+        r = 1 - 0.01 * i
+        c_hi, c_lo = r * hi, r * lo
+        c_scale = (c_hi - c_lo) / qmax
+        c_zp = torch.round(-c_lo / c_scale)
+        q = torch.round(t / c_scale) + c_zp
+        q = (q.clamp(0, qmax) - c_zp) * c_scale
+        loss = l2_loss(q, t)
+        if loss < best:
+            pick, best, scale, offset = i, loss, c_scale, c_zp
+    return (scale, offset, pick) if return_index else (scale, offset)
+
+
+def obs_l2loss_channel(t, n_bits, signed, ch_axis=0):
+    """ops.py:169-196 - per-channel sweep.  Reproduces two reference defects on
+    purpose: `signed` is ignored by the search (always clamps
+    to [0, 2^n-1]) and the running minimum ALIASES the offset vector, so accepting
+    a candidate rewrites the minimum used by the following candidates."""
+    rows, shape = _rows(t, ch_axis)
+    scale, offset = obs_minmax_channel(rows, n_bits, signed, ch_axis=0, allow_offset=True)
+    qmax = (2 ** n_bits) - 1
+    lo = offset                      # alias, as at ops.py:172
+    hi = offset + scale * qmax       # fresh tensor
+    for c in range(rows.shape[0]):
+        best = SWEEP_MIN_LOSS
+        for i in range(N_SWEEP):
+            r = 1 - 0.01 * i
+            c_lo, c_hi = r * lo[c], r * hi[c]
+            c_scale = (c_hi - c_lo) / qmax
+            c_zp = torch.round(-c_lo / c_scale)
+            q = torch.round(rows[c] / c_scale)
+            q = (q + c_zp).clamp(0, qmax)
+            q = (q - c_zp) * c_scale
+            loss = l2_loss(rows[c].view(1, -1), q.view(1, -1))
+            if best > loss:
+                scale[c] = c_scale
+                offset[c] = c_zp     # also rewrites lo[c]
+                best = loss
+    return scale.reshape(shape), offset.reshape(shape)
+
+
+def obs_l2norm_tensor(t, n_bits, signed, return_iters=False):
+    """ops.py:71-83 - fixed point s <- sum(x q)/sum(q q + 1e-7) from the min/max start."""
+    scale, offset = obs_minmax_tensor(t, n_bits, signed, allow_offset=True)
+    lo, hi = qrange(signed, n_bits)
+    diff, iters = float('inf'), 0
+    while diff > 1e-5:
+        q = codes_a1(t, scale, offset, lo, hi)
+        new = (t * q).sum() / (q * q + 1e-7).sum()
+        diff = (new - scale).abs() / scale
+        scale = new
+        iters += 1
+    return (scale, offset, iters) if return_iters else (scale, offset)
+
+
+def obs_l2norm_channel(t, n_bits, signed, ch_axis=0, return_iters=False):
+    """ops.py:198-215 - per-channel fixed point, global L2 stopping rule."""
+    rows, shape = _rows(t, ch_axis)
+    scale, offset = obs_minmax_channel(rows, n_bits, signed, ch_axis=0, allow_offset=True)
+    lo, hi = qrange(signed, n_bits)
+    diff, iters = float('inf'), 0
+    while diff > 1e-5:
+        q = codes_a1(rows, scale, offset, lo, hi)
+        new = ((rows * q).sum(axis=1) / (q * q + 1e-7).sum(axis=1)).reshape(scale.shape)
+        diff = ((new - scale) ** 2).sum().sqrt() / (scale ** 2).sum().sqrt()
+        scale = new
+        iters += 1
+    out = scale.reshape(shape), offset.reshape(shape)
+    return out + (iters,) if return_iters else out
+
+
+OBSERVERS = {
+    "minmax_tensor": obs_minmax_tensor,
+    "minmax_channel": obs_minmax_channel,
+    "minmax_pixel": obs_minmax_pixel,
+    "l2loss_tensor": obs_l2loss_tensor,
+    "l2loss_channel": obs_l2loss_channel,
+    "l2norm_tensor": obs_l2norm_tensor,
+    "l2norm_channel": obs_l2norm_channel,
+}
+
+
+def get_qparams_tensor(t, qtype, **kwargs):
+    """ops.py:15-18 - name dispatch."""
+    return OBSERVERS[qtype](t, **kwargs)
