@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py - fake-quant fwd+bwd throughput on the ResNet-50 W4A4 QAT quantizer set.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one synthetic ImageNet-shaped batch: for each of the 54
+quantised layers of torchvision ResNet-50 the activation fake-quant forward (A4 unsigned, per-tensor,
+QBase form, dlmc/quantization/scalar/modules/base.py:96-102) and backward (dx + d in_scale), plus
+the per-channel W4 weight fake-quant forward/backward of all 54 weight tensors (one grouped launch
+each way).  Metric: algorithmic HBM GB/s = 20 B/element (fp32: read x, write y, read dy, read x,
+write dx) * elements / time.
+
+  value        device-resident (inputs in HBM before the timed region), CUDA-graph replayed
+  e2e          same workload through the host-buffer C-ABI entry (pinned host tensors in and out,
+               H2D/D2H inside the timed region)
+  roofline     the dominant kernel (fq_bwd_flat: 12 B/elem) timed live with CUDA events
+  cpu_baseline the oracle port (the reference's eager torch chain) on the host cores, bounded sample
+
+`--impl reference` times that CPU implementation alone (rank 0 only under torchrun).
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "fakequant_fwd_bwd_hbm_gbps"
+UNIT = "GB/s"
+BYTES_FWD, BYTES_BWD = 8, 12      # fp32, per element
+A_BITS, W_BITS = 4, 4
+
+
+# ------------------------------------------------------------------------------------------
+def resnet50_layers():
+    """(name, activation C,H,W per image, weight shape) of the 54 quantised layers of torchvision
+    resnet50 at 224x224 (10 664 448 activation and 25 502 912 weight elements)."""
+    layers = [("conv1", (3, 224, 224), (64, 3, 7, 7))]
+    cin, hw = 64, 56
+    for li, (planes, blocks, stride) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)], 1):
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            pre = f"layer{li}.{b}"
+            layers.append((pre + ".conv1", (cin, hw, hw), (planes, cin, 1, 1)))
+            layers.append((pre + ".conv2", (planes, hw, hw), (planes, planes, 3, 3)))
+            layers.append((pre + ".conv3", (planes, hw // s, hw // s), (planes * 4, planes, 1, 1)))
+            if b == 0:
+                layers.append((pre + ".downsample.0", (cin, hw, hw), (planes * 4, cin, 1, 1)))
+            cin, hw = planes * 4, hw // s
+    layers.append(("fc", (2048,), (1000, 2048)))
+    assert len(layers) == 54
+    assert sum(math.prod(a) for _, a, _ in layers) == 10664448
+    assert sum(math.prod(w) for _, _, w in layers) == 25502912
+    return layers
+
+
+def qrange(signed, bits):
+    return (-(2 ** (bits - 1) - 1), 2 ** (bits - 1) - 1) if signed else (0, 2 ** bits - 1)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = torch.cuda.get_device_properties(device_index).uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if self.h is None:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------
+class Workload:
+    """Device-resident tensors + prebuilt C-ABI argument lists + CUDA graphs for one rank."""
+
+    def __init__(self, batch, device, seed):
+        from dlmc_quant_b200 import _lib
+        from dlmc_quant_b200 import functional as F
+        self.lib, self.F, self.h = _lib, F, _lib.lib()
+        self.device, self.batch = device, batch
+        self.layers = resnet50_layers()
+        gen = torch.Generator(device=device).manual_seed(seed)
+        ilo, ihi = qrange(False, A_BITS)
+        wlo, whi = qrange(True, W_BITS)
+        self.acts, self.wts = [], []
+        n_layers = len(self.layers)
+        wch = sum(w[0] for _, _, w in self.layers)
+        # every quantizer's scale gradient lands in ONE flat buffer: a single all-reduce per step
+        self.dscale = torch.zeros(n_layers + wch, dtype=torch.float32, device=device)
+        ch_off = n_layers
+        for i, (name, ashape, wshape) in enumerate(self.layers):
+            x = torch.randn((batch,) + ashape, generator=gen, device=device)
+            if i > 0:
+                x = torch.relu(x) * 2                 # post-ReLU-like, ~50 % zeros
+            dy = torch.randn(x.shape, generator=gen, device=device)
+            stats = F.obs_stats(x)
+            scale, off = F.minmax_from_stats(stats, A_BITS, False)
+            n = x.numel()
+            lay = _lib.Layout(1, 1, n, _lib.F32)
+            qp = _lib.QParams(_lib.FORM_AFFINE, ilo, ihi, 1 / math.sqrt(n * ihi), scale.data_ptr(), off.data_ptr())
+            self.acts.append(dict(x=x, dy=dy, y=torch.empty_like(x), dx=torch.empty_like(x), scale=scale, off=off,
+                                  lay=lay, qp=qp, n=n, ds=self.dscale[i:i + 1]))
+            w = torch.randn(wshape, generator=gen, device=device) * 0.02
+            dw = torch.randn(wshape, generator=gen, device=device)
+            wstats = F.obs_stats(w, ch_axis=0)
+            wscale, _ = F.minmax_from_stats(wstats, W_BITS, True)
+            c, k = wshape[0], math.prod(wshape[1:])
+            self.wts.append(dict(x=w, dy=dw, y=torch.empty_like(w), dx=torch.empty_like(w), scale=wscale, offset=None,
+                                 dscale=self.dscale[ch_off:ch_off + c], channels=c, inner=k, form=_lib.FORM_AFFINE,
+                                 lo=wlo, hi=whi, g=1 / math.sqrt(c * k * whi)))
+            ch_off += c
+        self.act_elems = sum(a["n"] for a in self.acts)
+        self.wt_elems = sum(w["x"].numel() for w in self.wts)
+        self.elems = self.act_elems + self.wt_elems
+        self.ws = torch.zeros(self.h.dlmcq_workspace_bytes(None), dtype=torch.uint8, device=device)
+        self.grp_f, self.grp_b = F.GroupedFakeQuant(device), F.GroupedFakeQuant(device)
+        self.wf = [dict(w) for w in self.wts]
+        self.wb = [dict(w, y=w["dx"]) for w in self.wts]
+        self.launches_per_step = 2 * len(self.acts) + 1 + 2
+
+    # -- eager launches (also what gets captured) ------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def fwd_acts(self):
+        st, f = self._stream(), self.h.dlmcq_fq_forward
+        for a in self.acts:
+            self.lib.check(f(a["x"].data_ptr(), a["y"].data_ptr(), None, C.byref(a["lay"]), C.byref(a["qp"]), st))
+
+    def bwd_acts(self):
+        st, f, ws, n = self._stream(), self.h.dlmcq_fq_backward, self.ws.data_ptr(), self.ws.numel()
+        for a in self.acts:
+            self.lib.check(f(a["x"].data_ptr(), a["dy"].data_ptr(), a["dx"].data_ptr(), a["ds"].data_ptr(), None,
+                             C.byref(a["lay"]), C.byref(a["qp"]), ws, n, st))
+
+    def weights(self):
+        self.grp_f.forward(self.wf)
+        self.grp_b.backward(self.wb)
+
+    def capture(self):
+        """Three CUDA graphs per step so that plain events between them can time the kernel groups."""
+        self.fwd_acts(); self.bwd_acts(); self.weights()          # warm: tables, lazy module load
+        torch.cuda.synchronize()
+        self.g_fwd, self.g_bwd, self.g_wt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            self.fwd_acts()
+        with torch.cuda.graph(self.g_bwd):
+            self.bwd_acts()
+        with torch.cuda.graph(self.g_wt):
+            self.weights()
+        torch.cuda.synchronize()
+
+
+def run_ours(args, rank, world, device):
+    import torch.distributed as dist
+    wl = Workload(args.batch, device, 2333 + rank)         # the reference's seed, per-rank offset
+    wl.capture()
+
+    def step(ev=None):
+        wl.g_fwd.replay()
+        if ev:
+            ev[0].record()
+        wl.g_bwd.replay()
+        if ev:
+            ev[1].record()
+        wl.g_wt.replay()
+        if world > 1:   # the path's one real exchange: scale gradients, one flat SUM all-reduce (NVLink)
+            dist.all_reduce(wl.dscale)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    t0.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t1.record()
+    fence()
+    clocks = sampler.stop()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=device)
+    bwd_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bwd_ms, op=dist.ReduceOp.MAX)
+    ms, bwd_ms = float(ms), float(bwd_ms)
+    total_elems = wl.elems * world * args.steps
+    value = total_elems * (BYTES_FWD + BYTES_BWD) / (ms * 1e-3) / 1e9
+
+    # roofline of the dominant kernel: fq_bwd_flat<AFFINE,float>, 54 launches per step, 12 B/elem
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_kind = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    launches = len(wl.acts) * args.steps
+    avg_launch_s = bwd_ms * 1e-3 / launches
+    bytes_per_launch = BYTES_BWD * wl.act_elems / len(wl.acts)
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["fq_bwd_flat_dram_bytes_per_elem"] * wl.act_elems / len(wl.acts)
+    except Exception:
+        pass
+    roofline = {"kernel": "fq_bwd_flat<AFFINE,f32>", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "bytes_per_launch": bytes_per_launch, "avg_launch_us": round(avg_launch_s * 1e6, 2),
+                "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
+
+    e2e = run_e2e(args, wl, rank, world, device)
+    out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "resnet50_w4a4_qat_quantizers (54 layers: A4 per-tensor act + W4 per-channel weight, "
+                                  "QBase form, fwd+bwd)", "per_gpu_batch": args.batch, "image": "3x224x224",
+                      "elements_per_step_per_gpu": wl.elems, "l2": "working set %.1f GB per GPU, far larger than the "
+                      "126 MB L2; no flush needed" % (wl.act_elems * 16 / 1e9), "cuda_graphs": True,
+                      "collective": "all_reduce(SUM) of %d scale-grad floats per step" % wl.dscale.numel() if world > 1
+                      else "none (1 GPU)"},
+           "elements_per_s": round(total_elems / (ms * 1e-3), 1),
+           "images_per_s_quantizer_path": round(args.batch * world * args.steps / (ms * 1e-3), 1),
+           "gpu_launches": wl.launches_per_step * args.steps, "roofline": roofline, "clocks": clocks, "e2e": e2e}
+    if rank == 0:
+        out["cpu_baseline"] = cpu_reference(sample_batch=1, passes=3) if world == 1 else None
+        print(json.dumps(out), flush=True)
+
+
+def run_e2e(args, wl, rank, world, device):
+    """Same workload through the host-buffer C-ABI call: pinned host x, dy in; y, dx, dscale out."""
+    import torch.distributed as dist
+    if args.no_e2e:
+        return None
+    F, lib = wl.F, wl.lib
+    steps = max(1, min(args.steps, args.e2e_steps))
+    hq = F.HostFakeQuant(device, chunk_elems=1 << 22)
+    host = []
+    for a in wl.acts:       # one pinned buffer set per layer; contents copied from the device tensors
+        hx, hdy = a["x"].cpu().pin_memory(), a["dy"].cpu().pin_memory()
+        host.append((hx, hdy, torch.empty_like(hx).pin_memory(), torch.empty_like(hx).pin_memory(),
+                     float(a["scale"]), float(a["off"]), a["qp"].lo, a["qp"].hi, a["qp"].g))
+    hw = [(w["x"].cpu().pin_memory(), w["dy"].cpu().pin_memory(), torch.empty_like(w["x"], device="cpu").pin_memory(),
+           torch.empty_like(w["x"], device="cpu").pin_memory()) for w in wl.wts]
+    hds = torch.empty(wl.dscale.numel(), dtype=torch.float32).pin_memory()
+
+    def step():
+        for i, (hx, hdy, hy, hdx, s, o, lo, hi, g) in enumerate(host):
+            hds[i] = hq.forward_backward(hx, hdy, hy, hdx, s, o, lo, hi, form=lib.FORM_AFFINE, g=g)
+        for w, (hx, hdy, hy, hdx) in zip(wl.wts, hw):
+            w["x"].copy_(hx, non_blocking=True)
+            w["dy"].copy_(hdy, non_blocking=True)
+        wl.weights()
+        for w, (hx, hdy, hy, hdx) in zip(wl.wts, hw):
+            hy.copy_(w["y"], non_blocking=True)
+            hdx.copy_(w["dx"], non_blocking=True)
+        hds[len(host):].copy_(wl.dscale[len(host):], non_blocking=True)
+        torch.cuda.synchronize()
+
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=device)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt)
+    h2d = 2 * 4 * wl.elems
+    d2h = 2 * 4 * wl.elems + 4 * wl.dscale.numel()
+    return {"value": round(wl.elems * world * steps * (BYTES_FWD + BYTES_BWD) / dt / 1e9, 2), "unit": UNIT,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "ms_per_step": round(dt / steps * 1e3, 2),
+            "api": "dlmcq_host_fq_forward_backward (activations) + H2D/grouped launch/D2H (weights)"}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference(sample_batch=1, passes=3):
+    """The oracle port (= the reference's eager PyTorch chain, restated op for op) on the host
+    cores: every layer's activation + per-channel weight fake-quant fwd+bwd at `sample_batch`."""
+    from oracle import restate as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(2333)
+    ilo, ihi = qrange(False, A_BITS)
+    wlo, whi = qrange(True, W_BITS)
+    data, elems = [], 0
+    for i, (name, ashape, wshape) in enumerate(resnet50_layers()):
+        x = torch.randn((sample_batch,) + ashape, generator=gen)
+        if i > 0:
+            x = torch.relu(x) * 2
+        dy = torch.randn(x.shape, generator=gen)
+        s, o = R.obs_minmax_tensor(x, A_BITS, False)
+        w = torch.randn(wshape, generator=gen) * 0.02
+        dw = torch.randn(wshape, generator=gen)
+        ws, wo = R.obs_minmax_channel(w, W_BITS, True, ch_axis=0)
+        data.append((x, dy, s.reshape(1), o.reshape(1), w, dw, ws, wo))
+        elems += x.numel() + w.numel()
+    best = float("inf")
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        for x, dy, s, o, w, dw, ws, wo in data:
+            R.fq_affine_fwd_bwd(x, s, o, ilo, ihi, R.lsq_g(x.numel(), ihi), dy)
+            R.fq_affine_fwd_bwd(w, ws, wo, wlo, whi, R.lsq_g(w.numel(), whi), dw)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": round(elems * (BYTES_FWD + BYTES_BWD) / best / 1e9, 3), "unit": UNIT, "cores": cores,
+            "threads": torch.get_num_threads(), "kind": "port",
+            "sample": f"all 54 layers (act + per-channel weight) at batch {sample_batch}: {elems} elements, "
+                      f"best of {passes} passes, torch {torch.__version__} CPU eager + autograd",
+            "elements_per_s": round(elems / best, 1), "seconds_per_pass": round(best, 3)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference
+    itself is pure Python and /root/reference does not exist on the GPU box)."""
+    if rank != 0:
+        return
+    from oracle import restate as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(2333)
+    ilo, ihi = qrange(False, A_BITS)
+    wlo, whi = qrange(True, W_BITS)
+    sb = args.ref_batch
+    data, elems = [], 0
+    for i, (name, ashape, wshape) in enumerate(resnet50_layers()):
+        x = torch.randn((sb,) + ashape, generator=gen)
+        if i > 0:
+            x = torch.relu(x) * 2
+        s, o = R.obs_minmax_tensor(x, A_BITS, False)
+        w = torch.randn(wshape, generator=gen) * 0.02
+        ws, wo = R.obs_minmax_channel(w, W_BITS, True, ch_axis=0)
+        data.append((x, torch.randn(x.shape, generator=gen), s.reshape(1), o.reshape(1), w,
+                     torch.randn(wshape, generator=gen), ws, wo))
+        elems += x.numel() + w.numel()
+
+    def step():
+        for x, dy, s, o, w, dw, ws, wo in data:
+            R.fq_affine_fwd_bwd(x, s, o, ilo, ihi, R.lsq_g(x.numel(), ihi), dy)
+            R.fq_affine_fwd_bwd(w, ws, wo, wlo, whi, R.lsq_g(w.numel(), whi), dw)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = round(elems * args.steps * (BYTES_FWD + BYTES_BWD) / dt / 1e9, 3)
+    sample = (f"each step = all 54 layers (act + per-channel weight) at batch {sb} ({elems} elements), "
+              f"{cores} host threads, torch {torch.__version__} CPU eager + autograd")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "resnet50_w4a4_qat_quantizers (54 layers: A4 per-tensor act + W4 per-channel weight, "
+                               "QBase form, fwd+bwd)", "per_gpu_batch": args.batch, "image": "3x224x224",
+                   "sample_batch_per_step": sb},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch of 3x224x224 images")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - this path has no CPU fallback (use --impl reference for the CPU arm)")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    try:
+        run_ours(args, rank, world, device)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,99 @@
+"""ctypes binding of libdlmcq.so (the C ABI declared in include/dlmcq.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or fails to load, every
+product entry point raises.  A CPU path would void the parity claims of this repo."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdlmcq.so")
+
+F32, BF16 = 0, 1
+FORM_A1, FORM_AFFINE, FORM_ZP, FORM_SYM = 0, 1, 2, 3
+STATS_PER_CHANNEL = 4
+SWEEP_CANDIDATES = 80
+ROOTQ_STATE_FLOATS = 8
+
+
+class Layout(C.Structure):
+    _fields_ = [("outer", C.c_int64), ("channels", C.c_int64), ("inner", C.c_int64), ("dtype", C.c_int32)]
+
+
+class QParams(C.Structure):
+    _fields_ = [("form", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32), ("g", C.c_float),
+                ("scale", C.c_void_p), ("offset", C.c_void_p)]
+
+
+class GroupItem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("scale", C.c_void_p),
+                ("offset", C.c_void_p), ("dscale", C.c_void_p), ("channels", C.c_int64), ("inner", C.c_int64),
+                ("form", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32), ("g", C.c_float)]
+
+
+class DlmcqError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_P, _I, _L, _F, _D, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+_LP, _QP = C.POINTER(Layout), C.POINTER(QParams)
+
+# name -> (restype, argtypes); mirrors include/dlmcq.h one to one
+SIGNATURES = {
+    "dlmcq_version": (_I, []),
+    "dlmcq_status_string": (C.c_char_p, [_I]),
+    "dlmcq_last_cuda_error": (C.c_char_p, []),
+    "dlmcq_workspace_bytes": (_Z, [_LP]),
+    "dlmcq_fq_forward": (_I, [_P, _P, _P, _LP, _QP, _P]),
+    "dlmcq_fq_backward": (_I, [_P, _P, _P, _P, _P, _LP, _QP, _P, _Z, _P]),
+    "dlmcq_dequantize": (_I, [_P, _P, _LP, _P, _P, _P]),
+    "dlmcq_adaround_forward": (_I, [_P, _P, _P, _LP, _P, _I, _I, _I, _P]),
+    "dlmcq_adaround_backward": (_I, [_P, _P, _P, _P, _P, _LP, _P, _I, _I, _P, _Z, _P]),
+    "dlmcq_adaround_init_alpha": (_I, [_P, _P, _LP, _P, _P]),
+    "dlmcq_rootq_act_prepare": (_I, [_P, _P, _D, _D, _I, _I, _I, _P, _P]),
+    "dlmcq_rootq_act_forward": (_I, [_P, _P, _L, _I, _P, _P]),
+    "dlmcq_rootq_act_backward": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _Z, _P]),
+    "dlmcq_rootq_wt_prepare": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _I, _I, _P, _P]),
+    "dlmcq_rootq_wt_forward": (_I, [_P, _P, _L, _I, _P, _P]),
+    "dlmcq_rootq_wt_backward": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _Z, _P]),
+    "dlmcq_obs_stats": (_I, [_P, _P, _LP, _P, _Z, _P]),
+    "dlmcq_obs_minmax_finalize": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
+    "dlmcq_obs_absmean_finalize": (_I, [_P, _P, _L, _D, _D, _D, _I, _P]),
+    "dlmcq_obs_sweep_tensor_sse": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _Z, _P]),
+    "dlmcq_obs_sweep_tensor_finalize": (_I, [_P, _P, _D, _I, _I, _P, _P, _P, _P]),
+    "dlmcq_obs_sweep_channel": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P]),
+    "dlmcq_obs_l2norm_step": (_I, [_P, _L, _L, _I, _P, _P, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "dlmcq_fq_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
+    "dlmcq_fq_backward_grouped": (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),
+    "dlmcq_host_staging_bytes": (_Z, [_L, _I]),
+    "dlmcq_host_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
+}
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DlmcqError(
+            f"{LIB_PATH} not found: build it with `python -m dlmc_quant_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback for this path.")
+    h = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)          # AttributeError here = header and library disagree
+        fn.restype, fn.argtypes = res, args
+    if h.dlmcq_version() != 100:
+        raise DlmcqError("libdlmcq.so version mismatch")
+    _lib = h
+    return h
+
+
+def check(status):
+    if status != 0:
+        h = lib()
+        msg = h.dlmcq_status_string(status).decode()
+        if status == -4:
+            msg += ": " + h.dlmcq_last_cuda_error().decode()
+        raise DlmcqError(f"libdlmcq: {msg} (status {status})")

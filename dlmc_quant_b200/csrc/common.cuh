@@ -1,0 +1,204 @@
+// common.cuh - shared device helpers for libdlmcq (sm_100a only).
+//
+// Everything on this path is HBM-bound element-wise / reduction work: the helpers here are
+// 128-bit vector access, dtype conversion, warp/block reductions and the "last block
+// finalises" pattern that keeps scale-gradient reductions deterministic without a second
+// launch.  Compiled with -fmad=false: the reference's chains are sequences of separately
+// rounded fp32 ops, so no multiply-add may be contracted unless written as fmaf() explicitly.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dlmcq.h"
+
+namespace dlmcq {
+
+constexpr int kThreads = 256;          // threads per CTA for the streaming kernels
+constexpr int kNumSmFallback = 148;    // B200
+constexpr int kMaxPartialBlocks = 2048;
+constexpr int kRowWarps = 8;           // warps per CTA in the warp-per-row kernels
+
+int num_sms();
+int set_cuda_error(cudaError_t e);
+#define DLMCQ_LAUNCH_CHECK()                                   \
+  do {                                                         \
+    cudaError_t e__ = cudaGetLastError();                      \
+    if (e__ != cudaSuccess) return ::dlmcq::set_cuda_error(e__); \
+  } while (0)
+
+// ---- dtype traits: 16-byte vectors -----------------------------------------------------
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  using raw = float4;
+  __device__ static __forceinline__ void unpack(const raw& r, float (&f)[4]) {
+    f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w;
+  }
+  __device__ static __forceinline__ raw pack(const float (&f)[4]) { return make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  using raw = uint4;
+  __device__ static __forceinline__ void unpack(const raw& r, float (&f)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // bf16 -> fp32 is a 16-bit shift, exact
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ raw pack(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);   // RNE, one rounding
+      w[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Streaming 128-bit access.  Inputs are read exactly once (no reuse inside the kernel):
+// bypass L1 allocation; outputs are written once: no-allocate in L1 as well.  L2 policy is
+// left at default so that a consumer kernel (the conv) can still hit the fake-quantised
+// tensor in the 126 MB L2.
+template <typename R>
+__device__ __forceinline__ R ld_stream(const R* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return *reinterpret_cast<R*>(&v);
+}
+template <typename R>
+__device__ __forceinline__ void st_stream(R* p, const R& r) {
+  const uint4 v = *reinterpret_cast<const uint4*>(&r);
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- reductions ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of NQ quantities; result valid in thread 0.  Fixed order -> deterministic.
+template <int NQ>
+__device__ __forceinline__ void block_sum(float (&v)[NQ], float* smem /* >= NQ*32 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();   // protect smem reuse across calls
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) smem[q * 32 + warp] = v[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float t = lane < nwarp ? smem[q * 32 + lane] : 0.f;
+      v[q] = warp_sum(t);
+    }
+  }
+}
+
+// "Last block finalises": every block publishes its partials, takes a ticket, and the block
+// that draws the last ticket reduces all partials in a fixed order.  The ticket counter is
+// reset by that block, so a workspace that was zeroed once stays reusable.
+__device__ __forceinline__ bool take_last_ticket(unsigned int* counter, unsigned int nblocks) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// Workspace layout: [0,256) bytes = ticket counters, then float partials.
+constexpr size_t kWsHeaderBytes = 256;
+__host__ __device__ inline float* ws_partials(void* ws) {
+  return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsHeaderBytes);
+}
+__host__ __device__ inline unsigned int* ws_counter(void* ws, int i = 0) {
+  return reinterpret_cast<unsigned int*>(ws) + i;
+}
+
+// Per-channel layouts are processed as rows = outer*channels of length `inner`, each row cut
+// into `segs` segments of `seg` elements; one warp owns one (row, segment) work item.
+struct RowGeom {
+  int64_t rows;
+  int64_t channels;
+  int64_t inner;
+  int64_t segs;   // segments per row
+  int64_t seg;    // elements per segment (multiple of 512 -> 16-byte aligned cuts)
+};
+constexpr int64_t kRowSegMin = 4096;
+constexpr int64_t kRowItemsTarget = 32768;
+inline RowGeom make_geom(int64_t outer, int64_t channels, int64_t inner) {
+  RowGeom gm;
+  gm.rows = outer * channels;
+  gm.channels = channels;
+  gm.inner = inner;
+  int64_t segs = (inner + kRowSegMin - 1) / kRowSegMin;
+  int64_t cap = kRowItemsTarget / (gm.rows > 0 ? gm.rows : 1);
+  if (cap < 1) cap = 1;
+  if (segs > cap) segs = cap;
+  if (segs < 1) segs = 1;
+  int64_t seg = (inner + segs - 1) / segs;
+  seg = (seg + 511) / 512 * 512;
+  if (seg < 512) seg = 512;
+  gm.seg = seg;
+  gm.segs = (inner + seg - 1) / seg;
+  if (gm.segs < 1) gm.segs = 1;
+  return gm;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Persistent grid for a streaming kernel over `work_items` block-tiles.
+inline int stream_grid(int64_t tiles, int blocks_per_sm) {
+  int64_t cap = static_cast<int64_t>(num_sms()) * blocks_per_sm;
+  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+  int64_t g = tiles < cap ? tiles : cap;
+  return g < 1 ? 1 : static_cast<int>(g);
+}
+
+}  // namespace dlmcq

@@ -1,0 +1,408 @@
+// fq_kernels.cu - fused fake-quant forward / backward kernels and their C-ABI entry points.
+//
+// Two kernel shapes cover every layout:
+//   * flat   (channels == 1): persistent grid of 148*k CTAs, each thread keeps UNROLL 128-bit
+//            loads in flight, one pass over HBM.  Backward also block-reduces the scale
+//            gradient and the last CTA to finish combines the partials (fixed order).
+//   * rows   (per-channel): the tensor is rows = outer*channels of length `inner`; one warp
+//            owns one row segment (<= kRowSeg elements), so the channel's qparams are loaded
+//            once per warp and the per-channel scale gradient is a warp-shuffle reduction.
+// Roofline: HBM.  Algorithmic bytes: forward 2*sizeof(T), backward 3*sizeof(T) per element.
+#include "fq_rows.cuh"
+
+namespace dlmcq {
+
+constexpr int kUnroll = 4;
+
+// ---------------------------------------------------------------------------------------
+// flat forward
+// ---------------------------------------------------------------------------------------
+template <int FORM, typename T>
+__global__ void __launch_bounds__(kThreads, 4)
+fq_fwd_flat(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, int64_t n,
+            const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  const ChanParams p = make_params<FORM>(scale, offset, 0, g);
+  const int64_t nvec = n / V::N;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const raw* xv = reinterpret_cast<const raw*>(x);
+  raw* yv = reinterpret_cast<raw*>(y);
+  raw* cv = reinterpret_cast<raw*>(codes);
+
+  auto body = [&](const raw& r, int64_t idx) {
+    float f[V::N], fy[V::N], fc[V::N];
+    V::unpack(r, f);
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) fq_elem<FORM>(f[e], p, lo, hi, fc[e], fy[e]);
+    if (y) st_stream(yv + idx, V::pack(fy));
+    if (codes) st_stream(cv + idx, V::pack(fc));
+  };
+  for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
+    raw r[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) r[k] = ld_stream(xv + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) body(r[k], i + k * stride);
+  }
+  for (; i < nvec; i += stride) body(ld_stream(xv + i), i);
+  // ragged tail (< one vector)
+  if (blockIdx.x == 0) {
+    const int64_t t = nvec * V::N + threadIdx.x;
+    if (t < n) {
+      float c, v;
+      fq_elem<FORM>(to_f32<T>(x[t]), p, lo, hi, c, v);
+      if (y) y[t] = from_f32<T>(v);
+      if (codes) codes[t] = from_f32<T>(c);
+    }
+  }
+}
+
+// scalar-access variant for pointers that are not 16-byte aligned (tensor views)
+template <int FORM, typename T>
+__global__ void __launch_bounds__(kThreads)
+fq_fwd_flat_unaligned(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, int64_t n,
+                      const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
+  const ChanParams p = make_params<FORM>(scale, offset, 0, g);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float c, v;
+    fq_elem<FORM>(to_f32<T>(x[i]), p, lo, hi, c, v);
+    if (y) y[i] = from_f32<T>(v);
+    if (codes) codes[i] = from_f32<T>(c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// flat backward: dx + reduced dscale (+ doffset)
+// ---------------------------------------------------------------------------------------
+template <int FORM>
+__device__ __forceinline__ void finalize_flat(float* partials, int nblocks, float g, float* dscale, float* doffset,
+                                              float* smem) {
+  // fixed-order combination of the block partials in double
+  double s = 0.0, o = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    s += static_cast<double>(partials[2 * b]);
+    o += static_cast<double>(partials[2 * b + 1]);
+  }
+  s = warp_sum(s);
+  o = warp_sum(o);
+  double* sm = reinterpret_cast<double*>(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) { sm[warp] = s; sm[32 + warp] = o; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, to = 0.0;
+    for (int w = 0; w < nwarp; ++w) { ts += sm[w]; to += sm[32 + w]; }
+    float r = static_cast<float>(ts);
+    // AFFINE: chain through grad_scale (utils.py:24-27) multiplies by g; A1: FunLSQ's "* g"
+    if (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) r = r * g;
+    dscale[0] = r;
+    if (doffset) doffset[0] = static_cast<float>(to);
+  }
+}
+
+template <int FORM, typename T, bool VECTOR>
+__global__ void __launch_bounds__(kThreads, 4)
+fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t n,
+            const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi,
+            float* __restrict__ dscale, float* __restrict__ doffset, void* ws) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  __shared__ __align__(16) float smem[128];
+  const ChanParams p = make_params<FORM>(scale, offset, 0, g);
+  float acc[2] = {0.f, 0.f};
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (VECTOR) {
+    const int64_t nvec = n / V::N;
+    const raw* xv = reinterpret_cast<const raw*>(x);
+    const raw* gv = reinterpret_cast<const raw*>(dy);
+    raw* ov = reinterpret_cast<raw*>(dx);
+    auto body = [&](const raw& rx, const raw& rg, int64_t idx) {
+      float fx[V::N], fg[V::N], fo[V::N];
+      V::unpack(rx, fx);
+      V::unpack(rg, fg);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) fo[e] = fq_elem_bwd<FORM>(fx[e], fg[e], p, lo, hi, acc[0], acc[1]);
+      st_stream(ov + idx, V::pack(fo));
+    };
+    for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
+      raw rx[kUnroll], rg[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        rx[k] = ld_stream(xv + i + k * stride);
+        rg[k] = ld_stream(gv + i + k * stride);
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) body(rx[k], rg[k], i + k * stride);
+    }
+    for (; i < nvec; i += stride) body(ld_stream(xv + i), ld_stream(gv + i), i);
+    if (blockIdx.x == 0) {
+      const int64_t t = nvec * V::N + threadIdx.x;
+      if (t < n) dx[t] = from_f32<T>(fq_elem_bwd<FORM>(to_f32<T>(x[t]), to_f32<T>(dy[t]), p, lo, hi, acc[0], acc[1]));
+    }
+  } else {
+    for (; i < n; i += stride)
+      dx[i] = from_f32<T>(fq_elem_bwd<FORM>(to_f32<T>(x[i]), to_f32<T>(dy[i]), p, lo, hi, acc[0], acc[1]));
+  }
+  block_sum<2>(acc, smem);
+  float* partials = ws_partials(ws);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = acc[0];
+    partials[2 * blockIdx.x + 1] = acc[1];
+  }
+  if (take_last_ticket(ws_counter(ws), gridDim.x)) {
+    finalize_flat<FORM>(partials, gridDim.x, g, dscale, doffset, smem);
+    if (threadIdx.x == 0) *ws_counter(ws) = 0u;   // leave the workspace reusable
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// row kernels (per-channel qparams): one warp per row segment
+// ---------------------------------------------------------------------------------------
+template <int FORM, typename T>
+__global__ void __launch_bounds__(kRowWarps * 32)
+fq_fwd_rows(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, RowGeom gm,
+            const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (item >= gm.rows * gm.segs) return;
+  const int64_t row = item / gm.segs, seg = item - row * gm.segs;
+  const ChanParams p = make_params<FORM>(scale, offset, row % gm.channels, g);
+  const int64_t beg = seg * gm.seg;
+  const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
+  const int64_t base = row * gm.inner + beg;
+  fwd_row_segment<FORM, T>(x + base, y ? y + base : nullptr, codes ? codes + base : nullptr, len, p, lo, hi, lane);
+}
+
+// Backward rows: writes dx; per-(row,segment) partials go to `part` (2 floats each) unless the
+// geometry has a single partial per channel, in which case dscale is written directly.
+template <int FORM, typename T>
+__global__ void __launch_bounds__(kRowWarps * 32)
+fq_bwd_rows(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, RowGeom gm,
+            const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi,
+            float* __restrict__ dscale, float* __restrict__ doffset, float* __restrict__ part, int direct) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (item >= gm.rows * gm.segs) return;
+  const int64_t row = item / gm.segs, seg = item - row * gm.segs;
+  const int64_t ch = row % gm.channels;
+  const ChanParams p = make_params<FORM>(scale, offset, ch, g);
+  const int64_t beg = seg * gm.seg;
+  const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
+  const int64_t base = row * gm.inner + beg;
+  float as = 0.f, ao = 0.f;
+  bwd_row_segment<FORM, T>(x + base, dy + base, dx + base, len, p, lo, hi, lane, as, ao);
+  if (lane == 0) {
+    if (direct) {
+      dscale[ch] = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? as * g : as;
+      if (doffset) doffset[ch] = ao;
+    } else {
+      part[2 * item] = as;
+      part[2 * item + 1] = ao;
+    }
+  }
+}
+
+// one warp per channel: sum the partials of (outer, segs) in a fixed order
+__global__ void __launch_bounds__(kRowWarps * 32)
+rows_finalize(const float* __restrict__ part, RowGeom gm, int64_t outer, float gmul,
+              float* __restrict__ dscale, float* __restrict__ doffset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ch = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (ch >= gm.channels) return;
+  double s = 0.0, o = 0.0;
+  const int64_t per = outer * gm.segs;
+  for (int64_t k = lane; k < per; k += 32) {
+    const int64_t b = k / gm.segs, sg = k - b * gm.segs;
+    const int64_t item = (b * gm.channels + ch) * gm.segs + sg;
+    s += static_cast<double>(part[2 * item]);
+    o += static_cast<double>(part[2 * item + 1]);
+  }
+  s = warp_sum(s);
+  o = warp_sum(o);
+  if (lane == 0) {
+    dscale[ch] = static_cast<float>(s) * gmul;
+    if (doffset) doffset[ch] = static_cast<float>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// dequantize (utils.py:5-6)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+dequant_kernel(const T* __restrict__ codes, T* __restrict__ y, int64_t n, int64_t channels, int64_t inner,
+               const float* __restrict__ scale, const float* __restrict__ offset) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t ch = channels == 1 ? 0 : (i / inner) % channels;
+    const float s = __ldg(scale + ch), o = offset ? __ldg(offset + ch) : 0.f;
+    y[i] = from_f32<T>(to_f32<T>(codes[i]) * s + o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------
+static inline int check_layout(const dlmcq_layout* l) {
+  if (!l || l->outer < 1 || l->channels < 1 || l->inner < 0) return DLMCQ_EINVAL;
+  if (l->dtype != DLMCQ_F32 && l->dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
+  return DLMCQ_OK;
+}
+static inline size_t elem_size(int dtype) { return dtype == DLMCQ_F32 ? 4 : 2; }
+static inline bool elem_aligned(const void* p, int dtype) {
+  return p == nullptr || (reinterpret_cast<uintptr_t>(p) % elem_size(dtype)) == 0;
+}
+static inline RowGeom make_geom(const dlmcq_layout* l) { return make_geom(l->outer, l->channels, l->inner); }
+
+template <int FORM, typename T>
+static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l, const dlmcq_qparams* qp,
+                      cudaStream_t st) {
+  const int64_t n = l->outer * l->channels * l->inner;
+  if (n == 0) return DLMCQ_OK;
+  const float lo = static_cast<float>(qp->lo), hi = static_cast<float>(qp->hi);
+  if (l->channels == 1) {
+    if (aligned16(x) && aligned16(y) && aligned16(codes)) {
+      const int64_t tiles = (n / Vec<T>::N + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+      fq_fwd_flat<FORM, T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
+          static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale, qp->offset, qp->g, lo, hi);
+    } else {
+      const int64_t tiles = (n + kThreads - 1) / kThreads;
+      fq_fwd_flat_unaligned<FORM, T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
+          static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale, qp->offset, qp->g, lo, hi);
+    }
+  } else {
+    const RowGeom gm = make_geom(l);
+    const int64_t items = gm.rows * gm.segs;
+    const int64_t blocks = (items + kRowWarps - 1) / kRowWarps;
+    if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+    fq_fwd_rows<FORM, T><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), gm, qp->scale, qp->offset, qp->g, lo, hi);
+  }
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+template <int FORM, typename T>
+static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, float* doffset, const dlmcq_layout* l,
+                      const dlmcq_qparams* qp, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = l->outer * l->channels * l->inner;
+  const float lo = static_cast<float>(qp->lo), hi = static_cast<float>(qp->hi);
+  if (ws_bytes < dlmcq_workspace_bytes(l)) return DLMCQ_EWORKSPACE;
+  if (l->channels == 1) {
+    const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx);
+    const int64_t per = vec ? Vec<T>::N : 1;
+    int64_t tiles = (n / per + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+    const int grid = stream_grid(tiles, 6);
+    if (vec)
+      fq_bwd_flat<FORM, T, true><<<grid, kThreads, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
+          static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi, dscale, doffset, ws);
+    else
+      fq_bwd_flat<FORM, T, false><<<grid, kThreads, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
+          static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi, dscale, doffset, ws);
+  } else {
+    const RowGeom gm = make_geom(l);
+    const int64_t items = gm.rows * gm.segs;
+    const int64_t blocks = (items + kRowWarps - 1) / kRowWarps;
+    if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+    const int direct = (l->outer == 1 && gm.segs == 1) ? 1 : 0;
+    if (n == 0) return DLMCQ_OK;
+    fq_bwd_rows<FORM, T><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), gm, qp->scale, qp->offset, qp->g,
+        lo, hi, dscale, doffset, ws_partials(ws), direct);
+    if (!direct) {
+      DLMCQ_LAUNCH_CHECK();
+      const float gmul = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? qp->g : 1.f;
+      const int64_t fb = (gm.channels + kRowWarps - 1) / kRowWarps;
+      rows_finalize<<<static_cast<unsigned>(fb), kRowWarps * 32, 0, st>>>(ws_partials(ws), gm, l->outer, gmul,
+                                                                          dscale, doffset);
+    }
+  }
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+template <typename T>
+static int dispatch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l, const dlmcq_qparams* qp,
+                        cudaStream_t st) {
+  switch (qp->form) {
+    case DLMCQ_FORM_A1: return launch_fwd<DLMCQ_FORM_A1, T>(x, y, codes, l, qp, st);
+    case DLMCQ_FORM_AFFINE: return launch_fwd<DLMCQ_FORM_AFFINE, T>(x, y, codes, l, qp, st);
+    case DLMCQ_FORM_ZP: return launch_fwd<DLMCQ_FORM_ZP, T>(x, y, codes, l, qp, st);
+    case DLMCQ_FORM_SYM: return launch_fwd<DLMCQ_FORM_SYM, T>(x, y, codes, l, qp, st);
+  }
+  return DLMCQ_EINVAL;
+}
+template <typename T>
+static int dispatch_bwd(const void* x, const void* dy, void* dx, float* ds, float* doff, const dlmcq_layout* l,
+                        const dlmcq_qparams* qp, void* ws, size_t wsb, cudaStream_t st) {
+  switch (qp->form) {
+    case DLMCQ_FORM_A1: return launch_bwd<DLMCQ_FORM_A1, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
+    case DLMCQ_FORM_AFFINE: return launch_bwd<DLMCQ_FORM_AFFINE, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
+    case DLMCQ_FORM_ZP: return launch_bwd<DLMCQ_FORM_ZP, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
+    case DLMCQ_FORM_SYM: return launch_bwd<DLMCQ_FORM_SYM, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
+  }
+  return DLMCQ_EINVAL;
+}
+
+}  // namespace dlmcq
+
+using namespace dlmcq;
+
+extern "C" size_t dlmcq_workspace_bytes(const dlmcq_layout* l) {
+  // header + flat partials (always; also covers the 80-candidate sweep) + per-(row,segment) partials
+  size_t bytes = kWsHeaderBytes + static_cast<size_t>(kMaxPartialBlocks) * 96 * sizeof(float);
+  if (l && l->outer >= 1 && l->channels >= 1 && l->inner >= 0) {
+    const RowGeom gm = make_geom(l->outer, l->channels, l->inner);
+    const size_t rows_bytes = static_cast<size_t>(gm.rows * gm.segs) * 4 * sizeof(float);
+    if (kWsHeaderBytes + rows_bytes > bytes) bytes = kWsHeaderBytes + rows_bytes;
+  }
+  return bytes;
+}
+
+extern "C" int dlmcq_fq_forward(const void* x, void* y, void* codes, const dlmcq_layout* layout,
+                                const dlmcq_qparams* qp, void* stream) {
+  if (int e = check_layout(layout)) return e;
+  if (!qp || !qp->scale || !x || (!y && !codes)) return DLMCQ_EINVAL;
+  if (!elem_aligned(x, layout->dtype) || !elem_aligned(y, layout->dtype) || !elem_aligned(codes, layout->dtype))
+    return DLMCQ_EALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return layout->dtype == DLMCQ_F32 ? dispatch_fwd<float>(x, y, codes, layout, qp, st)
+                                    : dispatch_fwd<__nv_bfloat16>(x, y, codes, layout, qp, st);
+}
+
+extern "C" int dlmcq_fq_backward(const void* x, const void* dy, void* dx, float* dscale, float* doffset,
+                                 const dlmcq_layout* layout, const dlmcq_qparams* qp, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (int e = check_layout(layout)) return e;
+  if (!qp || !qp->scale || !x || !dy || !dx || !dscale || !workspace) return DLMCQ_EINVAL;
+  if (!elem_aligned(x, layout->dtype) || !elem_aligned(dy, layout->dtype) || !elem_aligned(dx, layout->dtype))
+    return DLMCQ_EALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return layout->dtype == DLMCQ_F32
+             ? dispatch_bwd<float>(x, dy, dx, dscale, doffset, layout, qp, workspace, workspace_bytes, st)
+             : dispatch_bwd<__nv_bfloat16>(x, dy, dx, dscale, doffset, layout, qp, workspace, workspace_bytes, st);
+}
+
+extern "C" int dlmcq_dequantize(const void* codes, void* y, const dlmcq_layout* layout, const float* scale,
+                                const float* offset, void* stream) {
+  if (int e = check_layout(layout)) return e;
+  if (!codes || !y || !scale) return DLMCQ_EINVAL;
+  const int64_t n = layout->outer * layout->channels * layout->inner;
+  if (n == 0) return DLMCQ_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = stream_grid((n + kThreads - 1) / kThreads, 8);
+  if (layout->dtype == DLMCQ_F32)
+    dequant_kernel<float><<<grid, kThreads, 0, st>>>(static_cast<const float*>(codes), static_cast<float*>(y), n,
+                                                     layout->channels, layout->inner, scale, offset);
+  else
+    dequant_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(codes),
+                                                             static_cast<__nv_bfloat16*>(y), n, layout->channels,
+                                                             layout->inner, scale, offset);
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}

@@ -1,0 +1,444 @@
+"""Thin torch-facing wrappers over the C ABI (include/dlmcq.h).
+
+PyTorch is plumbing here: device memory, the current stream, autograd glue.  Every function
+extracts raw device pointers and the current CUDA stream and calls libdlmcq.so; nothing in
+this module computes on the CPU or falls back to eager torch ops."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (BF16, F32, FORM_A1, FORM_AFFINE, FORM_SYM, FORM_ZP, ROOTQ_STATE_FLOATS, STATS_PER_CHANNEL,
+                   SWEEP_CANDIDATES, DlmcqError, Layout, QParams)
+
+__all__ = ["fq_forward", "fq_backward", "dequantize", "obs_stats", "minmax_from_stats", "absmean_from_stats",
+           "sweep_tensor", "sweep_channel", "l2norm_fixed_point", "adaround_forward", "adaround_backward",
+           "adaround_init_alpha", "rootq_act_prepare", "rootq_act_forward", "rootq_act_backward", "rootq_wt_prepare",
+           "rootq_wt_forward", "rootq_wt_backward", "GroupedFakeQuant", "HostFakeQuant", "layout_of"]
+
+
+def _require_cuda(t, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise DlmcqError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise DlmcqError(f"unsupported dtype {t.dtype}: fp32 and bf16 only")
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def layout_of(t, ch_axis=None):
+    """[outer, channels, inner] view of a contiguous tensor (see include/dlmcq.h)."""
+    if ch_axis is None:
+        return Layout(1, 1, t.numel(), _dtype_code(t))
+    shape = list(t.shape)
+    ch_axis = ch_axis % len(shape)
+    return Layout(math.prod(shape[:ch_axis]), shape[ch_axis], math.prod(shape[ch_axis + 1:]), _dtype_code(t))
+
+
+def _qvec(v, channels, device, name):
+    """scale / offset as a float32 device vector of `channels` entries (no sync when already on device)."""
+    if v is None:
+        return None
+    if not isinstance(v, torch.Tensor):
+        v = torch.full((channels,), float(v), dtype=torch.float32, device=device)
+    if v.device != device or v.dtype != torch.float32:
+        v = v.to(device=device, dtype=torch.float32)
+    v = v.detach().reshape(-1)
+    if v.numel() == 1 and channels != 1:
+        v = v.expand(channels)
+    if v.numel() != channels:
+        raise DlmcqError(f"{name} has {v.numel()} entries, layout has {channels} channels")
+    return v.contiguous()
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Zero-initialised scratch, one per (device, stream); kernels leave it zeroed."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ws_for(t, lay):
+    n = _lib.lib().dlmcq_workspace_bytes(C.byref(lay))
+    return _workspace(t.device, n), n
+
+
+# --------------------------------------------------------------------------------------
+def fq_forward(x, scale, offset, lo, hi, form, g=0.0, ch_axis=None, want_codes=False, want_y=True):
+    """Fused fake-quant forward -> y (and/or the integer codes as a float tensor)."""
+    _require_cuda(x, "x")
+    x = x.detach().contiguous()
+    lay = layout_of(x, ch_axis)
+    s = _qvec(scale, lay.channels, x.device, "scale")
+    o = _qvec(offset, lay.channels, x.device, "offset")
+    y = torch.empty_like(x) if want_y else None
+    codes = torch.empty_like(x) if want_codes else None
+    qp = QParams(form, int(lo), int(hi), float(g), s.data_ptr(), o.data_ptr() if o is not None else None)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().dlmcq_fq_forward(_ptr(x), _ptr(y), _ptr(codes), C.byref(lay), C.byref(qp), _stream_ptr()))
+    if want_y and want_codes:
+        return y, codes
+    return y if want_y else codes
+
+
+def fq_backward(x, dy, scale, offset, lo, hi, form, g=0.0, ch_axis=None, want_doffset=False):
+    """Fused backward: one pass over (x, dy) -> dx, dscale[channels] (, doffset[channels])."""
+    _require_cuda(x, "x")
+    _require_cuda(dy, "dy")
+    x = x.detach().contiguous()
+    dy = dy.detach().contiguous()
+    if dy.dtype != x.dtype or dy.shape != x.shape:
+        raise DlmcqError("dy must match x in dtype and shape")
+    lay = layout_of(x, ch_axis)
+    s = _qvec(scale, lay.channels, x.device, "scale")
+    o = _qvec(offset, lay.channels, x.device, "offset")
+    dx = torch.empty_like(x)
+    ds = torch.empty(lay.channels, dtype=torch.float32, device=x.device)
+    do = torch.empty(lay.channels, dtype=torch.float32, device=x.device) if want_doffset else None
+    qp = QParams(form, int(lo), int(hi), float(g), s.data_ptr(), o.data_ptr() if o is not None else None)
+    with torch.cuda.device(x.device):
+        ws, n = _ws_for(x, lay)
+        _lib.check(_lib.lib().dlmcq_fq_backward(_ptr(x), _ptr(dy), _ptr(dx), _ptr(ds), _ptr(do), C.byref(lay),
+                                                C.byref(qp), _ptr(ws), n, _stream_ptr()))
+    return (dx, ds, do) if want_doffset else (dx, ds)
+
+
+def dequantize(codes, scale, offset, ch_axis=None):
+    _require_cuda(codes, "codes")
+    codes = codes.detach().contiguous()
+    lay = layout_of(codes, ch_axis)
+    s = _qvec(scale, lay.channels, codes.device, "scale")
+    o = _qvec(offset, lay.channels, codes.device, "offset")
+    y = torch.empty_like(codes)
+    with torch.cuda.device(codes.device):
+        _lib.check(_lib.lib().dlmcq_dequantize(_ptr(codes), _ptr(y), C.byref(lay), _ptr(s), _ptr(o), _stream_ptr()))
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# observers
+def obs_stats(x, ch_axis=None):
+    """One read of x -> float32 [channels, 4] = (min, max, max|x|, sum|x|)."""
+    _require_cuda(x, "x")
+    x = x.detach().contiguous()
+    lay = layout_of(x, ch_axis)
+    stats = torch.empty(lay.channels, STATS_PER_CHANNEL, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws, n = _ws_for(x, lay)
+        _lib.check(_lib.lib().dlmcq_obs_stats(_ptr(x), _ptr(stats), C.byref(lay), _ptr(ws), n, _stream_ptr()))
+    return stats
+
+
+def minmax_from_stats(stats, n_bits, signed, allow_offset=True):
+    ch = stats.shape[0]
+    scale = torch.empty(ch, dtype=torch.float32, device=stats.device)
+    offset = torch.empty(ch, dtype=torch.float32, device=stats.device)
+    with torch.cuda.device(stats.device):
+        _lib.check(_lib.lib().dlmcq_obs_minmax_finalize(_ptr(stats), _ptr(scale), _ptr(offset), ch, int(n_bits),
+                                                        int(bool(signed)), int(bool(allow_offset)), _stream_ptr()))
+    return scale, offset
+
+
+def absmean_from_stats(stats, count, mul_a, mul_b, mode):
+    ch = stats.shape[0]
+    out = torch.empty(ch, dtype=torch.float32, device=stats.device)
+    with torch.cuda.device(stats.device):
+        _lib.check(_lib.lib().dlmcq_obs_absmean_finalize(_ptr(stats), _ptr(out), ch, float(count), float(mul_a),
+                                                         float(mul_b), int(mode), _stream_ptr()))
+    return out
+
+
+def sweep_tensor_sse(x, stats, n_bits, allow_offset=True):
+    """80 squared-error sums of the per-tensor clip sweep (ops.py:52-61) in one read of x."""
+    x = x.detach().contiguous()
+    sse = torch.empty(SWEEP_CANDIDATES, dtype=torch.float32, device=x.device)
+    lay = layout_of(x)
+    with torch.cuda.device(x.device):
+        ws, n = _ws_for(x, lay)
+        _lib.check(_lib.lib().dlmcq_obs_sweep_tensor_sse(_ptr(x), x.numel(), _dtype_code(x), _ptr(stats), int(n_bits),
+                                                         int(bool(allow_offset)), _ptr(sse), _ptr(ws), n, _stream_ptr()))
+    return sse
+
+
+def sweep_tensor_pick(sse, stats, rows_for_mean, n_bits, allow_offset=True):
+    scale = torch.empty(1, dtype=torch.float32, device=sse.device)
+    offset = torch.empty(1, dtype=torch.float32, device=sse.device)
+    picked = torch.empty(1, dtype=torch.int32, device=sse.device)
+    with torch.cuda.device(sse.device):
+        _lib.check(_lib.lib().dlmcq_obs_sweep_tensor_finalize(_ptr(sse), _ptr(stats), float(rows_for_mean), int(n_bits),
+                                                              int(bool(allow_offset)), _ptr(scale), _ptr(offset),
+                                                              _ptr(picked), _stream_ptr()))
+    return scale, offset, picked
+
+
+def sweep_tensor(x, n_bits, allow_offset=True, reduce_stats=None, reduce_sse=None):
+    """ops.py:36-68 unsigned branch.  reduce_* are optional collectives for multi-GPU callers."""
+    _require_cuda(x, "x")
+    stats = obs_stats(x)
+    if reduce_stats is not None:
+        stats = reduce_stats(stats)
+    sse = sweep_tensor_sse(x, stats, n_bits, allow_offset)
+    rows = x.numel() / x.shape[1] if x.dim() >= 2 else 1.0
+    if reduce_sse is not None:
+        sse, rows = reduce_sse(sse, rows)
+    return sweep_tensor_pick(sse, stats, rows, n_bits, allow_offset)
+
+
+def sweep_channel(rows2d, n_bits, signed):
+    """ops.py:169-196 on a contiguous [channels, inner] matrix -> (scale[C], offset[C])."""
+    _require_cuda(rows2d, "tensor")
+    rows2d = rows2d.detach().contiguous()
+    ch, inner = rows2d.shape
+    scale = torch.empty(ch, dtype=torch.float32, device=rows2d.device)
+    offset = torch.empty(ch, dtype=torch.float32, device=rows2d.device)
+    with torch.cuda.device(rows2d.device):
+        _lib.check(_lib.lib().dlmcq_obs_sweep_channel(_ptr(rows2d), ch, inner, _dtype_code(rows2d), int(n_bits),
+                                                      int(bool(signed)), _ptr(scale), _ptr(offset), _stream_ptr()))
+    return scale, offset
+
+
+def l2norm_fixed_point(rows2d, scale, offset, lo, hi, max_iters=1000, poll_every=8):
+    """ops.py:71-83 / 198-215: iterate s <- sum(x q)/sum(q q + 1e-7) on device until the relative
+    change is <= 1e-5.  The loop runs on the device; the host only polls a flag every `poll_every`
+    launches.  `max_iters` bounds the search (the reference loops forever on some inputs)."""
+    _require_cuda(rows2d, "tensor")
+    rows2d = rows2d.detach().contiguous()
+    ch, inner = rows2d.shape
+    dev = rows2d.device
+    scale = _qvec(scale, ch, dev, "scale").clone()
+    offset = _qvec(offset, ch, dev, "offset")
+    diff = torch.zeros(1, dtype=torch.float32, device=dev)
+    flags = torch.zeros(2, dtype=torch.int32, device=dev)       # [done, iters]
+    lay = Layout(1, ch, inner, _dtype_code(rows2d))
+    h = _lib.lib()
+    with torch.cuda.device(dev):
+        ws, n = _ws_for(rows2d, lay)
+        it = 0
+        while it < max_iters:
+            for _ in range(min(poll_every, max_iters - it)):
+                _lib.check(h.dlmcq_obs_l2norm_step(_ptr(rows2d), ch, inner, lay.dtype, _ptr(scale), _ptr(offset),
+                                                   int(lo), int(hi), _ptr(diff), C.c_void_p(flags.data_ptr()),
+                                                   C.c_void_p(flags.data_ptr() + 4), _ptr(ws), n, _stream_ptr()))
+                it += 1
+            if int(flags[0].item()):
+                break
+    return scale, int(flags[1].item()), bool(flags[0].item())
+
+
+# --------------------------------------------------------------------------------------
+# AdaRound
+def adaround_forward(w, alpha, scale, lo, hi, soft, ch_axis=0):
+    _require_cuda(w, "w")
+    w, alpha = w.detach().contiguous(), alpha.detach().contiguous()
+    lay = layout_of(w, ch_axis)
+    s = _qvec(scale, lay.channels, w.device, "scale")
+    y = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.lib().dlmcq_adaround_forward(_ptr(w), _ptr(alpha), _ptr(y), C.byref(lay), _ptr(s), int(lo),
+                                                     int(hi), int(bool(soft)), _stream_ptr()))
+    return y
+
+
+def adaround_backward(w, alpha, dy, scale, lo, hi, ch_axis=0):
+    w, alpha, dy = w.detach().contiguous(), alpha.detach().contiguous(), dy.detach().contiguous()
+    lay = layout_of(w, ch_axis)
+    s = _qvec(scale, lay.channels, w.device, "scale")
+    dalpha = torch.empty_like(w)
+    ds = torch.empty(lay.channels, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        ws, n = _ws_for(w, lay)
+        _lib.check(_lib.lib().dlmcq_adaround_backward(_ptr(w), _ptr(alpha), _ptr(dy), _ptr(dalpha), _ptr(ds),
+                                                      C.byref(lay), _ptr(s), int(lo), int(hi), _ptr(ws), n,
+                                                      _stream_ptr()))
+    return dalpha, ds
+
+
+def adaround_init_alpha(w, scale, ch_axis=0):
+    _require_cuda(w, "w")
+    w = w.detach().contiguous()
+    lay = layout_of(w, ch_axis)
+    s = _qvec(scale, lay.channels, w.device, "scale")
+    alpha = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.lib().dlmcq_adaround_init_alpha(_ptr(w), _ptr(alpha), C.byref(lay), _ptr(s), _stream_ptr()))
+    return alpha
+
+
+# --------------------------------------------------------------------------------------
+# RootQ
+def _f32_scalar(t, device, name):
+    if t.device != device or t.dtype != torch.float32:
+        raise DlmcqError(f"{name} must be a float32 tensor on {device}")
+    return t
+
+
+def rootq_act_prepare(in_scale, run_scale, momentum, g, lo, hi, training):
+    """RootQ/base.py:92-106.  Updates run_scale in place when training; returns the state block."""
+    dev = run_scale.device
+    state = torch.empty(ROOTQ_STATE_FLOATS, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dlmcq_rootq_act_prepare(_ptr(_f32_scalar(in_scale.detach(), dev, "in_scale")),
+                                                      _ptr(_f32_scalar(run_scale, dev, "run_scale")), float(momentum),
+                                                      float(g), int(lo), int(hi), int(bool(training)), _ptr(state),
+                                                      _stream_ptr()))
+    return state
+
+
+def rootq_wt_prepare(upper, lower, alpha, run_upper, run_lower, momentum, g, lo, hi, training):
+    """RootQ/base.py:131-147 (+ alpha clamp of function.py:25-26)."""
+    dev = run_upper.device
+    state = torch.empty(ROOTQ_STATE_FLOATS, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dlmcq_rootq_wt_prepare(_ptr(_f32_scalar(upper.detach(), dev, "wt_upper")),
+                                                     _ptr(_f32_scalar(lower.detach(), dev, "wt_lower")),
+                                                     _ptr(_f32_scalar(alpha.detach(), dev, "wt_alpha")),
+                                                     _ptr(run_upper), _ptr(run_lower), float(momentum), float(g),
+                                                     int(lo), int(hi), int(bool(training)), _ptr(state), _stream_ptr()))
+    return state
+
+
+def _rootq_fwd(fn_name, x, state):
+    _require_cuda(x, "x")
+    x = x.detach().contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(getattr(_lib.lib(), fn_name)(_ptr(x), _ptr(y), x.numel(), _dtype_code(x), _ptr(state), _stream_ptr()))
+    return y
+
+
+def _rootq_bwd(fn_name, x, dy, state, ngrads):
+    x, dy = x.detach().contiguous(), dy.detach().contiguous()
+    dx = torch.empty_like(x)
+    grads = torch.empty(ngrads, dtype=torch.float32, device=x.device)
+    lay = layout_of(x)
+    with torch.cuda.device(x.device):
+        ws, n = _ws_for(x, lay)
+        _lib.check(getattr(_lib.lib(), fn_name)(_ptr(x), _ptr(dy), _ptr(dx), _ptr(grads), x.numel(), _dtype_code(x),
+                                                _ptr(state), _ptr(ws), n, _stream_ptr()))
+    return dx, grads
+
+
+def rootq_act_forward(x, state):
+    return _rootq_fwd("dlmcq_rootq_act_forward", x, state)
+
+
+def rootq_wt_forward(w, state):
+    return _rootq_fwd("dlmcq_rootq_wt_forward", w, state)
+
+
+def rootq_act_backward(x, dy, state):
+    """-> dx, d_in_scale[1]"""
+    return _rootq_bwd("dlmcq_rootq_act_backward", x, dy, state, 1)
+
+
+def rootq_wt_backward(w, dy, state):
+    """-> dw, grads[3] = (d wt_upper, d wt_lower, d wt_alpha)"""
+    return _rootq_bwd("dlmcq_rootq_wt_backward", w, dy, state, 3)
+
+
+# --------------------------------------------------------------------------------------
+GROUP_SEG = 4096
+
+
+class GroupedFakeQuant:
+    """All weight tensors of a model in one launch (forward) / two launches (backward).
+
+    The descriptor table lives on the device and is rebuilt only when the set of tensors changes,
+    so a training step costs one small H2D copy at most (none when pointers are stable)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._key = None
+        self._items = self._unit_prefix = self._chan_prefix = self._partials = None
+        self._total_units = self._total_channels = 0
+
+    def _table(self, entries, backward):
+        key = tuple((e["x"].data_ptr(), e["y"].data_ptr(), e["dy"].data_ptr() if backward else 0, e["scale"].data_ptr(),
+                     e["offset"].data_ptr() if e.get("offset") is not None else 0,
+                     e["dscale"].data_ptr() if backward else 0, e["channels"], e["inner"], e["form"], e["lo"], e["hi"],
+                     e["g"]) for e in entries)
+        if key == self._key:
+            return
+        arr = (_lib.GroupItem * len(entries))()
+        units, chans = [0], [0]
+        for i, e in enumerate(entries):
+            it = arr[i]
+            it.x, it.y = e["x"].data_ptr(), e["y"].data_ptr()
+            it.dy = e["dy"].data_ptr() if backward else None
+            it.scale = e["scale"].data_ptr()
+            it.offset = e["offset"].data_ptr() if e.get("offset") is not None else None
+            it.dscale = e["dscale"].data_ptr() if backward else None
+            it.channels, it.inner = e["channels"], e["inner"]
+            it.form, it.lo, it.hi, it.g = e["form"], e["lo"], e["hi"], e["g"]
+            units.append(units[-1] + e["channels"] * ((e["inner"] + GROUP_SEG - 1) // GROUP_SEG))
+            chans.append(chans[-1] + e["channels"])
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._items = raw.to(self.device)
+        self._unit_prefix = torch.tensor(units, dtype=torch.int64).to(self.device)
+        self._chan_prefix = torch.tensor(chans, dtype=torch.int64).to(self.device)
+        self._total_units, self._total_channels = units[-1], chans[-1]
+        if self._partials is None or self._partials.numel() < self._total_units:
+            self._partials = torch.empty(max(self._total_units, 1), dtype=torch.float32, device=self.device)
+        self._key = key
+
+    def forward(self, entries, dtype=torch.float32):
+        """entries: dicts with x, y, scale, offset|None, channels, inner, form, lo, hi, g."""
+        self._table(entries, backward=False)
+        code = F32 if dtype == torch.float32 else BF16
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_fq_forward_grouped(_ptr(self._items), _ptr(self._unit_prefix), len(entries),
+                                                           self._total_units, code, _stream_ptr()))
+
+    def backward(self, entries, dtype=torch.float32):
+        """entries additionally carry dy, dscale; `y` receives dx."""
+        self._table(entries, backward=True)
+        code = F32 if dtype == torch.float32 else BF16
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_fq_backward_grouped(_ptr(self._items), _ptr(self._unit_prefix),
+                                                            _ptr(self._chan_prefix), len(entries), self._total_units,
+                                                            self._total_channels, code, _ptr(self._partials),
+                                                            _stream_ptr()))
+
+
+class HostFakeQuant:
+    """End-to-end path for HOST tensors (pinned memory): forward + backward with the H2D / D2H
+    copies pipelined against the kernels (dlmcq_host_fq_forward_backward)."""
+
+    def __init__(self, device, chunk_elems=1 << 22, dtype=torch.float32):
+        self.device = torch.device(device)
+        self.chunk = int(chunk_elems)
+        self.code = F32 if dtype == torch.float32 else BF16
+        n = _lib.lib().dlmcq_host_staging_bytes(self.chunk, self.code)
+        self.staging = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.nbytes = n
+
+    def forward_backward(self, x, dy, y, dx, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
+        """x, dy: host inputs; y, dx: host outputs (same shape/dtype).  Returns dscale (python float)."""
+        for t in (x, dy, y, dx):
+            if t.is_cuda or not t.is_contiguous():
+                raise DlmcqError("host path takes contiguous CPU tensors")
+        ds = C.c_float(0.0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_host_fq_forward_backward(
+                _ptr(x), _ptr(dy), _ptr(y), _ptr(dx), C.byref(ds), x.numel(), self.code, int(form), int(lo), int(hi),
+                float(g), float(scale), float(offset), _ptr(self.staging), self.nbytes, self.chunk))
+        return ds.value

@@ -1,0 +1,243 @@
+/* dlmcq.h - C ABI of the B200-native fake-quantization library (libdlmcq.so).
+ *
+ * This is the drop-in boundary for ONE hot path of ilur98/DLMC-QUANT: the weight /
+ * activation fake-quantizers of dlmc/quantization/scalar (quantize, clamp, round,
+ * dequantize), their STE / LSQ / RootQ backward, and the PTQ observers.  The reference
+ * has no FFI (it is pure Python); every entry point below names the reference
+ * expression (file:line under /root/reference) that it replaces, and INTEGRATION.md
+ * shows the ctypes stub a maintainer would add at that line.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, a CUDA stream passed as void* (cudaStream_t).
+ *   - no allocation and no host synchronisation on the device-pointer entry points: outputs
+ *     and workspaces are provided by the caller and every launch goes to `stream`.  The only
+ *     process state is a cached SM count and the stream pool of the host-buffer entry.
+ *   - returns DLMCQ_OK (0) or a negative dlmcq_status; CUDA launch errors are reported
+ *     as DLMCQ_ECUDA and the text is available from dlmcq_last_cuda_error().
+ *   - arithmetic is IEEE fp32, one rounding per reference op, no FMA contraction, true
+ *     division, round-half-even: integer codes and fp32 outputs are bit-identical to the
+ *     reference's eager PyTorch chain.  bf16 tensors are up-converted, computed in fp32
+ *     and rounded once (RNE) on store.
+ *   - tensor layout: a contiguous tensor viewed as [outer, channels, inner]; the channel
+ *     of flat element i is (i / inner) % channels.  Per-tensor qparams: channels = 1.
+ *     Weights [C, K] with ch_axis=0: outer=1, channels=C, inner=K.  Activations [B,C,H,W]
+ *     with ch_axis=1: outer=B, channels=C, inner=H*W.  scale/offset/zp arrays hold
+ *     `channels` floats.
+ */
+#ifndef DLMCQ_H_
+#define DLMCQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLMCQ_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  DLMCQ_OK = 0,
+  DLMCQ_EINVAL = -1,     /* bad argument (null pointer, negative size, unknown enum) */
+  DLMCQ_EALIGN = -2,     /* pointer not aligned to the element size */
+  DLMCQ_EWORKSPACE = -3, /* workspace too small (see dlmcq_workspace_bytes) */
+  DLMCQ_ECUDA = -4,      /* CUDA runtime reported an error at launch */
+  DLMCQ_EUNSUPPORTED = -5
+} dlmcq_status;
+
+typedef enum { DLMCQ_F32 = 0, DLMCQ_BF16 = 1 } dlmcq_dtype;
+
+/* Which reference expression a fake-quant call reproduces. */
+typedef enum {
+  /* dlmc/quantization/scalar/utils.py:1-11  quantize()/emulate_quantize():
+   *   codes = clamp(round((x-off)/(s+1e-7)), lo, hi);  y = codes*s + off          */
+  DLMCQ_FORM_A1 = 0,
+  /* dlmc/quantization/scalar/modules/base.py:96-102,131-133 (QBase, LSQ-style):
+   *   s' = (s - s*g) + s*g;  codes = round_pass(clamp((x-off)/s', lo, hi));  y = codes*s' + off */
+  DLMCQ_FORM_AFFINE = 1,
+  /* dlmc/quantization/scalar/FSPTQuant/base.py:108-109 (integer zero-point):
+   *   codes = clamp(round_pass(x/s) + zp, lo, hi);  y = (codes - zp)*s            */
+  DLMCQ_FORM_ZP = 2,
+  /* dlmc/quantization/scalar/FSPTQuant/base.py:149-152 (symmetric, per-channel weights):
+   *   codes = clamp(round_pass(w/s), lo, hi);  y = codes*s                        */
+  DLMCQ_FORM_SYM = 3
+} dlmcq_form;
+
+/* A contiguous tensor viewed as [outer, channels, inner]. */
+typedef struct {
+  int64_t outer;
+  int64_t channels;
+  int64_t inner;
+  int32_t dtype; /* dlmcq_dtype of x / y / dy / dx */
+} dlmcq_layout;
+
+/* Quantisation parameters.  `scale` and `offset` are DEVICE arrays of layout.channels
+ * floats (offset may be NULL = 0; for FORM_ZP it is the zero-point).  They stay on the
+ * device so that learnable scales never force a host sync. */
+typedef struct {
+  int32_t form;        /* dlmcq_form */
+  int32_t lo, hi;      /* integer clamp range, utils.py:14-22 get_qrange() */
+  float g;             /* grad_scale factor 1/sqrt(numel*qmax) (FORM_AFFINE only) */
+  const float* scale;
+  const float* offset;
+} dlmcq_qparams;
+
+int dlmcq_version(void);
+const char* dlmcq_status_string(int status);
+const char* dlmcq_last_cuda_error(void);
+
+/* Bytes of zero-initialised device workspace the backward / observer entry points need
+ * for this layout.  The library leaves the workspace zeroed again when a call finishes,
+ * so one allocation (zeroed once) can be reused by successive calls on the same stream. */
+size_t dlmcq_workspace_bytes(const dlmcq_layout* layout);
+
+/* ---- fake-quant forward --------------------------------------------------------------
+ * Replaces the eager chains at modules/base.py:102,133; FSPTQuant/base.py:108-109,149-152;
+ * utils.py:1-11.  `y` (dequantised) and `codes` (fp32/bf16-valued integers) may each be
+ * NULL; at least one must be given.  x may alias y. */
+int dlmcq_fq_forward(const void* x, void* y, void* codes, const dlmcq_layout* layout,
+                     const dlmcq_qparams* qp, void* stream);
+
+/* ---- fake-quant backward -------------------------------------------------------------
+ * One pass over (x, dy): writes dx and the reduced scale gradient dscale[channels]
+ * (and, if doffset != NULL, the offset / zero-point gradient doffset[channels]).
+ * Replaces autograd through the chains above (FORM_AFFINE: dscale includes the factor g;
+ * FORM_ZP / FORM_SYM: plain sum; FORM_A1: FunLSQ.backward, modules/function.py:38-47,
+ * strict masks, offset ignored, dscale includes g).  Deterministic: block partials are
+ * combined in a fixed order by the last block to finish. */
+int dlmcq_fq_backward(const void* x, const void* dy, void* dx, float* dscale, float* doffset,
+                      const dlmcq_layout* layout, const dlmcq_qparams* qp,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* dequantize(): utils.py:5-6   y = codes*scale + offset */
+int dlmcq_dequantize(const void* codes, void* y, const dlmcq_layout* layout,
+                     const float* scale, const float* offset, void* stream);
+
+/* ---- AdaRound weight form (FSPTQuant/base.py:69-79,136-141,151-152) -------------------
+ * soft=1: codes = clamp(floor(w/s) + clamp(sigmoid(alpha)*1.2-0.1,0,1), lo, hi)
+ * soft=0: codes = clamp(floor(w/s) + (alpha>=0), lo, hi);       y = codes*s
+ * backward (soft only): dscale[c] = sum dy*codes, dalpha elementwise; dw is identically 0. */
+int dlmcq_adaround_forward(const void* w, const void* alpha, void* y, const dlmcq_layout* layout,
+                           const float* scale, int lo, int hi, int soft, void* stream);
+int dlmcq_adaround_backward(const void* w, const void* alpha, const void* dy, void* dalpha,
+                            float* dscale, const dlmcq_layout* layout, const float* scale,
+                            int lo, int hi, void* workspace, size_t workspace_bytes, void* stream);
+/* init_alpha(): FSPTQuant/base.py:73-76 */
+int dlmcq_adaround_init_alpha(const void* w, void* alpha, const dlmcq_layout* layout,
+                              const float* scale, void* stream);
+
+/* ---- RootQ (RootQ/base.py:77-156, RootQ/function.py) ----------------------------------
+ * State block written by the *_prepare calls and consumed by forward/backward (device):
+ *   act: [0]=sr' (effective scale) [1]=upper=sr'*Q [2]=g [3]=m [4]=Q
+ *   wt : [0]=U [1]=L [2]=delta [3]=alpha' [4]=g [5]=m [6]=1[1e-4<alpha<1] [7]=Q
+ * momentum and g are the reference's python doubles; (1-m), (1-g) are formed in double and
+ * rounded to fp32 exactly where the eager chain does it. */
+#define DLMCQ_ROOTQ_STATE_FLOATS 8
+
+/* RootQ/base.py:92-106: EMA + gradient-mix of the activation scale; updates run_scale in
+ * place when training (:101). */
+int dlmcq_rootq_act_prepare(const float* in_scale, float* run_scale, double momentum, double g,
+                            int lo, int hi, int training, float* state, void* stream);
+/* RootQ/base.py:108-111 */
+int dlmcq_rootq_act_forward(const void* x, void* y, int64_t numel, int dtype,
+                            const float* state, void* stream);
+int dlmcq_rootq_act_backward(const void* x, const void* dy, void* dx, float* d_in_scale,
+                             int64_t numel, int dtype, const float* state,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* RootQ/base.py:131-145 */
+int dlmcq_rootq_wt_prepare(const float* upper, const float* lower, const float* alpha,
+                           float* run_upper, float* run_lower, double momentum, double g,
+                           int lo, int hi, int training, float* state, void* stream);
+/* RootQ/base.py:146-155 */
+int dlmcq_rootq_wt_forward(const void* w, void* y, int64_t numel, int dtype,
+                           const float* state, void* stream);
+/* grads[0..2] = d wt_upper, d wt_lower, d wt_alpha */
+int dlmcq_rootq_wt_backward(const void* w, const void* dy, void* dw, float* grads,
+                            int64_t numel, int dtype, const float* state,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- observers (dlmc/quantization/scalar/ops.py) --------------------------------------
+ * Statistics pass: one read of the tensor -> stats[channels][4] = {min, max, max|x|, sum|x|}
+ * (NaN-propagating like torch.min/max).  Multi-GPU callers all-reduce `stats` between this
+ * call and the *_finalize call. */
+#define DLMCQ_STATS_PER_CHANNEL 4
+int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* layout,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* ops.py:20-34,121-140 (minmax_tensor / minmax_channel): signed: s = absmax/(2^(n-1)-1), off=0;
+ * unsigned: s = (max-min)/(2^n-1), off = min (or 0 when allow_offset==0). */
+int dlmcq_obs_minmax_finalize(const float* stats, float* scale, float* offset, int64_t channels,
+                              int n_bits, int is_signed, int allow_offset, void* stream);
+/* mean|x| based initialisers; `count` = elements behind each stats row.
+ *   mode 0: out = (mul_a*mean)/mul_b   modules/base.py:84,119 LSQ init 2*mean|x|/sqrt(qmax)
+ *   mode 1: out = (mul_a*mean)*mul_b   RootQ/base.py:115-116   +-2*mean|w|*sqrt(qmax)        */
+int dlmcq_obs_absmean_finalize(const float* stats, float* out, int64_t channels, double count,
+                               double mul_a, double mul_b, int mode, void* stream);
+
+/* ops.py:36-68 quantize_l2loss_tensor (unsigned branch): 80-candidate clip-ratio sweep.
+ * Pass 1 (dlmcq_obs_stats) gives min/max; this pass accumulates the 80 squared-error sums
+ * sse[80] in one read of x; the finalize picks the first strict minimum below 1000 of
+ * sse[i]/rows_for_mean (l2_loss = sum over axis 1, mean over the rest).  */
+#define DLMCQ_SWEEP_CANDIDATES 80
+int dlmcq_obs_sweep_tensor_sse(const void* x, int64_t numel, int dtype, const float* stats,
+                               int n_bits, int allow_offset, float* sse,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int dlmcq_obs_sweep_tensor_finalize(const float* sse, const float* stats, double rows_for_mean,
+                                    int n_bits, int allow_offset, float* scale, float* offset,
+                                    int32_t* picked, void* stream);
+/* ops.py:169-196 quantize_l2loss_channel on rows [channels, inner]: whole search per channel
+ * in one launch, each row staged once in shared memory (bulk async copy) and swept 80 times
+ * on chip.  Reproduces the reference's aliasing of the running minimum with the offset vector
+ * and its disregard of `signed` in the search. */
+int dlmcq_obs_sweep_channel(const void* x, int64_t channels, int64_t inner, int dtype,
+                            int n_bits, int is_signed, float* scale, float* offset, void* stream);
+
+/* ops.py:71-83,198-215 l2norm fixed point, one iteration over rows [channels, inner]
+ * (channels=1 for the per-tensor form):
+ *   q = A1 codes(x, scale, offset);  new_scale[c] = sum(x*q)/sum(q*q + 1e-7)
+ *   *diff = |new-s|/s (channels==1) or ||new-s||_2/||s||_2;  if *done is already set the call
+ *   is a no-op; it sets *done when diff <= 1e-5 and then leaves `scale` = the converged value.
+ * The caller launches iterations back to back and polls `done` every few launches. */
+int dlmcq_obs_l2norm_step(const void* x, int64_t channels, int64_t inner, int dtype,
+                          float* scale, const float* offset, int lo, int hi,
+                          float* diff, int32_t* done, int32_t* iters,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- grouped (multi-tensor) launches --------------------------------------------------
+ * All weight tensors of a model in ONE launch: the per-layer tensors of a CNN (<= 9.4 MB)
+ * are launch-latency-bound on B200 when quantised one by one.  `items` is a DEVICE array. */
+#define DLMCQ_GROUP_SEG 4096 /* elements per work unit (one warp) */
+typedef struct {
+  const void* x;
+  void* y;            /* forward: output; backward: dx */
+  const void* dy;     /* backward only */
+  const float* scale; /* [channels] */
+  const float* offset;/* [channels] or NULL */
+  float* dscale;      /* backward only, [channels] */
+  int64_t channels;   /* rows of this tensor (1 = per-tensor qparams) */
+  int64_t inner;      /* elements per row */
+  int32_t form, lo, hi;
+  float g;
+} dlmcq_group_item;
+/* unit_prefix[k] = sum_{j<k} channels_j * ceil(inner_j / DLMCQ_GROUP_SEG), k = 0..n_items (DEVICE);
+ * chan_prefix[k] = sum_{j<k} channels_j (DEVICE); partials: total_units floats (DEVICE). */
+int dlmcq_fq_forward_grouped(const dlmcq_group_item* items, const int64_t* unit_prefix, int n_items,
+                             int64_t total_units, int dtype, void* stream);
+int dlmcq_fq_backward_grouped(const dlmcq_group_item* items, const int64_t* unit_prefix,
+                              const int64_t* chan_prefix, int n_items, int64_t total_units,
+                              int64_t total_channels, int dtype, float* partials, void* stream);
+
+/* ---- host-buffer entry (end-to-end path) ----------------------------------------------
+ * Same arithmetic as dlmcq_fq_forward + dlmcq_fq_backward on a per-tensor-scale tensor that
+ * lives in (pinned) HOST memory: x, dy in; y, dx and dscale out.  Chunks are pipelined
+ * H2D -> kernel -> D2H over internal streams and a caller-provided device staging buffer.
+ * Synchronous: returns when the host outputs are complete. */
+size_t dlmcq_host_staging_bytes(int64_t chunk_elems, int dtype);
+int dlmcq_host_fq_forward_backward(const void* x_host, const void* dy_host, void* y_host,
+                                   void* dx_host, float* dscale_host, int64_t numel, int dtype,
+                                   int form, int lo, int hi, float g, float scale, float offset,
+                                   void* device_staging, size_t staging_bytes, int64_t chunk_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLMCQ_H_ */

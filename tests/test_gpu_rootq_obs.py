@@ -1,0 +1,278 @@
+"""GPU parity tests: RootQ kernels and PTQ observers, through the C ABI, against the golden
+fixtures (reference outputs) and the oracle restatement."""
+import math
+
+import pytest
+import torch
+
+from oracle import restate as R
+from tests.golden_io import bits_equal, first_mismatch, load
+from tests.test_gpu_fq import F, dev, exact, red_close
+
+pytestmark = pytest.mark.gpu
+
+ROOTQ = load("rootq")
+
+
+def _scalar(t):
+    return t.reshape(()).float().cuda().clone()
+
+
+@pytest.mark.parametrize("name", sorted(n for n in ROOTQ if n.startswith("conv_") and not n.endswith("_step1")))
+def test_golden_rootq(name):
+    c = ROOTQ[name]
+    q = c.meta["qconfig"]
+    m = q["momentum"]
+    x, w = c.inp["x"], c.inp["weight"]
+    ilo, ihi = R.qrange(False, q["input"]["args"]["n_bits"])
+    wlo, whi = R.qrange(False, q["weight"]["args"]["n_bits"])
+    g_i, g_w = 1 / math.sqrt(x.numel() * ihi), 1 / math.sqrt(w.numel() * whi)
+    if name.endswith("_eval"):
+        run = _scalar(c.out["buf_in_run_scale"])
+        st = F().rootq_act_prepare(_scalar(c.out["param_in_scale"]), run, m, g_i, ilo, ihi, False)
+        exact(F().rootq_act_forward(dev(x), st), c.out["qx"], "qx eval")
+        ru, rl = _scalar(c.out["buf_wt_run_upper"]), _scalar(c.out["buf_wt_run_lower"])
+        sw = F().rootq_wt_prepare(_scalar(c.out["param_wt_upper"]), _scalar(c.out["param_wt_lower"]),
+                                  _scalar(c.out["param_wt_alpha"]), ru, rl, m, g_w, wlo, whi, False)
+        exact(F().rootq_wt_forward(dev(w), sw), c.out["qw"], "qw eval")
+        exact(run, c.out["buf_in_run_scale"], "eval must not touch run_scale")
+        return
+    run = _scalar(c.inp["pre_in_run_scale"])
+    st = F().rootq_act_prepare(_scalar(c.inp["pre_in_scale"]), run, m, g_i, ilo, ihi, True)
+    exact(run, c.out["buf_in_run_scale"], "EMA'd run_scale")
+    exact(F().rootq_act_forward(dev(x), st), c.out["qx"], "qx")
+    dx, ds = F().rootq_act_backward(dev(x), dev(c.out["d_qx"]), st)
+    assert torch.equal(dx.cpu() == 0, c.out["dx"] == 0)
+    assert torch.allclose(dx.cpu(), c.out["dx"], rtol=1e-6, atol=0)
+    red_close(ds, c.out["grad_in_scale"], abs_sum=(c.out["d_qx"].abs().sum() * ihi * m * g_i).reshape(1), rtol=2e-5)
+
+    ru, rl = _scalar(c.inp["pre_wt_run_upper"]), _scalar(c.inp["pre_wt_run_lower"])
+    sw = F().rootq_wt_prepare(_scalar(c.inp["pre_wt_upper"]), _scalar(c.inp["pre_wt_lower"]),
+                              _scalar(c.inp["pre_wt_alpha"]), ru, rl, m, g_w, wlo, whi, True)
+    exact(ru, c.out["buf_wt_run_upper"], "run_upper")
+    exact(rl, c.out["buf_wt_run_lower"], "run_lower")
+    exact(F().rootq_wt_forward(dev(w), sw), c.out["qw"], "qw")
+    dw, gr = F().rootq_wt_backward(dev(w), dev(c.out["d_qw"]), sw)
+    assert torch.allclose(dw.cpu(), c.out["grad_weight"], rtol=1e-5, atol=1e-8)      # north_star: 1e-5 relative
+    floor = c.out["d_qw"].abs().sum() * whi * m * g_w
+    red_close(gr[0], c.out["grad_wt_upper"], abs_sum=floor.reshape(1), rtol=2e-5)
+    red_close(gr[1], c.out["grad_wt_lower"], abs_sum=floor.reshape(1), rtol=2e-5)
+    red_close(gr[2], c.out["grad_wt_alpha"], abs_sum=(c.out["d_qw"].abs().sum() * 1e-3).reshape(1), rtol=2e-5)
+
+
+@pytest.mark.parametrize("wbits,abits,mom,alpha", [(4, 4, 0.1, 0.25), (2, 3, 0.3, 0.6), (8, 8, 0.05, 1.7), (3, 4, 0.1, -0.2)])
+def test_rootq_vs_oracle_large(wbits, abits, mom, alpha):
+    """C1-sized tensors (ResNet-18 CIFAR: 128x64x32x32 activations, 512x512x3x3 weights scaled down)."""
+    gen = torch.Generator().manual_seed(100 + wbits)
+    x = torch.relu(torch.randn(16, 64, 32, 32, generator=gen)) * 1.3
+    w = torch.randn(128, 256, 3, 3, generator=gen) * 0.03
+    dyx, dyw = torch.randn(x.shape, generator=gen), torch.randn(w.shape, generator=gen)
+    ilo, ihi = R.qrange(False, abits)
+    wlo, whi = R.qrange(False, wbits)
+    in_scale = R.rootq_act_init(x, ilo, ihi) * 0.9
+    run_scale = in_scale * 1.05
+    up, dn = R.rootq_wt_init(w, whi)
+    up, dn = (up * 0.8).float(), (dn * 1.1).float()
+    run_up, run_dn = up * 1.02, dn * 0.97
+    a = torch.tensor(alpha)
+    y, new_run, dx_ref, ds_ref = R.rootq_act_fwd_bwd(x, in_scale, run_scale, mom, ilo, ihi, dyx)
+    g_i, g_w = 1 / math.sqrt(x.numel() * ihi), 1 / math.sqrt(w.numel() * whi)
+    run = _scalar(run_scale)
+    st = F().rootq_act_prepare(_scalar(in_scale), run, mom, g_i, ilo, ihi, True)
+    exact(run, new_run, "run_scale")
+    exact(F().rootq_act_forward(dev(x), st), y, "act fwd")
+    dx, ds = F().rootq_act_backward(dev(x), dev(dyx), st)
+    assert torch.equal(dx.cpu() == 0, dx_ref == 0) and torch.allclose(dx.cpu(), dx_ref, rtol=1e-6, atol=0)
+    red_close(ds, ds_ref, abs_sum=(dyx.abs().sum() * ihi * mom * g_i).reshape(1))
+
+    yw, nru, nrl, dw_ref, du, dl, da = R.rootq_wt_fwd_bwd(w, up, dn, a, run_up, run_dn, mom, wlo, whi, dyw)
+    ru, rl = _scalar(run_up), _scalar(run_dn)
+    sw = F().rootq_wt_prepare(_scalar(up), _scalar(dn), _scalar(a), ru, rl, mom, g_w, wlo, whi, True)
+    exact(ru, nru, "run_upper")
+    exact(rl, nrl, "run_lower")
+    exact(F().rootq_wt_forward(dev(w), sw), yw, "wt fwd")
+    dw, gr = F().rootq_wt_backward(dev(w), dev(dyw), sw)
+    assert torch.allclose(dw.cpu(), dw_ref, rtol=1e-5, atol=1e-7)
+    floor = (dyw.abs().sum() * whi * mom * g_w).reshape(1)
+    red_close(gr[0], du, abs_sum=floor)
+    red_close(gr[1], dl, abs_sum=floor)
+    red_close(gr[2], da, abs_sum=(dyw.abs().sum() * 1e-3).reshape(1))
+
+
+def test_rootq_clipping_special_values():
+    c = ROOTQ["clipping_0_15"]
+    # clipping(x, 15, 0) followed by round(x/1)*1 : use scale 1 so that y = round_pass(clip(x))
+    run = torch.tensor(1.0).cuda()
+    st = F().rootq_act_prepare(torch.tensor(1.0).cuda(), run, 0.1, 0.01, 0, 15, False)
+    y = F().rootq_act_forward(dev(c.inp["x"]), st)
+    ref, _ = R.rootq_act(c.inp["x"], torch.tensor(1.0), torch.tensor(1.0), 0.1, 0, 15, False)
+    exact(y, ref, "rootq act on special values")
+
+
+# --------------------------------------------------------------------------------------
+OBS = load("observers")
+
+
+def _kind(name):
+    return name.split("_")[0] + "_" + name.split("_")[1]
+
+
+@pytest.mark.parametrize("name", sorted(n for n in OBS if n.startswith("minmax_tensor") or n.startswith("minmax_channel")))
+def test_golden_minmax(name):
+    c = OBS[name]
+    t = c.inp["t"]
+    ax = c.meta.get("ch_axis") if name.startswith("minmax_channel") else None
+    stats = F().obs_stats(dev(t), ch_axis=ax)
+    s, o = F().minmax_from_stats(stats, c.meta["n_bits"], c.meta["signed"])
+    exact(s, c.out["scale"].reshape(-1), "scale")
+    exact(o, c.out["offset"].reshape(-1), "offset")
+
+
+@pytest.mark.parametrize("name", sorted(n for n in OBS if n.startswith("l2loss_tensor")))
+def test_golden_sweep_tensor(name):
+    c = OBS[name]
+    t = c.inp["t"]
+    if c.meta["signed"]:
+        pytest.skip("signed l2loss_tensor is the min/max answer (ops.py:37-40), covered by test_golden_minmax")
+    s, o, picked = F().sweep_tensor(dev(t), c.meta["n_bits"])
+    ref_s, ref_o, ref_pick = R.obs_l2loss_tensor(t, c.meta["n_bits"], False, return_index=True)
+    assert c.meta["picked"] == ref_pick
+    if int(picked) == ref_pick:
+        exact(s, c.out["scale"].reshape(-1), "scale")
+        exact(o, c.out["offset"].reshape(-1), "offset")
+    else:   # near-tie between two candidates decided by summation order: losses must agree to 1e-5
+        sse = F().sweep_tensor_sse(dev(t), F().obs_stats(dev(t)), c.meta["n_bits"]).cpu()
+        assert abs(float(sse[int(picked)]) - float(sse[ref_pick])) <= 1e-5 * float(sse[ref_pick])
+
+
+@pytest.mark.parametrize("name", sorted(n for n in OBS if n.startswith("l2loss_channel")))
+def test_golden_sweep_channel(name):
+    c = OBS[name]
+    t = c.inp["t"]
+    rows = t.reshape(t.shape[0], -1)
+    s, o = F().sweep_channel(dev(rows), c.meta["n_bits"], c.meta["signed"])
+    ref_s, ref_o = c.out["scale"].reshape(-1), c.out["offset"].reshape(-1)
+    same = (s.cpu() == ref_s) & (o.cpu() == ref_o)
+    # rows where a near-tie flipped the accepted candidate must still be within one sweep step (1 %)
+    assert same.float().mean() >= 0.8, f"only {same.float().mean():.2f} of rows identical"
+    assert torch.allclose(s.cpu()[~same], ref_s[~same], rtol=0.03)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in OBS if n.startswith("l2norm_")))
+def test_golden_l2norm(name):
+    c = OBS[name]
+    t = c.inp["t"]
+    signed, bits = c.meta["signed"], c.meta["n_bits"]
+    lo, hi = R.qrange(signed, bits)
+    per_channel = name.startswith("l2norm_channel")
+    rows = t.reshape(t.shape[0], -1) if per_channel else t.reshape(1, -1)
+    stats = F().obs_stats(dev(rows), ch_axis=0 if per_channel else None)
+    s0, o0 = F().minmax_from_stats(stats, bits, signed)
+    s, iters, done = F().l2norm_fixed_point(dev(rows), s0, o0, lo, hi)
+    assert done, "did not converge although the reference did"
+    assert torch.allclose(s.cpu(), c.out["scale"].reshape(-1), rtol=2e-4), (s.cpu(), c.out["scale"].reshape(-1))
+
+
+def test_sweep_tensor_vs_oracle_large():
+    gen = torch.Generator().manual_seed(9)
+    t = torch.relu(torch.randn(8, 32, 28, 28, generator=gen)) * 2 + 0.0
+    for bits in (4, 8):
+        s, o, picked = F().sweep_tensor(dev(t), bits)
+        rs, ro, rp = R.obs_l2loss_tensor(t, bits, False, return_index=True)
+        assert abs(int(picked) - rp) <= 1, (int(picked), rp)
+        if int(picked) == rp:
+            exact(s, rs.reshape(1), "scale")
+            exact(o, ro.reshape(1).float(), "zero point")
+
+
+def test_sweep_channel_vs_oracle_rows():
+    """Signed weights (the search clamps to [0, qmax] - reference quirk) and shifted positive rows
+    (exercise the aliasing of the running minimum), row lengths 27..4608 and > shared-memory cap."""
+    gen = torch.Generator().manual_seed(10)
+    for shape, kind in [((48, 27), "wt"), ((16, 576), "wt"), ((8, 4608), "wt"), ((6, 50), "shift"), ((3, 7000), "wt"),
+                        ((5, 147), "shift")]:
+        t = torch.randn(shape, generator=gen) * 0.02 if kind == "wt" else torch.rand(shape, generator=gen) * 3 + 0.75
+        for signed in (True, False):
+            s, o = F().sweep_channel(dev(t), 4, signed)
+            rs, ro = R.obs_l2loss_channel(t.clone(), 4, signed)
+            same = (s.cpu() == rs.reshape(-1)) & (o.cpu() == ro.reshape(-1))
+            assert same.float().mean() >= 0.75, (shape, kind, signed, same)
+            assert torch.allclose(s.cpu(), rs.reshape(-1), rtol=0.03)
+
+
+def test_stats_nan_and_layouts():
+    gen = torch.Generator().manual_seed(12)
+    t = torch.randn(4, 6, 7, 7, generator=gen)
+    st = F().obs_stats(dev(t), ch_axis=1).cpu()
+    rows = t.transpose(0, 1).reshape(6, -1)
+    assert torch.equal(st[:, 0], rows.min(1)[0]) and torch.equal(st[:, 1], rows.max(1)[0])
+    assert torch.equal(st[:, 2], rows.abs().max(1)[0])
+    assert torch.allclose(st[:, 3], rows.abs().sum(1), rtol=1e-5)
+    t2 = t.clone()
+    t2[1, 2, 3, 3] = float("nan")
+    st = F().obs_stats(dev(t2), ch_axis=1).cpu()
+    assert torch.isnan(st[2]).all() and not torch.isnan(st[[0, 1, 3, 4, 5]]).any()   # torch.min/max propagate NaN
+    big = torch.randn((1 << 22) + 5, generator=gen)
+    st = F().obs_stats(dev(big)).cpu()[0]
+    assert st[0] == big.min() and st[1] == big.max() and st[2] == big.abs().max()
+    assert abs(float(st[3]) - float(big.abs().double().sum())) <= 1e-5 * float(st[3])
+
+
+def test_absmean_initialisers():
+    gen = torch.Generator().manual_seed(13)
+    x = torch.randn(64, 3, 3, 3, generator=gen) * 0.1
+    stats = F().obs_stats(dev(x))
+    lsq = F().absmean_from_stats(stats, x.numel(), 2.0, math.sqrt(7), 0).cpu()
+    assert torch.allclose(lsq, R.lsq_init_scale(x, 7).reshape(1), rtol=1e-6)
+    up = F().absmean_from_stats(stats, x.numel(), 2.0, math.sqrt(15), 1).cpu()
+    assert torch.allclose(up, R.rootq_wt_init(x, 15)[0].reshape(1).float(), rtol=1e-6)
+
+
+def test_grouped_matches_single_launches():
+    """All weight tensors of a model in one launch == the per-tensor launches, bit for bit."""
+    from dlmc_quant_b200.functional import GroupedFakeQuant
+    gen = torch.Generator().manual_seed(14)
+    shapes = [(64, 147), (64, 64), (128, 1152), (256, 2304), (512, 4608), (1000, 2048), (32, 9)]
+    entries, singles = [], []
+    for i, (c, k) in enumerate(shapes):
+        per_channel = i % 2 == 0
+        w = dev(torch.randn(c, k, generator=gen) * 0.03)
+        dy = dev(torch.randn(c, k, generator=gen))
+        nch = c if per_channel else 1
+        scale = dev(torch.rand(nch, generator=gen) * 0.004 + 0.004)
+        form = 3 if per_channel else 1
+        g = 1 / math.sqrt(c * k * 7)
+        e = dict(x=w, y=torch.empty_like(w), dy=dy, scale=scale, offset=None, dscale=torch.zeros(nch, device="cuda"),
+                 channels=nch, inner=k if per_channel else c * k, form=form, lo=-7, hi=7, g=g)
+        entries.append(e)
+        singles.append((w, dy, scale, form, g, 0 if per_channel else None))
+    grp = GroupedFakeQuant("cuda")
+    grp.forward(entries)
+    for e, (w, dy, scale, form, g, ax) in zip(entries, singles):
+        assert torch.equal(e["y"], F().fq_forward(w, scale, None, -7, 7, form, g=g, ch_axis=ax))
+    outs = [e["y"].clone() for e in entries]
+    bentries = [dict(e, y=torch.empty_like(e["x"])) for e in entries]
+    grp2 = GroupedFakeQuant("cuda")
+    grp2.backward(bentries)
+    for e, (w, dy, scale, form, g, ax) in zip(bentries, singles):
+        dx, ds = F().fq_backward(w, dy, scale, None, -7, 7, form, g=g, ch_axis=ax)
+        assert torch.equal(e["y"], dx)
+        red_close(e["dscale"], ds, abs_sum=(dy.abs().sum() * 7).expand(ds.numel()) * (g if form == 1 else 1.0), rtol=1e-5)
+    assert all(torch.equal(a, e["y"]) for a, e in zip(outs, entries))
+
+
+def test_host_pipeline_matches_device_path():
+    from dlmc_quant_b200.functional import HostFakeQuant
+    gen = torch.Generator().manual_seed(15)
+    n = (1 << 21) + 1000
+    x = (torch.relu(torch.randn(n, generator=gen)) * 2).pin_memory()
+    dy = torch.randn(n, generator=gen).pin_memory()
+    y, dx = torch.empty(n).pin_memory(), torch.empty(n).pin_memory()
+    hq = HostFakeQuant("cuda", chunk_elems=1 << 19)
+    g = R.lsq_g(n, 15)
+    ds = hq.forward_backward(x, dy, y, dx, 0.25, 0.0, 0, 15, form=1, g=g)
+    s, o = dev(torch.tensor([0.25])), dev(torch.tensor([0.0]))
+    assert torch.equal(y, F().fq_forward(dev(x), s, o, 0, 15, 1, g=g).cpu())
+    dxd, dsd = F().fq_backward(dev(x), dev(dy), s, o, 0, 15, 1, g=g)
+    assert torch.equal(dx, dxd.cpu())
+    assert abs(ds - float(dsd)) <= 1e-5 * abs(float(dsd)) + 1e-7
