@@ -48,6 +48,8 @@ SIGNATURES = {
     "dlmcq_fq_forward": (_I, [_P, _P, _P, _LP, _QP, _P]),
     "dlmcq_fq_backward": (_I, [_P, _P, _P, _P, _P, _LP, _QP, _P, _Z, _P]),
     "dlmcq_dequantize": (_I, [_P, _P, _LP, _P, _P, _P]),
+    "dlmcq_ste_value": (_I, [_P, _P, _L, _I, _I, _P]),
+    "dlmcq_grad_scale_value": (_I, [_P, _P, _L, _F, _P]),
     "dlmcq_adaround_forward": (_I, [_P, _P, _P, _LP, _P, _I, _I, _I, _P]),
     "dlmcq_adaround_backward": (_I, [_P, _P, _P, _P, _P, _LP, _P, _I, _I, _P, _Z, _P]),
     "dlmcq_adaround_init_alpha": (_I, [_P, _P, _LP, _P, _P]),
@@ -57,7 +59,7 @@ SIGNATURES = {
     "dlmcq_rootq_wt_prepare": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _I, _I, _P, _P]),
     "dlmcq_rootq_wt_forward": (_I, [_P, _P, _L, _I, _P, _P]),
     "dlmcq_rootq_wt_backward": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _Z, _P]),
-    "dlmcq_obs_stats": (_I, [_P, _P, _LP, _P, _Z, _P]),
+    "dlmcq_obs_stats": (_I, [_P, _P, _LP, _I, _P, _Z, _P]),
     "dlmcq_obs_minmax_finalize": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
     "dlmcq_obs_absmean_finalize": (_I, [_P, _P, _L, _D, _D, _D, _I, _P]),
     "dlmcq_obs_sweep_tensor_sse": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _Z, _P]),

@@ -367,6 +367,7 @@ extern "C" size_t dlmcq_workspace_bytes(const dlmcq_layout* l) {
 extern "C" int dlmcq_fq_forward(const void* x, void* y, void* codes, const dlmcq_layout* layout,
                                 const dlmcq_qparams* qp, void* stream) {
   if (int e = check_layout(layout)) return e;
+  if (layout->outer * layout->channels * layout->inner == 0) return DLMCQ_OK;   // empty tensor: nothing to do
   if (!qp || !qp->scale || !x || (!y && !codes)) return DLMCQ_EINVAL;
   if (!elem_aligned(x, layout->dtype) || !elem_aligned(y, layout->dtype) || !elem_aligned(codes, layout->dtype))
     return DLMCQ_EALIGN;
@@ -379,7 +380,8 @@ extern "C" int dlmcq_fq_backward(const void* x, const void* dy, void* dx, float*
                                  const dlmcq_layout* layout, const dlmcq_qparams* qp, void* workspace,
                                  size_t workspace_bytes, void* stream) {
   if (int e = check_layout(layout)) return e;
-  if (!qp || !qp->scale || !x || !dy || !dx || !dscale || !workspace) return DLMCQ_EINVAL;
+  const bool empty = layout->outer * layout->channels * layout->inner == 0;
+  if (!qp || !qp->scale || !dscale || !workspace || (!empty && (!x || !dy || !dx))) return DLMCQ_EINVAL;
   if (!elem_aligned(x, layout->dtype) || !elem_aligned(dy, layout->dtype) || !elem_aligned(dx, layout->dtype))
     return DLMCQ_EALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

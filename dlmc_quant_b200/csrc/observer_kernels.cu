@@ -28,8 +28,10 @@ struct Stat4 {
 __device__ __forceinline__ void stat_init(Stat4& s) {
   s.mn = INFINITY; s.mx = -INFINITY; s.am = 0.f; s.sm = 0.f;
 }
+template <bool ABS = false>
 __device__ __forceinline__ void stat_add(Stat4& s, float v) {
   const float a = fabsf(v);
+  if (ABS) v = a;
   s.mn = fminf(s.mn, v); s.mx = fmaxf(s.mx, v); s.am = fmaxf(s.am, a); s.sm += a;   // NaN reaches sm
 }
 __device__ __forceinline__ void stat_merge(Stat4& s, const Stat4& o) {
@@ -57,7 +59,7 @@ __device__ __forceinline__ void stat_store(float* out, const Stat4& s) {
   out[3] = s.sm;
 }
 
-template <typename T>
+template <typename T, bool ABS>
 __global__ void __launch_bounds__(kThreads, 4)
 stats_flat_kernel(const T* __restrict__ x, int64_t n, float* __restrict__ stats, void* ws) {
   using V = Vec<T>;
@@ -80,21 +82,21 @@ stats_flat_kernel(const T* __restrict__ x, int64_t n, float* __restrict__ stats,
         float f[V::N];
         V::unpack(r[k], f);
 #pragma unroll
-        for (int e = 0; e < V::N; ++e) stat_add(s, f[e]);
+        for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
       }
     }
     for (; i < nvec; i += stride) {
       float f[V::N];
       V::unpack(ld_stream(xv + i), f);
 #pragma unroll
-      for (int e = 0; e < V::N; ++e) stat_add(s, f[e]);
+      for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
     }
     if (blockIdx.x == 0) {
       const int64_t t = nvec * V::N + threadIdx.x;
-      if (t < n) stat_add(s, to_f32<T>(x[t]));
+      if (t < n) stat_add<ABS>(s, to_f32<T>(x[t]));
     }
   } else {
-    for (; i < n; i += stride) stat_add(s, to_f32<T>(x[i]));
+    for (; i < n; i += stride) stat_add<ABS>(s, to_f32<T>(x[i]));
   }
   s = stat_warp(s);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -121,7 +123,7 @@ stats_flat_kernel(const T* __restrict__ x, int64_t n, float* __restrict__ stats,
   }
 }
 
-template <typename T>
+template <typename T, bool ABS>
 __global__ void __launch_bounds__(kRowWarps * 32)
 stats_rows_kernel(const T* __restrict__ x, RowGeom gm, float* __restrict__ stats, Stat4* __restrict__ part, int direct) {
   using V = Vec<T>;
@@ -143,11 +145,11 @@ stats_rows_kernel(const T* __restrict__ x, RowGeom gm, float* __restrict__ stats
       float f[V::N];
       V::unpack(ld_stream(xv + j), f);
 #pragma unroll
-      for (int e = 0; e < V::N; ++e) stat_add(s, f[e]);
+      for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
     }
     done = nvec * V::N;
   }
-  for (int64_t j = done + lane; j < len; j += 32) stat_add(s, to_f32<T>(xr[j]));
+  for (int64_t j = done + lane; j < len; j += 32) stat_add<ABS>(s, to_f32<T>(xr[j]));
   s = stat_warp(s);
   if (lane == 0) {
     if (direct) stat_store(stats + 4 * (row % gm.channels), s);
@@ -505,13 +507,13 @@ l2norm_finalize_kernel(const float* __restrict__ part, RowGeom gm, float* __rest
   }
 }
 
-template <typename T>
+template <typename T, bool ABS>
 static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = l->outer * l->channels * l->inner;
   if (ws_bytes < dlmcq_workspace_bytes(l)) return DLMCQ_EWORKSPACE;
   if (l->channels == 1) {
     const int64_t tiles = (n / Vec<T>::N + kThreads * 4 - 1) / (kThreads * 4);
-    stats_flat_kernel<T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(x, n, stats, ws);
+    stats_flat_kernel<T, ABS><<<stream_grid(tiles, 8), kThreads, 0, st>>>(x, n, stats, ws);
   } else {
     const RowGeom gm = make_geom(l->outer, l->channels, l->inner);
     const int64_t items = gm.rows * gm.segs;
@@ -519,7 +521,7 @@ static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* w
     if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
     const int direct = (l->outer == 1 && gm.segs == 1) ? 1 : 0;
     Stat4* part = reinterpret_cast<Stat4*>(ws_partials(ws));
-    stats_rows_kernel<T><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(x, gm, stats, part, direct);
+    stats_rows_kernel<T, ABS><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(x, gm, stats, part, direct);
     if (!direct) {
       DLMCQ_LAUNCH_CHECK();
       const int64_t fb = (gm.channels + kRowWarps - 1) / kRowWarps;
@@ -534,16 +536,22 @@ static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* w
 
 using namespace dlmcq;
 
-extern "C" int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* layout, void* workspace,
+extern "C" int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* layout, int flags, void* workspace,
                                size_t workspace_bytes, void* stream) {
   if (!layout || layout->outer < 1 || layout->channels < 1 || layout->inner < 1) return DLMCQ_EINVAL;
   if (!x || !stats || !workspace) return DLMCQ_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (layout->dtype == DLMCQ_F32)
-    return stats_launch<float>(static_cast<const float*>(x), stats, layout, workspace, workspace_bytes, st);
-  if (layout->dtype == DLMCQ_BF16)
-    return stats_launch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), stats, layout, workspace,
-                                       workspace_bytes, st);
+  const bool ab = (flags & DLMCQ_STATS_ABS_INPUT) != 0;
+  if (layout->dtype == DLMCQ_F32) {
+    const float* p = static_cast<const float*>(x);
+    return ab ? stats_launch<float, true>(p, stats, layout, workspace, workspace_bytes, st)
+              : stats_launch<float, false>(p, stats, layout, workspace, workspace_bytes, st);
+  }
+  if (layout->dtype == DLMCQ_BF16) {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(x);
+    return ab ? stats_launch<__nv_bfloat16, true>(p, stats, layout, workspace, workspace_bytes, st)
+              : stats_launch<__nv_bfloat16, false>(p, stats, layout, workspace, workspace_bytes, st);
+  }
   return DLMCQ_EINVAL;
 }
 

@@ -134,9 +134,31 @@ def dequantize(codes, scale, offset, ch_axis=None):
     return y
 
 
+def ste_value(x, mode):
+    """mode 0 round_pass value, 1 floor_pass value, 2 sgn (utils.py:29-37, RootQ/function.py:5-8)."""
+    _require_cuda(x, "x")
+    x = x.detach().contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().dlmcq_ste_value(_ptr(x), _ptr(y), x.numel(), _dtype_code(x), int(mode), _stream_ptr()))
+    return y
+
+
+def grad_scale_value(s, g):
+    """utils.py:24-27 value (s - s*g) + s*g for a float32 device tensor of scales."""
+    _require_cuda(s, "scale")
+    s = s.detach().contiguous()
+    if s.dtype != torch.float32:
+        raise DlmcqError("scales are float32")
+    out = torch.empty_like(s)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib().dlmcq_grad_scale_value(_ptr(s), _ptr(out), s.numel(), float(g), _stream_ptr()))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # observers
-def obs_stats(x, ch_axis=None):
+def obs_stats(x, ch_axis=None, abs_input=False):
     """One read of x -> float32 [channels, 4] = (min, max, max|x|, sum|x|)."""
     _require_cuda(x, "x")
     x = x.detach().contiguous()
@@ -144,7 +166,8 @@ def obs_stats(x, ch_axis=None):
     stats = torch.empty(lay.channels, STATS_PER_CHANNEL, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         ws, n = _ws_for(x, lay)
-        _lib.check(_lib.lib().dlmcq_obs_stats(_ptr(x), _ptr(stats), C.byref(lay), _ptr(ws), n, _stream_ptr()))
+        _lib.check(_lib.lib().dlmcq_obs_stats(_ptr(x), _ptr(stats), C.byref(lay), int(bool(abs_input)), _ptr(ws), n,
+                                              _stream_ptr()))
     return stats
 
 

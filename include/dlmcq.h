@@ -109,6 +109,12 @@ int dlmcq_fq_backward(const void* x, const void* dy, void* dx, float* dscale, fl
                       const dlmcq_layout* layout, const dlmcq_qparams* qp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* utils.py:29-37 round_pass / floor_pass values and RootQ/function.py:5-8 sgn:
+ * mode 0: (round(x)-x)+x   mode 1: (floor(x)-x)+x   mode 2: sign(x) (sign(NaN)=0) */
+int dlmcq_ste_value(const void* x, void* y, int64_t numel, int dtype, int mode, void* stream);
+/* utils.py:24-27 grad_scale value (s - s*g) + s*g for numel scales */
+int dlmcq_grad_scale_value(const float* s, float* out, int64_t numel, float g, void* stream);
+
 /* dequantize(): utils.py:5-6   y = codes*scale + offset */
 int dlmcq_dequantize(const void* codes, void* y, const dlmcq_layout* layout,
                      const float* scale, const float* offset, void* stream);
@@ -161,7 +167,8 @@ int dlmcq_rootq_wt_backward(const void* w, const void* dy, void* dw, float* grad
  * (NaN-propagating like torch.min/max).  Multi-GPU callers all-reduce `stats` between this
  * call and the *_finalize call. */
 #define DLMCQ_STATS_PER_CHANNEL 4
-int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* layout,
+#define DLMCQ_STATS_ABS_INPUT 1 /* take |x| first (quantize_minmax_pixel unsigned branch, ops.py:156-159) */
+int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* layout, int flags,
                     void* workspace, size_t workspace_bytes, void* stream);
 /* ops.py:20-34,121-140 (minmax_tensor / minmax_channel): signed: s = absmax/(2^(n-1)-1), off=0;
  * unsigned: s = (max-min)/(2^n-1), off = min (or 0 when allow_offset==0). */
