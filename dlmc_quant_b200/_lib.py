@@ -42,6 +42,7 @@ _LP, _QP = C.POINTER(Layout), C.POINTER(QParams)
 # name -> (restype, argtypes); mirrors include/dlmcq.h one to one
 SIGNATURES = {
     "dlmcq_version": (_I, []),
+    "dlmcq_selftest_fastdiv": (_I, [C.c_uint64, _I, _I, _I, _P, _P]),
     "dlmcq_status_string": (C.c_char_p, [_I]),
     "dlmcq_last_cuda_error": (C.c_char_p, []),
     "dlmcq_workspace_bytes": (_Z, [_LP]),

@@ -23,7 +23,7 @@ fq_fwd_flat(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, i
             const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
   using V = Vec<T>;
   using raw = typename V::raw;
-  const ChanParams p = make_params<FORM>(scale, offset, 0, g);
+  const ChanParams p = make_params<FORM>(scale, offset, 0, g, lo, hi);
   const int64_t nvec = n / V::N;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -34,8 +34,7 @@ fq_fwd_flat(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, i
   auto body = [&](const raw& r, int64_t idx) {
     float f[V::N], fy[V::N], fc[V::N];
     V::unpack(r, f);
-#pragma unroll
-    for (int e = 0; e < V::N; ++e) fq_elem<FORM>(f[e], p, lo, hi, fc[e], fy[e]);
+    fq_vec<FORM, V::N>(f, p, lo, hi, fc, fy);
     if (y) st_stream(yv + idx, V::pack(fy));
     if (codes) st_stream(cv + idx, V::pack(fc));
   };
@@ -64,7 +63,7 @@ template <int FORM, typename T>
 __global__ void __launch_bounds__(kThreads)
 fq_fwd_flat_unaligned(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, int64_t n,
                       const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
-  const ChanParams p = make_params<FORM>(scale, offset, 0, g);
+  const ChanParams p = make_params<FORM>(scale, offset, 0, g, lo, hi);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     float c, v;
@@ -104,7 +103,7 @@ __device__ __forceinline__ void finalize_flat(float* partials, int nblocks, floa
   }
 }
 
-template <int FORM, typename T, bool VECTOR>
+template <int FORM, typename T, bool VECTOR, bool WANT_OFF>
 __global__ void __launch_bounds__(kThreads, 4)
 fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t n,
             const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi,
@@ -112,7 +111,7 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
   using V = Vec<T>;
   using raw = typename V::raw;
   __shared__ __align__(16) float smem[128];
-  const ChanParams p = make_params<FORM>(scale, offset, 0, g);
+  const ChanParams p = make_params<FORM>(scale, offset, 0, g, lo, hi);
   float acc[2] = {0.f, 0.f};
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -125,8 +124,7 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
       float fx[V::N], fg[V::N], fo[V::N];
       V::unpack(rx, fx);
       V::unpack(rg, fg);
-#pragma unroll
-      for (int e = 0; e < V::N; ++e) fo[e] = fq_elem_bwd<FORM>(fx[e], fg[e], p, lo, hi, acc[0], acc[1]);
+      fq_vec_bwd<FORM, WANT_OFF, V::N>(fx, fg, p, lo, hi, fo, acc[0], acc[1]);
       st_stream(ov + idx, V::pack(fo));
     };
     for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
@@ -142,11 +140,11 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
     for (; i < nvec; i += stride) body(ld_stream(xv + i), ld_stream(gv + i), i);
     if (blockIdx.x == 0) {
       const int64_t t = nvec * V::N + threadIdx.x;
-      if (t < n) dx[t] = from_f32<T>(fq_elem_bwd<FORM>(to_f32<T>(x[t]), to_f32<T>(dy[t]), p, lo, hi, acc[0], acc[1]));
+      if (t < n) dx[t] = from_f32<T>(fq_elem_bwd<FORM, WANT_OFF>(to_f32<T>(x[t]), to_f32<T>(dy[t]), p, lo, hi, acc[0], acc[1]));
     }
   } else {
     for (; i < n; i += stride)
-      dx[i] = from_f32<T>(fq_elem_bwd<FORM>(to_f32<T>(x[i]), to_f32<T>(dy[i]), p, lo, hi, acc[0], acc[1]));
+      dx[i] = from_f32<T>(fq_elem_bwd<FORM, WANT_OFF>(to_f32<T>(x[i]), to_f32<T>(dy[i]), p, lo, hi, acc[0], acc[1]));
   }
   block_sum<2>(acc, smem);
   float* partials = ws_partials(ws);
@@ -171,7 +169,7 @@ fq_fwd_rows(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, R
   const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (item >= gm.rows * gm.segs) return;
   const int64_t row = item / gm.segs, seg = item - row * gm.segs;
-  const ChanParams p = make_params<FORM>(scale, offset, row % gm.channels, g);
+  const ChanParams p = make_params<FORM>(scale, offset, row % gm.channels, g, lo, hi);
   const int64_t beg = seg * gm.seg;
   const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
   const int64_t base = row * gm.inner + beg;
@@ -190,7 +188,7 @@ fq_bwd_rows(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
   if (item >= gm.rows * gm.segs) return;
   const int64_t row = item / gm.segs, seg = item - row * gm.segs;
   const int64_t ch = row % gm.channels;
-  const ChanParams p = make_params<FORM>(scale, offset, ch, g);
+  const ChanParams p = make_params<FORM>(scale, offset, ch, g, lo, hi);
   const int64_t beg = seg * gm.seg;
   const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
   const int64_t base = row * gm.inner + beg;
@@ -298,12 +296,10 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
     const int64_t per = vec ? Vec<T>::N : 1;
     int64_t tiles = (n / per + kThreads * kUnroll - 1) / (kThreads * kUnroll);
     const int grid = stream_grid(tiles, 6);
-    if (vec)
-      fq_bwd_flat<FORM, T, true><<<grid, kThreads, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
-          static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi, dscale, doffset, ws);
-    else
-      fq_bwd_flat<FORM, T, false><<<grid, kThreads, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy),
-          static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi, dscale, doffset, ws);
+    auto k = vec ? (doffset ? fq_bwd_flat<FORM, T, true, true> : fq_bwd_flat<FORM, T, true, false>)
+                 : (doffset ? fq_bwd_flat<FORM, T, false, true> : fq_bwd_flat<FORM, T, false, false>);
+    k<<<grid, kThreads, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), n,
+                                 qp->scale, qp->offset, qp->g, lo, hi, dscale, doffset, ws);
   } else {
     const RowGeom gm = make_geom(l);
     const int64_t items = gm.rows * gm.segs;

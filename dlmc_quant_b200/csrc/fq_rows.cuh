@@ -27,8 +27,7 @@ __device__ __forceinline__ void fwd_row_segment(const T* __restrict__ xr, T* __r
         if (h == 1 && !two) break;
         float f[V::N], fy[V::N], fc[V::N];
         V::unpack(h ? r1 : r0, f);
-#pragma unroll
-        for (int e = 0; e < V::N; ++e) fq_elem<FORM>(f[e], p, lo, hi, fc[e], fy[e]);
+        fq_vec<FORM, V::N>(f, p, lo, hi, fc, fy);
         if (yr) st_stream(reinterpret_cast<raw*>(yr) + j + 32 * h, V::pack(fy));
         if (cr) st_stream(reinterpret_cast<raw*>(cr) + j + 32 * h, V::pack(fc));
       }
@@ -68,15 +67,14 @@ __device__ __forceinline__ void bwd_row_segment(const T* __restrict__ xr, const 
         float fx[V::N], fg[V::N], fo[V::N];
         V::unpack(h ? x1 : x0, fx);
         V::unpack(h ? g1 : g0, fg);
-#pragma unroll
-        for (int e = 0; e < V::N; ++e) fo[e] = fq_elem_bwd<FORM>(fx[e], fg[e], p, lo, hi, as, ao);
+        fq_vec_bwd<FORM, true, V::N>(fx, fg, p, lo, hi, fo, as, ao);
         st_stream(reinterpret_cast<raw*>(dr) + j + 32 * h, V::pack(fo));
       }
     }
     done = nvec * V::N;
   }
   for (int64_t j = done + lane; j < len; j += 32)
-    dr[j] = from_f32<T>(fq_elem_bwd<FORM>(to_f32<T>(xr[j]), to_f32<T>(gr[j]), p, lo, hi, as, ao));
+    dr[j] = from_f32<T>(fq_elem_bwd<FORM, true>(to_f32<T>(xr[j]), to_f32<T>(gr[j]), p, lo, hi, as, ao));
   as = warp_sum(as);
   ao = warp_sum(ao);
 }

@@ -21,7 +21,7 @@ __device__ __forceinline__ int find_item(const int64_t* __restrict__ prefix, int
 
 template <int FORM>
 __device__ __forceinline__ ChanParams item_params(const dlmcq_group_item& it, int64_t ch) {
-  return make_params<FORM>(it.scale, it.offset, ch, it.g);
+  return make_params<FORM>(it.scale, it.offset, ch, it.g, static_cast<float>(it.lo), static_cast<float>(it.hi));
 }
 
 template <typename T>

@@ -428,16 +428,25 @@ l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict_
   const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (item >= gm.rows * gm.segs) return;
   const int64_t row = item / gm.segs, seg = item - row * gm.segs;
-  const ChanParams p = make_params<DLMCQ_FORM_A1>(scale, offset, row % gm.channels, 0.f);
+  const ChanParams p = make_params<DLMCQ_FORM_A1>(scale, offset, row % gm.channels, 0.f, lo, hi);
   const int64_t beg = seg * gm.seg;
   const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
   const T* xr = x + row * gm.inner + beg;
   float a = 0.f, b = 0.f;
+  auto add_vec = [&](const float (&f)[V::N]) {
+    float code[V::N], y[V::N];
+    fq_vec<DLMCQ_FORM_A1, V::N>(f, p, lo, hi, code, y);   // ops.py:78,206 quantize()
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) {
+      a += f[e] * code[e];                                 // (tensor * tensor_q).sum()
+      b += code[e] * code[e] + 1e-7f;                      // (tensor_q * tensor_q + 1e-7).sum()
+    }
+  };
   auto add = [&](float v) {
     float code, y;
-    fq_elem<DLMCQ_FORM_A1>(v, p, lo, hi, code, y);      // ops.py:78,206 quantize()
-    a += v * code;                                       // (tensor * tensor_q).sum()
-    b += code * code + 1e-7f;                            // (tensor_q * tensor_q + 1e-7).sum()
+    fq_elem<DLMCQ_FORM_A1>(v, p, lo, hi, code, y);
+    a += v * code;
+    b += code * code + 1e-7f;
   };
   int64_t fin = 0;
   if ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {
@@ -445,16 +454,14 @@ l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict_
     const raw* xv = reinterpret_cast<const raw*>(xr);
     for (int64_t j = lane; j < nvec; j += 64) {
       const bool two = (j + 32) < nvec;
-      raw r0 = ld_stream(xv + j), r1;
+      raw r0 = ld_stream(xv + j), r1 = r0;
       if (two) r1 = ld_stream(xv + j + 32);
       float f[V::N];
       V::unpack(r0, f);
-#pragma unroll
-      for (int e = 0; e < V::N; ++e) add(f[e]);
+      add_vec(f);
       if (two) {
         V::unpack(r1, f);
-#pragma unroll
-        for (int e = 0; e < V::N; ++e) add(f[e]);
+        add_vec(f);
       }
     }
     fin = nvec * V::N;

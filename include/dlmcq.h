@@ -83,6 +83,11 @@ typedef struct {
 } dlmcq_qparams;
 
 int dlmcq_version(void);
+/* Diagnostic: compares the kernels' residual-corrected division (x*r, fma, fma with r = RN(1/s))
+ * bitwise with IEEE division on blocks*256*per_thread*2 pseudo-random (x, s) pairs inside the
+ * fast-path domain; *mismatches_dev (zeroed by the caller) receives the count - expected 0. */
+int dlmcq_selftest_fastdiv(uint64_t seed, int blocks, int per_thread, int narrow,
+                           unsigned long long* mismatches_dev, void* stream);
 const char* dlmcq_status_string(int status);
 const char* dlmcq_last_cuda_error(void);
 

@@ -352,3 +352,16 @@ def test_full_size_properties(n):
     dxe, dse = torch.autograd.grad(R.fq_affine(xs, ss, off, 0, 15, g), (xs, ss), dy)
     assert torch.equal(dxe == 0, dx == 0)
     red_close(ds, dse, abs_sum=(dy.abs().sum() * 15 * g).reshape(1))
+
+
+def test_fast_division_is_ieee_exact():
+    """4.3e9 (x, s) pairs per domain: the fast path's 3-instruction division == __fdiv_rn bit for bit."""
+    import ctypes as C
+    from dlmc_quant_b200 import _lib
+    h = _lib.lib()
+    for narrow in (1, 0):
+        bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+        for rep in range(4):
+            _lib.check(h.dlmcq_selftest_fastdiv(2333 + rep, 148 * 8, 1775, narrow, C.c_void_p(bad.data_ptr()), None))
+        torch.cuda.synchronize()
+        assert int(bad) == 0, f"{int(bad)} quotients differ from IEEE division (narrow={narrow})"
