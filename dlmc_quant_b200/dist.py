@@ -1,0 +1,67 @@
+"""The path's only cross-GPU exchange: observer statistics and scale gradients, combined with
+torch.distributed collectives (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+Activations shard by batch and weights are replicated, so the fake-quant kernels themselves need no
+collective.  What must agree across ranks is O(channels) data:
+  * observer statistics  - [C,4] = (min, max, max|x|, sum|x|): MIN / MAX / SUM all-reduces,
+  * sweep partial sums   - 80 squared-error sums per tensor: SUM,
+  * scale gradients      - one flat buffer per step: SUM (DDP averages parameter grads itself).
+At world size 1 every function is the identity, i.e. bit-identical to the reference."""
+import torch
+import torch.distributed as dist
+
+__all__ = ["world_size", "sync_stats", "sync_sse", "allreduce_grads_"]
+
+_enabled = True
+
+
+def set_enabled(flag):
+    """Observers all-reduce their statistics only while enabled (default on)."""
+    global _enabled
+    _enabled = bool(flag)
+
+
+def world_size(group=None):
+    if not _enabled or not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group)
+
+
+def sync_stats(stats, group=None):
+    """stats [C,4] = (min, max, absmax, abssum) -> the statistics of the union of all ranks' tensors.
+    NaN statistics (NaN inputs) stay NaN: MIN/MAX of NaN is handled by reducing a flag with the sum."""
+    if world_size(group) == 1:
+        return stats
+    s = stats.clone()
+    lo = s[:, 0].contiguous()
+    hi = s[:, 1:3].contiguous()
+    sm = s[:, 3].contiguous()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)      # NaN on any rank -> NaN everywhere
+    nan = torch.isnan(sm)
+    out = torch.stack([lo, hi[:, 0], hi[:, 1], sm], dim=1)
+    if bool(nan.any()):
+        out[nan, :3] = float("nan")
+    return out
+
+
+def sync_sse(sse, rows, group=None):
+    """Sweep squared-error sums and the row count of l2_loss's mean, summed over ranks."""
+    w = world_size(group)
+    if w == 1:
+        return sse, rows
+    sse = sse.clone()
+    dist.all_reduce(sse, op=dist.ReduceOp.SUM, group=group)
+    return sse, rows * w
+
+
+def allreduce_grads_(flat, average=False, group=None):
+    """In-place SUM (or mean) of a flat scale-gradient buffer across ranks."""
+    w = world_size(group)
+    if w == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.div_(w)
+    return flat

@@ -1,0 +1,14 @@
+"""dlmc/quantization/scalar/RootQ/linear.py: RootQLinear."""
+import torch.nn.functional as F
+from torch.nn import Linear
+
+from .base import RootQBase
+
+
+class RootQLinear(RootQBase, Linear):
+    def __init__(self, *args, qconfig=None, **kwargs):
+        Linear.__init__(self, *args, **kwargs)
+        self.initialize(qconfig)
+
+    def _forward_func(self, input, weight):
+        return F.linear(input, weight, self.bias)

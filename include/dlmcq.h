@@ -84,8 +84,9 @@ typedef struct {
 
 int dlmcq_version(void);
 /* Diagnostic: compares the kernels' residual-corrected division (x*r, fma, fma with r = RN(1/s))
- * bitwise with IEEE division on blocks*256*per_thread*2 pseudo-random (x, s) pairs inside the
- * fast-path domain; *mismatches_dev (zeroed by the caller) receives the count - expected 0. */
+ * bitwise with IEEE division on blocks*256*per_thread*3 pseudo-random (x, s) pairs inside the
+ * fast-path domain (2^-40<=|s|<=2^40, |x|<=2^60; quotients below 2^-100 only have to stay below
+ * 2^-99); *mismatches_dev (zeroed by the caller) receives the count - expected 0. */
 int dlmcq_selftest_fastdiv(uint64_t seed, int blocks, int per_thread, int narrow,
                            unsigned long long* mismatches_dev, void* stream);
 const char* dlmcq_status_string(int status);

@@ -355,7 +355,7 @@ def test_full_size_properties(n):
 
 
 def test_fast_division_is_ieee_exact():
-    """4.3e9 (x, s) pairs per domain: the fast path's 3-instruction division == __fdiv_rn bit for bit."""
+    """6.4e9 (x, s) pairs per domain: the fast path's 3-instruction division == __fdiv_rn bit for bit."""
     import ctypes as C
     from dlmc_quant_b200 import _lib
     h = _lib.lib()
