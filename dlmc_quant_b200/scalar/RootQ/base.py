@@ -32,18 +32,23 @@ class RootQBase(Module):
                                                       qconfig['weight']['args']['n_bits'])
         self.in_min_val, self.in_max_val = get_qrange(qconfig['input']['args']['signed'],
                                                       qconfig['input']['args']['n_bits'])
-        self.register_parameter('in_scale', torch.nn.Parameter(torch.tensor(1.).float()))
+        dev = self.weight.device if isinstance(getattr(self, 'weight', None), torch.Tensor) else None
+
+        def scalar(v):
+            return torch.tensor(float(v), dtype=torch.float32, device=dev)
+
+        self.register_parameter('in_scale', torch.nn.Parameter(scalar(1.)))
         self.register_buffer('in_offset', None)
-        self.register_buffer('in_run_upper', torch.tensor(0.))
-        self.register_buffer('in_run_scale', torch.tensor(0.))
-        self.register_buffer('in_init_state', torch.tensor(0.))
-        self.register_parameter('wt_upper', torch.nn.Parameter(torch.tensor(2 ** 2 - 1).float()))
-        self.register_parameter('wt_lower', torch.nn.Parameter(torch.tensor((-1) * (2 ** 2)).float()))
-        self.register_parameter('wt_alpha', torch.nn.Parameter(torch.tensor(1. / 4).float()))
+        self.register_buffer('in_run_upper', scalar(0.))
+        self.register_buffer('in_run_scale', scalar(0.))
+        self.register_buffer('in_init_state', scalar(0.))
+        self.register_parameter('wt_upper', torch.nn.Parameter(scalar(2 ** 2 - 1)))
+        self.register_parameter('wt_lower', torch.nn.Parameter(scalar((-1) * (2 ** 2))))
+        self.register_parameter('wt_alpha', torch.nn.Parameter(scalar(1. / 4)))
         self.register_buffer('wt_offset', None)
-        self.register_buffer('wt_run_upper', torch.tensor(0.))
-        self.register_buffer('wt_run_lower', torch.tensor(0.))
-        self.register_buffer('wt_init_state', torch.tensor(0.))
+        self.register_buffer('wt_run_upper', scalar(0.))
+        self.register_buffer('wt_run_lower', scalar(0.))
+        self.register_buffer('wt_init_state', scalar(0.))
         self.momentum = qconfig['momentum']
         self._host_init = {'in': None, 'wt': None}
 

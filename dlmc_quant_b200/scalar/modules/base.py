@@ -50,12 +50,13 @@ class QBase(Module):
                                                       qconfig['weight']['args']['n_bits'])
         self.in_min_val, self.in_max_val = get_qrange(qconfig['input']['args']['signed'],
                                                       qconfig['input']['args']['n_bits'])
-        self.register_parameter('in_scale', torch.nn.Parameter(torch.ones(1)))
+        dev = self.weight.device if isinstance(getattr(self, 'weight', None), torch.Tensor) else None
+        self.register_parameter('in_scale', torch.nn.Parameter(torch.ones(1, device=dev)))
         self.register_buffer('in_offset', None)
-        self.register_buffer('in_init_state', torch.zeros(1))
-        self.register_parameter('wt_scale', torch.nn.Parameter(torch.ones(1)))
+        self.register_buffer('in_init_state', torch.zeros(1, device=dev))
+        self.register_parameter('wt_scale', torch.nn.Parameter(torch.ones(1, device=dev)))
         self.register_buffer('wt_offset', None)
-        self.register_buffer('wt_init_state', torch.zeros(1))
+        self.register_buffer('wt_init_state', torch.zeros(1, device=dev))
         self._host_init = {'in': None, 'wt': None}      # host mirror of *_init_state (None = unknown)
 
     def reset_qparams(self):
