@@ -297,8 +297,8 @@ def run_e2e(args, wl, rank, world, device):
     hds = torch.empty(wl.dscale.numel(), dtype=torch.float32).pin_memory()
 
     def step():
-        for i, (hx, hdy, hy, hdx, s, o, lo, hi, g) in enumerate(host):
-            hds[i] = hq.forward_backward(hx, hdy, hy, hdx, s, o, lo, hi, form=lib.FORM_AFFINE, g=g)
+        for i, (hx, hdy, hy, hdx, s, o, lo, hi, g) in enumerate(host):       # enqueue all layers, drain once
+            hq.forward_backward_async(hx, hdy, hy, hdx, hds[i:i + 1], s, o, lo, hi, form=lib.FORM_AFFINE, g=g)
         for w, (hx, hdy, hy, hdx) in zip(wl.wts, hw):
             w["x"].copy_(hx, non_blocking=True)
             w["dy"].copy_(hdy, non_blocking=True)
@@ -307,6 +307,7 @@ def run_e2e(args, wl, rank, world, device):
             hy.copy_(w["y"], non_blocking=True)
             hdx.copy_(w["dx"], non_blocking=True)
         hds[len(host):].copy_(wl.dscale[len(host):], non_blocking=True)
+        hq.synchronize()
         torch.cuda.synchronize()
 
     step()
@@ -327,7 +328,7 @@ def run_e2e(args, wl, rank, world, device):
     return {"value": round(wl.elems * world * steps * (BYTES_FWD + BYTES_BWD) / dt / 1e9, 2), "unit": UNIT,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
             "ms_per_step": round(dt / steps * 1e3, 2),
-            "api": "dlmcq_host_fq_forward_backward (activations) + H2D/grouped launch/D2H (weights)"}
+            "api": "dlmcq_host_fq_forward_backward_async per layer + one dlmcq_host_synchronize (activations); H2D/grouped launch/D2H (weights)"}
 
 
 # ------------------------------------------------------------------------------------------

@@ -71,6 +71,8 @@ SIGNATURES = {
     "dlmcq_fq_backward_grouped": (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),
     "dlmcq_host_staging_bytes": (_Z, [_L, _I]),
     "dlmcq_host_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
+    "dlmcq_host_fq_forward_backward_async": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
+    "dlmcq_host_synchronize": (_I, []),
 }
 
 

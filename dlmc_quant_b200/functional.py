@@ -444,24 +444,37 @@ class GroupedFakeQuant:
 
 class HostFakeQuant:
     """End-to-end path for HOST tensors (pinned memory): forward + backward with the H2D / D2H
-    copies pipelined against the kernels (dlmcq_host_fq_forward_backward)."""
+    copies pipelined against the kernels (dlmcq_host_fq_forward_backward[_async])."""
 
     def __init__(self, device, chunk_elems=1 << 22, dtype=torch.float32):
         self.device = torch.device(device)
         self.chunk = int(chunk_elems)
         self.code = F32 if dtype == torch.float32 else BF16
         n = _lib.lib().dlmcq_host_staging_bytes(self.chunk, self.code)
-        self.staging = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.staging = torch.zeros(n, dtype=torch.uint8, device=self.device)      # ticket counters start at 0
         self.nbytes = n
 
-    def forward_backward(self, x, dy, y, dx, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
-        """x, dy: host inputs; y, dx: host outputs (same shape/dtype).  Returns dscale (python float)."""
+    def _call(self, fn, x, dy, y, dx, ds_ptr, scale, offset, lo, hi, form, g):
         for t in (x, dy, y, dx):
             if t.is_cuda or not t.is_contiguous():
                 raise DlmcqError("host path takes contiguous CPU tensors")
-        ds = C.c_float(0.0)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().dlmcq_host_fq_forward_backward(
-                _ptr(x), _ptr(dy), _ptr(y), _ptr(dx), C.byref(ds), x.numel(), self.code, int(form), int(lo), int(hi),
-                float(g), float(scale), float(offset), _ptr(self.staging), self.nbytes, self.chunk))
+            _lib.check(fn(_ptr(x), _ptr(dy), _ptr(y), _ptr(dx), ds_ptr, x.numel(), self.code, int(form), int(lo),
+                          int(hi), float(g), float(scale), float(offset), _ptr(self.staging), self.nbytes, self.chunk))
+
+    def forward_backward(self, x, dy, y, dx, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
+        """x, dy: host inputs; y, dx: host outputs (same shape/dtype).  Returns dscale (python float)."""
+        ds = C.c_float(0.0)
+        self._call(_lib.lib().dlmcq_host_fq_forward_backward, x, dy, y, dx, C.cast(C.byref(ds), C.c_void_p), scale,
+                   offset, lo, hi, form, g)
         return ds.value
+
+    def forward_backward_async(self, x, dy, y, dx, dscale_out, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
+        """Enqueue only; `dscale_out` is a 1-element pinned float32 tensor that receives the scale
+        gradient.  Call synchronize() before reading any output."""
+        self._call(_lib.lib().dlmcq_host_fq_forward_backward_async, x, dy, y, dx, C.c_void_p(dscale_out.data_ptr()),
+                   scale, offset, lo, hi, form, g)
+
+    def synchronize(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_host_synchronize())

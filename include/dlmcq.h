@@ -242,9 +242,19 @@ int dlmcq_fq_backward_grouped(const dlmcq_group_item* items, const int64_t* unit
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------
  * Same arithmetic as dlmcq_fq_forward + dlmcq_fq_backward on a per-tensor-scale tensor that
  * lives in (pinned) HOST memory: x, dy in; y, dx and dscale out.  Chunks are pipelined
- * H2D -> kernel -> D2H over internal streams and a caller-provided device staging buffer.
- * Synchronous: returns when the host outputs are complete. */
+ * H2D -> kernels -> D2H over internal streams through a caller-provided device staging buffer
+ * (dlmcq_host_staging_bytes(); must be ZERO-initialised once by the caller).
+ *   _async      returns when the work is enqueued, so successive tensors (the layers of a model)
+ *               keep the copy engines busy; outputs (incl. *dscale_host, which should be pinned)
+ *               are valid after dlmcq_host_synchronize().
+ *   (plain)     = _async + dlmcq_host_synchronize(). */
 size_t dlmcq_host_staging_bytes(int64_t chunk_elems, int dtype);
+int dlmcq_host_fq_forward_backward_async(const void* x_host, const void* dy_host, void* y_host,
+                                         void* dx_host, float* dscale_host, int64_t numel, int dtype,
+                                         int form, int lo, int hi, float g, float scale, float offset,
+                                         void* device_staging, size_t staging_bytes,
+                                         int64_t chunk_elems);
+int dlmcq_host_synchronize(void);
 int dlmcq_host_fq_forward_backward(const void* x_host, const void* dy_host, void* y_host,
                                    void* dx_host, float* dscale_host, int64_t numel, int dtype,
                                    int form, int lo, int hi, float g, float scale, float offset,

@@ -290,3 +290,15 @@ def test_host_pipeline_matches_device_path():
     dxd, dsd = F().fq_backward(dev(x), dev(dy), s, o, 0, 15, 1, g=g)
     assert torch.equal(dx, dxd.cpu())
     assert abs(ds - float(dsd)) <= 1e-5 * abs(float(dsd)) + 1e-7
+    # async form: several tensors in flight, one synchronize
+    outs = []
+    for k in range(3):
+        yk, dxk, dsk = torch.empty(n).pin_memory(), torch.empty(n).pin_memory(), torch.zeros(1).pin_memory()
+        hq.forward_backward_async(x, dy, yk, dxk, dsk, 0.25 + 0.05 * k, 0.0, 0, 15, form=1, g=g)
+        outs.append((yk, dxk, dsk, 0.25 + 0.05 * k))
+    hq.synchronize()
+    for yk, dxk, dsk, sk in outs:
+        sd = dev(torch.tensor([sk]))
+        assert torch.equal(yk, F().fq_forward(dev(x), sd, o, 0, 15, 1, g=g).cpu())
+        dxd, dsd = F().fq_backward(dev(x), dev(dy), sd, o, 0, 15, 1, g=g)
+        assert torch.equal(dxk, dxd.cpu()) and abs(float(dsk) - float(dsd)) <= 1e-5 * abs(float(dsd)) + 1e-7
