@@ -287,11 +287,18 @@ def run_e2e(args, wl, rank, world, device):
     F, lib = wl.F, wl.lib
     steps = max(1, min(args.steps, args.e2e_steps))
     hq = F.HostFakeQuant(device, chunk_elems=1 << 22)
+    # One pinned buffer set sized to the largest layer, reused by all 54 layers: the bytes that cross PCIe
+    # per step are exactly the workload's (every layer's x, dy in and y, dx out), while host memory stays
+    # at 4 x 411 MB per rank instead of 4 x 5.5 GB (8 ranks would not fit the box's RAM otherwise).
+    nmax = max(a["n"] for a in wl.acts)
+    big = max(wl.acts, key=lambda a: a["n"])
+    hx_all, hdy_all = big["x"].reshape(-1).cpu().pin_memory(), big["dy"].reshape(-1).cpu().pin_memory()
+    hy_all, hdx_all = torch.empty(nmax).pin_memory(), torch.empty(nmax).pin_memory()
     host = []
-    for a in wl.acts:       # one pinned buffer set per layer; contents copied from the device tensors
-        hx, hdy = a["x"].cpu().pin_memory(), a["dy"].cpu().pin_memory()
-        host.append((hx, hdy, torch.empty_like(hx).pin_memory(), torch.empty_like(hx).pin_memory(),
-                     float(a["scale"]), float(a["off"]), a["qp"].lo, a["qp"].hi, a["qp"].g))
+    for a in wl.acts:
+        n = a["n"]
+        host.append((hx_all[:n], hdy_all[:n], hy_all[:n], hdx_all[:n], float(a["scale"]), float(a["off"]),
+                     a["qp"].lo, a["qp"].hi, a["qp"].g))
     hw = [(w["x"].cpu().pin_memory(), w["dy"].cpu().pin_memory(), torch.empty_like(w["x"], device="cpu").pin_memory(),
            torch.empty_like(w["x"], device="cpu").pin_memory()) for w in wl.wts]
     hds = torch.empty(wl.dscale.numel(), dtype=torch.float32).pin_memory()
@@ -327,7 +334,7 @@ def run_e2e(args, wl, rank, world, device):
     d2h = 2 * 4 * wl.elems + 4 * wl.dscale.numel()
     return {"value": round(wl.elems * world * steps * (BYTES_FWD + BYTES_BWD) / dt / 1e9, 2), "unit": UNIT,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-            "ms_per_step": round(dt / steps * 1e3, 2),
+            "ms_per_step": round(dt / steps * 1e3, 2), "host_buffers": "pinned, one set sized to the largest layer, reused by all layers",
             "api": "dlmcq_host_fq_forward_backward_async per layer + one dlmcq_host_synchronize (activations); H2D/grouped launch/D2H (weights)"}
 
 
@@ -422,7 +429,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch of 3x224x224 images")
+    ap.add_argument("--batch", type=int, default=128,
+                    help="per-GPU batch of 3x224x224 images (the reference harness runs 256 on 2 GPUs: benchmark.yaml:8,38)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")

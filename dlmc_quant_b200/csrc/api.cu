@@ -1,4 +1,5 @@
 // api.cu - library-level entry points: version, status strings, device query.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -24,6 +25,14 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DLMCQ_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
 }
 
 }  // namespace dlmcq

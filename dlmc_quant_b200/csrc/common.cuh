@@ -191,6 +191,29 @@ inline RowGeom make_geom(int64_t outer, int64_t channels, int64_t inner) {
   return gm;
 }
 
+// Programmatic dependent launch: consecutive kernels of one stream (the per-layer quantizer launches of a
+// training step) hide their launch latency behind the predecessor's tail.  Every kernel launched this way
+// executes pdl_wait() before its first global-memory access - it then sees all of the predecessor's
+// writes - and pdl_trigger() right away so that its own successor can be staged early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Persistent grid for a streaming kernel over `work_items` block-tiles.

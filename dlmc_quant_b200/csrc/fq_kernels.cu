@@ -23,6 +23,8 @@ fq_fwd_flat(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, i
             const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
   using V = Vec<T>;
   using raw = typename V::raw;
+  pdl_wait();
+  pdl_trigger();
   const ChanParams p = make_params<FORM>(scale, offset, 0, g, lo, hi);
   const int64_t nvec = n / V::N;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -111,6 +113,8 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
   using V = Vec<T>;
   using raw = typename V::raw;
   __shared__ __align__(16) float smem[128];
+  pdl_wait();
+  pdl_trigger();
   const ChanParams p = make_params<FORM>(scale, offset, 0, g, lo, hi);
   float acc[2] = {0.f, 0.f};
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -266,8 +270,10 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
   if (l->channels == 1) {
     if (aligned16(x) && aligned16(y) && aligned16(codes)) {
       const int64_t tiles = (n / Vec<T>::N + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-      fq_fwd_flat<FORM, T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
-          static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale, qp->offset, qp->g, lo, hi);
+      cudaError_t e = launch_pdl(fq_fwd_flat<FORM, T>, dim3(stream_grid(tiles, 8)), dim3(kThreads), 0, st,
+                                 static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale,
+                                 qp->offset, qp->g, lo, hi);
+      if (e != cudaSuccess) return set_cuda_error(e);
     } else {
       const int64_t tiles = (n + kThreads - 1) / kThreads;
       fq_fwd_flat_unaligned<FORM, T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
@@ -298,8 +304,10 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
     const int grid = stream_grid(tiles, 6);
     auto k = vec ? (doffset ? fq_bwd_flat<FORM, T, true, true> : fq_bwd_flat<FORM, T, true, false>)
                  : (doffset ? fq_bwd_flat<FORM, T, false, true> : fq_bwd_flat<FORM, T, false, false>);
-    k<<<grid, kThreads, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), n,
-                                 qp->scale, qp->offset, qp->g, lo, hi, dscale, doffset, ws);
+    cudaError_t e = launch_pdl(k, dim3(grid), dim3(kThreads), 0, st, static_cast<const T*>(x),
+                               static_cast<const T*>(dy), static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi,
+                               dscale, doffset, ws);
+    if (e != cudaSuccess) return set_cuda_error(e);
   } else {
     const RowGeom gm = make_geom(l);
     const int64_t items = gm.rows * gm.segs;

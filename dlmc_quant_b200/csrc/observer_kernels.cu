@@ -212,10 +212,19 @@ __device__ __forceinline__ void sweep_candidate(int i, float lo, float hi, float
   sc = (c_hi - c_lo) / qmax;
   zp = rintf((-c_lo) / sc);
 }
-// squared error of one element under one candidate (ops.py:59-61)
+// squared error of one element under one candidate (ops.py:59-61), literal chain
 __device__ __forceinline__ float sweep_err2(float x, float sc, float zp, float qmax) {
   float q = rintf(x / sc) + zp;
   q = (clamp_ref(q, 0.f, qmax) - zp) * sc;
+  const float d = q - x;
+  return d * d;
+}
+// same value on the fast-path domain (|x| <= 2^60, candidate scale in [2^-40, 2^40]): residual-corrected
+// division by the candidate's hoisted reciprocal, NaN-propagating min/max clamp (a zero's sign is erased
+// by the following "- zp").  11 instructions instead of ~22: the sweep is fp32-issue-bound.
+__device__ __forceinline__ float sweep_err2_fast(float x, const FastDiv& fd, float zp, float qmax) {
+  float q = rintf(fast_div(x, fd)) + zp;
+  q = (clamp_fast(q, 0.f, qmax) - zp) * fd.s;
   const float d = q - x;
   return d * d;
 }
@@ -230,12 +239,16 @@ sweep_tensor_kernel(const T* __restrict__ x, int64_t n, const float* __restrict_
   using raw = typename V::raw;
   constexpr int NV = kSweepElems / V::N >= 1 ? kSweepElems / V::N : 1;   // vectors per thread per tile
   constexpr int NE = NV * V::N;
-  __shared__ float c_sc[kNC], c_zp[kNC];
+  __shared__ float c_sc[kNC], c_zp[kNC], c_rc[kNC];
+  __shared__ int c_ok[kNC];
   __shared__ float w_acc[kThreads / 32][kNC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < kNC) {
     const float lo = allow_offset ? stats[0] : 0.f;
     sweep_candidate(threadIdx.x, lo, stats[1], qmax, c_sc[threadIdx.x], c_zp[threadIdx.x]);
+    const FastDiv fd = make_fastdiv(c_sc[threadIdx.x]);
+    c_rc[threadIdx.x] = fd.r;
+    c_ok[threadIdx.x] = fd.ok ? 1 : 0;
   }
   for (int k = threadIdx.x; k < (kThreads / 32) * kNC; k += blockDim.x) (&w_acc[0][0])[k] = 0.f;
   __syncthreads();
@@ -253,12 +266,23 @@ sweep_tensor_kernel(const T* __restrict__ x, int64_t n, const float* __restrict_
 #pragma unroll
       for (int e = 0; e < V::N; ++e) f[v * V::N + e] = tmp[e];
     }
+    float m = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) m = fmaxf(m, fabsf(f[e]));
+    const bool tile_ok = m <= kFastDivMaxX;      // inf / huge values: literal chain for this thread's tile
 #pragma unroll 2
     for (int c = 0; c < kNC; ++c) {
       const float sc = c_sc[c], zp = c_zp[c];
       float a = 0.f;
+      if (tile_ok && c_ok[c]) {
+        FastDiv fd;
+        fd.s = sc; fd.r = c_rc[c]; fd.ok = true;
 #pragma unroll
-      for (int e = 0; e < NE; ++e) a += sweep_err2(f[e], sc, zp, qmax);
+        for (int e = 0; e < NE; ++e) a += sweep_err2_fast(f[e], fd, zp, qmax);
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) a += sweep_err2(f[e], sc, zp, qmax);
+      }
       a = warp_sum(a);
       if (lane == 0) w_acc[warp][c] += a;
     }
@@ -390,6 +414,7 @@ sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, f
   }
   mn = warp_min(mn); mx = warp_max(mx); am = warp_max(am);
   nan = __any_sync(0xffffffffu, nan);
+  const bool row_fast = am <= kFastDivMaxX;      // no inf / huge value in the row
   if (nan) mn = mx = am = NAN;
   float cur_scale, cur_off;
   if (is_signed) { cur_scale = am / signed_div; cur_off = 0.f; }           // ops.py:125-127
@@ -401,7 +426,12 @@ sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, f
     float sc, zp;
     sweep_candidate(i, min_v, max_v, qmax, sc, zp);                        // ops.py:179-185
     float a = 0.f;
-    for (int64_t j = lane; j < inner; j += 32) a += sweep_err2(at(j), sc, zp, qmax);
+    const FastDiv fd = make_fastdiv(sc);
+    if (fd.ok && row_fast) {
+      for (int64_t j = lane; j < inner; j += 32) a += sweep_err2_fast(at(j), fd, zp, qmax);
+    } else {
+      for (int64_t j = lane; j < inner; j += 32) a += sweep_err2(at(j), sc, zp, qmax);
+    }
     a = warp_sum(a);
     if (best > a) {                                                        // ops.py:191-194
       cur_scale = sc;
@@ -472,40 +502,63 @@ l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict_
   if (lane == 0) { part[2 * item] = a; part[2 * item + 1] = b; }
 }
 
-// single CTA: new scale per channel, convergence measure, done flag (ops.py:79-81,207-210)
+// single CTA: new scale per channel, convergence measure, done flag (ops.py:79-81,207-210).
+// One warp per channel with the lanes striding over that channel's segments (per-tensor: the whole
+// CTA strides over the segments of the single channel).
 __global__ void __launch_bounds__(kThreads)
 l2norm_finalize_kernel(const float* __restrict__ part, RowGeom gm, float* __restrict__ scale, float* __restrict__ diff,
                        int32_t* __restrict__ done, int32_t* __restrict__ iters) {
-  __shared__ double sh[2][kThreads / 32];
+  __shared__ double sh[4][kThreads / 32];
   if (*done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kThreads / 32;
   double num = 0.0, den = 0.0;
   float single_new = 0.f, single_old = 0.f;
-  for (int64_t c = threadIdx.x; c < gm.channels; c += blockDim.x) {
+  if (gm.channels == 1) {
     double a = 0.0, b = 0.0;
-    for (int64_t sg = 0; sg < gm.segs; ++sg) {
-      a += part[2 * (c * gm.segs + sg)];
-      b += part[2 * (c * gm.segs + sg) + 1];
+    for (int64_t sg = threadIdx.x; sg < gm.segs; sg += blockDim.x) {
+      a += part[2 * sg];
+      b += part[2 * sg + 1];
     }
-    const float s_old = scale[c];
-    const float s_new = static_cast<float>(a) / static_cast<float>(b);
-    scale[c] = s_new;
-    const float d = s_new - s_old;
-    num += static_cast<double>(d * d);
-    den += static_cast<double>(s_old * s_old);
-    single_new = s_new; single_old = s_old;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { sh[2][warp] = a; sh[3][warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double ta = 0.0, tb = 0.0;
+      for (int w = 0; w < NW; ++w) { ta += sh[2][w]; tb += sh[3][w]; }
+      single_old = scale[0];
+      single_new = static_cast<float>(ta) / static_cast<float>(tb);
+      scale[0] = single_new;
+    }
+  } else {
+    for (int64_t c = warp; c < gm.channels; c += NW) {
+      double a = 0.0, b = 0.0;
+      for (int64_t sg = lane; sg < gm.segs; sg += 32) {
+        a += part[2 * (c * gm.segs + sg)];
+        b += part[2 * (c * gm.segs + sg) + 1];
+      }
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) {
+        const float s_old = scale[c];
+        const float s_new = static_cast<float>(a) / static_cast<float>(b);
+        scale[c] = s_new;
+        const float d = s_new - s_old;
+        num += static_cast<double>(d * d);
+        den += static_cast<double>(s_old * s_old);
+      }
+    }
+    if (lane == 0) { sh[0][warp] = num; sh[1][warp] = den; }
+    __syncthreads();
   }
-  num = warp_sum(num);
-  den = warp_sum(den);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][warp] = num; sh[1][warp] = den; }
-  __syncthreads();
   if (threadIdx.x == 0) {
     float df;
     if (gm.channels == 1) {
       df = fabsf(single_new - single_old) / single_old;                 // ops.py:80
     } else {
       double tn = 0.0, td = 0.0;
-      for (int w = 0; w < kThreads / 32; ++w) { tn += sh[0][w]; td += sh[1][w]; }
+      for (int w = 0; w < NW; ++w) { tn += sh[0][w]; td += sh[1][w]; }
       df = sqrtf(static_cast<float>(tn)) / sqrtf(static_cast<float>(td));   // ops.py:209
     }
     diff[0] = df;
