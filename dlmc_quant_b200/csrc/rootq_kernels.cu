@@ -88,14 +88,75 @@ __device__ __forceinline__ float rq_act_bwd(float x, float dy, float rs, float u
   return ((nl > 0.f) || clipped_hi) ? 0.f : dy;
 }
 
+// Fast path of the activation chain on vectors (same results; see fq_math.cuh for the argument):
+// relu as max.NaN (the sign of a zero is erased by the following add), x/s by the hoisted reciprocal with
+// residual correction, round_pass(v) == rint(v)+0 for finite v.  Out-of-domain vectors use the literal chain.
+template <int N>
+__device__ __forceinline__ void rq_act_fwd_vec(const float (&x)[N], float rs, float up, const FastDiv& fd,
+                                               float (&y)[N]) {
+  if (fd.ok) {
+    float xq[N];
+    float m = 0.f;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      const float x1 = x[e] + max_nan(0.f - x[e], 0.f);
+      xq[e] = x1 - max_nan(x1 - up, 0.f);
+      m = fmaxf(m, fabsf(xq[e]));
+    }
+    if (m <= kFastDivMaxX) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) y[e] = (rintf(fast_div(xq[e], fd)) + 0.f) * rs;
+      return;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < N; ++e) y[e] = rq_act_fwd(x[e], rs, up);
+}
+template <int N>
+__device__ __forceinline__ void rq_act_bwd_vec(const float (&x)[N], const float (&dy)[N], float rs, float up, float q,
+                                               const FastDiv& fd, float (&dx)[N], float& acc) {
+  if (fd.ok) {
+    float xq[N], ov[N], nl[N];
+    float m = 0.f;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      nl[e] = 0.f - x[e];
+      const float x1 = x[e] + max_nan(nl[e], 0.f);
+      ov[e] = x1 - up;
+      xq[e] = x1 - max_nan(ov[e], 0.f);
+      m = fmaxf(m, fabsf(xq[e]));
+    }
+    if (m <= kFastDivMaxX) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float v = fast_div(xq[e], fd);
+        const float I = rintf(v) + 0.f;
+        const bool hi_clip = ov[e] > 0.f;
+        acc = __fmaf_rn(dy[e], (I - v) + (hi_clip ? q : 0.f), acc);
+        dx[e] = ((nl[e] > 0.f) || hi_clip) ? 0.f : dy[e];
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < N; ++e) dx[e] = rq_act_bwd(x[e], dy[e], rs, up, q, acc);
+}
+
 struct RqW {
   float U, L, delta, alpha, k, q, half_delta;
+  FastDiv fd;
 };
+// (c - L) / delta with the hoisted reciprocal when in the fast domain (uniform divisor delta)
+struct RqWDiv { FastDiv fd; };
+__device__ __forceinline__ float rq_div_delta(float num, float delta, const FastDiv& fd) {
+  return (fd.ok && fabsf(num) <= kFastDivMaxX) ? fast_div(num, fd) : num / delta;
+}
 __device__ __forceinline__ RqW load_rqw(const float* st) {
   RqW p;
   p.U = st[RW_U]; p.L = st[RW_L]; p.delta = st[RW_DELTA]; p.alpha = st[RW_ALPHA]; p.q = st[RW_Q];
   p.k = 2.f / p.delta;                               // function.py:29
   p.half_delta = p.delta * 0.5f;
+  p.fd = make_fastdiv(p.delta);
   return p;
 }
 // weight forward value: base.py:146-155.  sign(pow(b, alpha)*sg) == sign(z) because b >= 1e-5 > 0,
@@ -103,7 +164,7 @@ __device__ __forceinline__ RqW load_rqw(const float* st) {
 __device__ __forceinline__ float rq_wt_fwd(float w, const RqW& p) {
   const float x1 = w + relu_ref(p.L - w);
   const float c = x1 - relu_ref(x1 - p.U);
-  const float t = (c - p.L) / p.delta;
+  const float t = rq_div_delta(c - p.L, p.delta, p.fd);
   const float fl = floorf(t);
   const float I = (fl - t) + t;                      // floor_pass value, utils.py:34-37
   const float mi = (I + 0.5f) * p.delta + p.L;       // base.py:149
@@ -121,7 +182,7 @@ __device__ __forceinline__ float rq_wt_bwd(float w, float dy, const RqW& p, floa
   const float dcw = (m_lo || m_hi) ? 0.f : 1.f;
   const float cu = m_hi ? 1.f : 0.f;
   const float cl = (m_lo && !m_hi) ? 1.f : 0.f;
-  const float t = (c - p.L) / p.delta;
+  const float t = rq_div_delta(c - p.L, p.delta, p.fd);
   const float fl = floorf(t);
   const float I = (fl - t) + t;
   const float mi = (I + 0.5f) * p.delta + p.L;
@@ -153,8 +214,11 @@ rootq_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, const fl
   using raw = typename V::raw;
   RqW pw = {};
   float rs = 0.f, up = 0.f;
+  FastDiv fd = {};
+  pdl_wait();
+  pdl_trigger();
   if constexpr (WEIGHT) pw = load_rqw(state);
-  else { rs = state[RA_SCALE]; up = state[RA_UPPER]; }
+  else { rs = state[RA_SCALE]; up = state[RA_UPPER]; fd = make_fastdiv(rs); }
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -166,8 +230,12 @@ rootq_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, const fl
     auto body = [&](const raw& r, int64_t idx) {
       float a[V::N], o[V::N];
       V::unpack(r, a);
+      if constexpr (WEIGHT) {
 #pragma unroll
-      for (int e = 0; e < V::N; ++e) o[e] = f(a[e]);
+        for (int e = 0; e < V::N; ++e) o[e] = f(a[e]);
+      } else {
+        rq_act_fwd_vec<V::N>(a, rs, up, fd, o);
+      }
       st_stream(yv + idx, V::pack(o));
     };
     for (; i + (kRqUnroll - 1) * stride < nvec; i += kRqUnroll * stride) {
@@ -196,8 +264,11 @@ rootq_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restric
   __shared__ __align__(16) float smem[192];
   RqW pw = {};
   float rs = 0.f, up = 0.f, qa = 0.f;
+  FastDiv fd = {};
+  pdl_wait();
+  pdl_trigger();
   if constexpr (WEIGHT) pw = load_rqw(state);
-  else { rs = state[RA_SCALE]; up = state[RA_UPPER]; qa = state[RA_Q]; }
+  else { rs = state[RA_SCALE]; up = state[RA_UPPER]; qa = state[RA_Q]; fd = make_fastdiv(rs); }
   float acc[3] = {0.f, 0.f, 0.f};
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
                      reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
@@ -215,8 +286,12 @@ rootq_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restric
       float a[V::N], b[V::N], o[V::N];
       V::unpack(rx, a);
       V::unpack(rg, b);
+      if constexpr (WEIGHT) {
 #pragma unroll
-      for (int e = 0; e < V::N; ++e) o[e] = f(a[e], b[e]);
+        for (int e = 0; e < V::N; ++e) o[e] = f(a[e], b[e]);
+      } else {
+        rq_act_bwd_vec<V::N>(a, b, rs, up, qa, fd, o, acc[0]);
+      }
       st_stream(ov + idx, V::pack(o));
     };
     constexpr int U = WEIGHT ? 2 : kRqUnroll;
@@ -309,15 +384,16 @@ static int rootq_forward(const void* x, void* y, int64_t n, int dtype, const flo
   if (!x || !y || !state || n < 0) return DLMCQ_EINVAL;
   if (n == 0) return DLMCQ_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
   if (dtype == DLMCQ_F32)
-    rootq_fwd_kernel<float, WEIGHT><<<rq_grid(n, 4, 8), kThreads, 0, st>>>(static_cast<const float*>(x),
-                                                                           static_cast<float*>(y), n, state);
+    e = launch_pdl(rootq_fwd_kernel<float, WEIGHT>, dim3(rq_grid(n, 4, 8)), dim3(kThreads), 0, st,
+                   static_cast<const float*>(x), static_cast<float*>(y), n, state);
   else if (dtype == DLMCQ_BF16)
-    rootq_fwd_kernel<__nv_bfloat16, WEIGHT><<<rq_grid(n, 8, 8), kThreads, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, state);
+    e = launch_pdl(rootq_fwd_kernel<__nv_bfloat16, WEIGHT>, dim3(rq_grid(n, 8, 8)), dim3(kThreads), 0, st,
+                   static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, state);
   else
     return DLMCQ_EINVAL;
-  DLMCQ_LAUNCH_CHECK();
+  if (e != cudaSuccess) return set_cuda_error(e);
   return DLMCQ_OK;
 }
 
@@ -327,16 +403,18 @@ static int rootq_backward(const void* x, const void* dy, void* dx, float* grads,
   if (!x || !dy || !dx || !grads || !state || !ws || n < 0) return DLMCQ_EINVAL;
   if (ws_bytes < dlmcq_workspace_bytes(nullptr)) return DLMCQ_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
   if (dtype == DLMCQ_F32)
-    rootq_bwd_kernel<float, WEIGHT><<<rq_grid(n, 4, 6), kThreads, 0, st>>>(
-        static_cast<const float*>(x), static_cast<const float*>(dy), static_cast<float*>(dx), n, state, grads, ws);
+    e = launch_pdl(rootq_bwd_kernel<float, WEIGHT>, dim3(rq_grid(n, 4, 6)), dim3(kThreads), 0, st,
+                   static_cast<const float*>(x), static_cast<const float*>(dy), static_cast<float*>(dx), n, state,
+                   grads, ws);
   else if (dtype == DLMCQ_BF16)
-    rootq_bwd_kernel<__nv_bfloat16, WEIGHT><<<rq_grid(n, 8, 6), kThreads, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx),
-        n, state, grads, ws);
+    e = launch_pdl(rootq_bwd_kernel<__nv_bfloat16, WEIGHT>, dim3(rq_grid(n, 8, 6)), dim3(kThreads), 0, st,
+                   static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
+                   static_cast<__nv_bfloat16*>(dx), n, state, grads, ws);
   else
     return DLMCQ_EINVAL;
-  DLMCQ_LAUNCH_CHECK();
+  if (e != cudaSuccess) return set_cuda_error(e);
   return DLMCQ_OK;
 }
 
