@@ -158,10 +158,11 @@ class Workload:
         self.wt_elems = sum(w["x"].numel() for w in self.wts)
         self.elems = self.act_elems + self.wt_elems
         self.ws = torch.zeros(self.h.dlmcq_workspace_bytes(None), dtype=torch.uint8, device=device)
+        self.deferred = F.DeferredScaleGrads(device, len(self.acts))
         self.grp_f, self.grp_b = F.GroupedFakeQuant(device), F.GroupedFakeQuant(device)
         self.wf = [dict(w) for w in self.wts]
         self.wb = [dict(w, y=w["dx"]) for w in self.wts]
-        self.launches_per_step = 2 * len(self.acts) + 1 + 2
+        self.launches_per_step = 2 * len(self.acts) + 1 + 1 + 2      # + finalize_many + grouped fwd/bwd/finalize
 
     # -- eager launches (also what gets captured) ------------------------------------------
     def _stream(self):
@@ -173,10 +174,13 @@ class Workload:
             self.lib.check(f(a["x"].data_ptr(), a["y"].data_ptr(), None, C.byref(a["lay"]), C.byref(a["qp"]), st))
 
     def bwd_acts(self):
-        st, f, ws, n = self._stream(), self.h.dlmcq_fq_backward, self.ws.data_ptr(), self.ws.numel()
-        for a in self.acts:
-            self.lib.check(f(a["x"].data_ptr(), a["dy"].data_ptr(), a["dx"].data_ptr(), a["ds"].data_ptr(), None,
-                             C.byref(a["lay"]), C.byref(a["qp"]), ws, n, st))
+        """54 backward launches leave their per-CTA partial sums behind; one batched launch reduces all 54
+        scale gradients (dlmcq_fq_backward_partials + dlmcq_fq_finalize_many)."""
+        st, f = self._stream(), self.h.dlmcq_fq_backward_partials
+        for i, a in enumerate(self.acts):
+            self.lib.check(f(a["x"].data_ptr(), a["dy"].data_ptr(), a["dx"].data_ptr(), C.byref(a["lay"]),
+                             C.byref(a["qp"]), self.deferred.partials[i].data_ptr(), st))
+        self.deferred.finalize([a["ds"] for a in self.acts])
 
     def weights(self):
         self.grp_f.forward(self.wf)

@@ -30,6 +30,10 @@ class GroupItem(C.Structure):
                 ("form", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32), ("g", C.c_float)]
 
 
+class FinalizeItem(C.Structure):
+    _fields_ = [("partials", C.c_void_p), ("dscale", C.c_void_p)]
+
+
 class DlmcqError(RuntimeError):
     pass
 
@@ -48,6 +52,9 @@ SIGNATURES = {
     "dlmcq_workspace_bytes": (_Z, [_LP]),
     "dlmcq_fq_forward": (_I, [_P, _P, _P, _LP, _QP, _P]),
     "dlmcq_fq_backward": (_I, [_P, _P, _P, _P, _P, _LP, _QP, _P, _Z, _P]),
+    "dlmcq_fq_partials_floats": (_Z, []),
+    "dlmcq_fq_backward_partials": (_I, [_P, _P, _P, _LP, _QP, _P, _P]),
+    "dlmcq_fq_finalize_many": (_I, [_P, _I, _P]),
     "dlmcq_dequantize": (_I, [_P, _P, _LP, _P, _P, _P]),
     "dlmcq_ste_value": (_I, [_P, _P, _L, _I, _I, _P]),
     "dlmcq_grad_scale_value": (_I, [_P, _P, _L, _F, _P]),

@@ -140,15 +140,17 @@ __device__ __forceinline__ void block_sum(float (&v)[NQ], float* smem /* >= NQ*3
 // that draws the last ticket reduces all partials in a fixed order.  The ticket counter is
 // reset by that block, so a workspace that was zeroed once stays reusable.
 __device__ __forceinline__ bool take_last_ticket(unsigned int* counter, unsigned int nblocks) {
+  // Call after thread 0 has written this block's partials.  Only thread 0 fences: the fence orders ITS
+  // partial-sum stores before the ticket; making all 256 threads fence would stall the whole block until
+  // every streaming store of the block has been acknowledged.
   __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned int t = atomicAdd(counter, 1u);
     is_last = (t == nblocks - 1);
   }
   __syncthreads();
-  if (is_last) __threadfence();
+  if (is_last) __threadfence();   // acquire side: the other blocks' partials are visible below
   return is_last;
 }
 

@@ -105,7 +105,10 @@ __device__ __forceinline__ void finalize_flat(float* partials, int nblocks, floa
   }
 }
 
-template <int FORM, typename T, bool VECTOR, bool WANT_OFF>
+// DEFER: leave the per-CTA partials in `ws` ([0]=#CTAs, [1]=chain factor, then (ds, doff) pairs) for
+// dlmcq_fq_finalize_many instead of finalising in the last CTA - the ticket + serial finalisation costs
+// ~3.4 us per launch (measured, profiles/README.md), a once-per-step batched finalisation ~4 us in total.
+template <int FORM, typename T, bool VECTOR, bool WANT_OFF, bool DEFER>
 __global__ void __launch_bounds__(kThreads, 4)
 fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t n,
             const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi,
@@ -151,6 +154,18 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
       dx[i] = from_f32<T>(fq_elem_bwd<FORM, WANT_OFF>(to_f32<T>(x[i]), to_f32<T>(dy[i]), p, lo, hi, acc[0], acc[1]));
   }
   block_sum<2>(acc, smem);
+  if (DEFER) {
+    float* out = static_cast<float*>(ws);
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0) {
+        out[0] = __int_as_float(static_cast<int>(gridDim.x));
+        out[1] = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? g : 1.f;
+      }
+      out[2 + 2 * blockIdx.x] = acc[0];
+      out[3 + 2 * blockIdx.x] = acc[1];
+    }
+    return;
+  }
   float* partials = ws_partials(ws);
   if (threadIdx.x == 0) {
     partials[2 * blockIdx.x] = acc[0];
@@ -293,17 +308,19 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
 
 template <int FORM, typename T>
 static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, float* doffset, const dlmcq_layout* l,
-                      const dlmcq_qparams* qp, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      const dlmcq_qparams* qp, void* ws, size_t ws_bytes, cudaStream_t st, bool defer = false) {
   const int64_t n = l->outer * l->channels * l->inner;
   const float lo = static_cast<float>(qp->lo), hi = static_cast<float>(qp->hi);
-  if (ws_bytes < dlmcq_workspace_bytes(l)) return DLMCQ_EWORKSPACE;
+  if (!defer && ws_bytes < dlmcq_workspace_bytes(l)) return DLMCQ_EWORKSPACE;
+  if (defer && l->channels != 1) return DLMCQ_EUNSUPPORTED;
   if (l->channels == 1) {
     const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx);
     const int64_t per = vec ? Vec<T>::N : 1;
     int64_t tiles = (n / per + kThreads * kUnroll - 1) / (kThreads * kUnroll);
     const int grid = stream_grid(tiles, 6);
-    auto k = vec ? (doffset ? fq_bwd_flat<FORM, T, true, true> : fq_bwd_flat<FORM, T, true, false>)
-                 : (doffset ? fq_bwd_flat<FORM, T, false, true> : fq_bwd_flat<FORM, T, false, false>);
+    auto k = vec ? (doffset ? fq_bwd_flat<FORM, T, true, true, false> : fq_bwd_flat<FORM, T, true, false, false>)
+                 : (doffset ? fq_bwd_flat<FORM, T, false, true, false> : fq_bwd_flat<FORM, T, false, false, false>);
+    if (defer) k = vec ? fq_bwd_flat<FORM, T, true, false, true> : fq_bwd_flat<FORM, T, false, false, true>;
     cudaError_t e = launch_pdl(k, dim3(grid), dim3(kThreads), 0, st, static_cast<const T*>(x),
                                static_cast<const T*>(dy), static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi,
                                dscale, doffset, ws);
@@ -343,14 +360,40 @@ static int dispatch_fwd(const void* x, void* y, void* codes, const dlmcq_layout*
 }
 template <typename T>
 static int dispatch_bwd(const void* x, const void* dy, void* dx, float* ds, float* doff, const dlmcq_layout* l,
-                        const dlmcq_qparams* qp, void* ws, size_t wsb, cudaStream_t st) {
+                        const dlmcq_qparams* qp, void* ws, size_t wsb, cudaStream_t st, bool defer = false) {
   switch (qp->form) {
-    case DLMCQ_FORM_A1: return launch_bwd<DLMCQ_FORM_A1, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
-    case DLMCQ_FORM_AFFINE: return launch_bwd<DLMCQ_FORM_AFFINE, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
-    case DLMCQ_FORM_ZP: return launch_bwd<DLMCQ_FORM_ZP, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
-    case DLMCQ_FORM_SYM: return launch_bwd<DLMCQ_FORM_SYM, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st);
+    case DLMCQ_FORM_A1: return launch_bwd<DLMCQ_FORM_A1, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st, defer);
+    case DLMCQ_FORM_AFFINE: return launch_bwd<DLMCQ_FORM_AFFINE, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st, defer);
+    case DLMCQ_FORM_ZP: return launch_bwd<DLMCQ_FORM_ZP, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st, defer);
+    case DLMCQ_FORM_SYM: return launch_bwd<DLMCQ_FORM_SYM, T>(x, dy, dx, ds, doff, l, qp, ws, wsb, st, defer);
   }
   return DLMCQ_EINVAL;
+}
+
+// one CTA per deferred backward call: fixed-order reduction of its per-CTA partials in double
+__global__ void __launch_bounds__(kThreads)
+finalize_many_kernel(const dlmcq_finalize_item* __restrict__ items, int n_items) {
+  __shared__ double sm[2][kThreads / 32];
+  const dlmcq_finalize_item it = items[blockIdx.x];
+  const float* p = it.partials;
+  const int nblocks = __float_as_int(p[0]);
+  const float gmul = p[1];
+  double s = 0.0, o = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+    s += static_cast<double>(p[2 + 2 * b]);
+    o += static_cast<double>(p[3 + 2 * b]);
+  }
+  s = warp_sum(s);
+  o = warp_sum(o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][warp] = s; sm[1][warp] = o; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, to = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { ts += sm[0][w]; to += sm[1][w]; }
+    it.dscale[0] = static_cast<float>(ts) * gmul;
+    (void)to;
+  }
 }
 
 }  // namespace dlmcq
@@ -409,6 +452,29 @@ extern "C" int dlmcq_dequantize(const void* codes, void* y, const dlmcq_layout* 
     dequant_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(codes),
                                                              static_cast<__nv_bfloat16*>(y), n, layout->channels,
                                                              layout->inner, scale, offset);
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" size_t dlmcq_fq_partials_floats(void) { return 2 + 2 * static_cast<size_t>(kMaxPartialBlocks); }
+
+extern "C" int dlmcq_fq_backward_partials(const void* x, const void* dy, void* dx, const dlmcq_layout* layout,
+                                          const dlmcq_qparams* qp, float* partials, void* stream) {
+  if (int e = check_layout(layout)) return e;
+  if (layout->channels != 1) return DLMCQ_EUNSUPPORTED;
+  if (!qp || !qp->scale || !partials || !x || !dy || !dx) return DLMCQ_EINVAL;
+  if (!elem_aligned(x, layout->dtype) || !elem_aligned(dy, layout->dtype) || !elem_aligned(dx, layout->dtype))
+    return DLMCQ_EALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return layout->dtype == DLMCQ_F32
+             ? dispatch_bwd<float>(x, dy, dx, nullptr, nullptr, layout, qp, partials, 0, st, true)
+             : dispatch_bwd<__nv_bfloat16>(x, dy, dx, nullptr, nullptr, layout, qp, partials, 0, st, true);
+}
+
+extern "C" int dlmcq_fq_finalize_many(const dlmcq_finalize_item* items, int n_items, void* stream) {
+  if (!items || n_items < 0) return DLMCQ_EINVAL;
+  if (n_items == 0) return DLMCQ_OK;
+  finalize_many_kernel<<<n_items, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(items, n_items);
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
 }

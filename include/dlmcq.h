@@ -115,6 +115,19 @@ int dlmcq_fq_backward(const void* x, const void* dy, void* dx, float* dscale, fl
                       const dlmcq_layout* layout, const dlmcq_qparams* qp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Deferred reduction for per-tensor layouts: dlmcq_fq_backward_partials writes dx and leaves the per-CTA
+ * partial sums in `partials` (dlmcq_fq_partials_floats() floats, no initialisation needed) instead of
+ * finalising in-kernel; dlmcq_fq_finalize_many then reduces any number of such calls - e.g. all layers
+ * of a training step - in ONE launch, in a fixed order (deterministic).  `items` is a DEVICE array. */
+typedef struct {
+  const float* partials; /* as written by dlmcq_fq_backward_partials */
+  float* dscale;         /* [1]; the offset gradient is not produced in deferred mode */
+} dlmcq_finalize_item;
+size_t dlmcq_fq_partials_floats(void);
+int dlmcq_fq_backward_partials(const void* x, const void* dy, void* dx, const dlmcq_layout* layout,
+                               const dlmcq_qparams* qp, float* partials, void* stream);
+int dlmcq_fq_finalize_many(const dlmcq_finalize_item* items, int n_items, void* stream);
+
 /* utils.py:29-37 round_pass / floor_pass values and RootQ/function.py:5-8 sgn:
  * mode 0: (round(x)-x)+x   mode 1: (floor(x)-x)+x   mode 2: sign(x) (sign(NaN)=0) */
 int dlmcq_ste_value(const void* x, void* y, int64_t numel, int dtype, int mode, void* stream);

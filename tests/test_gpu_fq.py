@@ -365,3 +365,26 @@ def test_fast_division_is_ieee_exact():
             _lib.check(h.dlmcq_selftest_fastdiv(2333 + rep, 148 * 8, 1775, narrow, C.c_void_p(bad.data_ptr()), None))
         torch.cuda.synchronize()
         assert int(bad) == 0, f"{int(bad)} quotients differ from IEEE division (narrow={narrow})"
+
+
+def test_deferred_finalize_equals_inline():
+    """backward_partials + finalize_many == backward, bit for bit (same partials, same summation order)."""
+    from dlmc_quant_b200.functional import DeferredScaleGrads
+    gen = torch.Generator().manual_seed(21)
+    sizes = [1 << 20, 12345, (1 << 22) + 7, 64]
+    dq = DeferredScaleGrads("cuda", len(sizes))
+    outs, refs = [], []
+    for i, n in enumerate(sizes):
+        x = dev(torch.relu(torch.randn(n, generator=gen)) * 2)
+        dy = dev(torch.randn(n, generator=gen))
+        s, o = dev(torch.tensor([0.21 + 0.01 * i])), dev(torch.tensor([0.0]))
+        g = R.lsq_g(n, 15)
+        dx = torch.empty_like(x)
+        ds = torch.zeros(1, device="cuda")
+        dq.backward(i, x, dy, dx, s, o, 0, 15, AFFINE, g)
+        outs.append((dx, ds))
+        refs.append(F().fq_backward(x, dy, s, o, 0, 15, AFFINE, g=g))
+    dq.finalize([ds for _, ds in outs])
+    for (dx, ds), (rdx, rds) in zip(outs, refs):
+        assert torch.equal(dx, rdx)
+        exact(ds, rds, "deferred dscale")
