@@ -18,18 +18,21 @@ __device__ __forceinline__ void fwd_row_segment(const T* __restrict__ xr, T* __r
   if (vec_ok) {
     const int64_t nvec = len / V::N;
     const raw* xv = reinterpret_cast<const raw*>(xr);
-    for (int64_t j = lane; j < nvec; j += 64) {
-      const bool two = (j + 32) < nvec;
-      raw r0 = ld_stream(xv + j), r1 = r0;
-      if (two) r1 = ld_stream(xv + j + 32);
+    constexpr int U = 4;                       // 128-bit loads in flight per lane
+    for (int64_t j = lane; j < nvec; j += 32 * U) {
+      raw r[U];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !two) break;
-        float f[V::N], fy[V::N], fc[V::N];
-        V::unpack(h ? r1 : r0, f);
-        fq_vec<FORM, V::N>(f, p, lo, hi, fc, fy);
-        if (yr) st_stream(reinterpret_cast<raw*>(yr) + j + 32 * h, V::pack(fy));
-        if (cr) st_stream(reinterpret_cast<raw*>(cr) + j + 32 * h, V::pack(fc));
+      for (int h = 0; h < U; ++h)
+        if (j + 32 * h < nvec) r[h] = ld_stream(xv + j + 32 * h);
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        if (j + 32 * h < nvec) {
+          float f[V::N], fy[V::N], fc[V::N];
+          V::unpack(r[h], f);
+          fq_vec<FORM, V::N>(f, p, lo, hi, fc, fy);
+          if (yr) st_stream(reinterpret_cast<raw*>(yr) + j + 32 * h, V::pack(fy));
+          if (cr) st_stream(reinterpret_cast<raw*>(cr) + j + 32 * h, V::pack(fc));
+        }
       }
     }
     done = nvec * V::N;
