@@ -58,6 +58,8 @@ SIGNATURES = {
     "dlmcq_dequantize": (_I, [_P, _P, _LP, _P, _P, _P]),
     "dlmcq_ste_value": (_I, [_P, _P, _L, _I, _I, _P]),
     "dlmcq_grad_scale_value": (_I, [_P, _P, _L, _F, _P]),
+    "dlmcq_export_codes": (_I, [_P, _P, _LP, _QP, _I, _P]),
+    "dlmcq_import_codes": (_I, [_P, _P, _LP, _QP, _I, _P]),
     "dlmcq_adaround_forward": (_I, [_P, _P, _P, _LP, _P, _I, _I, _I, _P]),
     "dlmcq_adaround_backward": (_I, [_P, _P, _P, _P, _P, _LP, _P, _I, _I, _P, _Z, _P]),
     "dlmcq_adaround_init_alpha": (_I, [_P, _P, _LP, _P, _P]),

@@ -134,6 +134,36 @@ def dequantize(codes, scale, offset, ch_axis=None):
     return y
 
 
+def export_codes(x, scale, offset, lo, hi, form, g=0.0, ch_axis=None, pack4=False):
+    """Integer codes as bytes: int8 (signed ranges) / uint8, or two 4-bit codes per byte (`pack4`)."""
+    _require_cuda(x, "x")
+    x = x.detach().contiguous()
+    lay = layout_of(x, ch_axis)
+    s = _qvec(scale, lay.channels, x.device, "scale")
+    o = _qvec(offset, lay.channels, x.device, "offset")
+    n = x.numel()
+    out = torch.empty((n + 1) // 2 if pack4 else n, dtype=torch.uint8 if (pack4 or lo >= 0) else torch.int8, device=x.device)
+    qp = QParams(form, int(lo), int(hi), float(g), s.data_ptr(), o.data_ptr() if o is not None else None)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().dlmcq_export_codes(_ptr(x), _ptr(out), C.byref(lay), C.byref(qp), int(bool(pack4)),
+                                                 _stream_ptr()))
+    return out if pack4 else out.reshape(x.shape)
+
+
+def import_codes(codes, shape, scale, offset, lo, hi, form, g=0.0, ch_axis=None, pack4=False, dtype=torch.float32):
+    """Unpack + dequantise exported codes; bit-identical to fq_forward's output for the same qparams."""
+    _require_cuda(codes, "codes")
+    y = torch.empty(shape, dtype=dtype, device=codes.device)
+    lay = layout_of(y, ch_axis)
+    s = _qvec(scale, lay.channels, y.device, "scale")
+    o = _qvec(offset, lay.channels, y.device, "offset")
+    qp = QParams(form, int(lo), int(hi), float(g), s.data_ptr(), o.data_ptr() if o is not None else None)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().dlmcq_import_codes(_ptr(codes.contiguous()), _ptr(y), C.byref(lay), C.byref(qp),
+                                                 int(bool(pack4)), _stream_ptr()))
+    return y
+
+
 def ste_value(x, mode):
     """mode 0 round_pass value, 1 floor_pass value, 2 sgn (utils.py:29-37, RootQ/function.py:5-8)."""
     _require_cuda(x, "x")

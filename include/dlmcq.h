@@ -138,6 +138,16 @@ int dlmcq_grad_scale_value(const float* s, float* out, int64_t numel, float g, v
 int dlmcq_dequantize(const void* codes, void* y, const dlmcq_layout* layout,
                      const float* scale, const float* offset, void* stream);
 
+/* ---- integer export (the reference only ever holds fp32-valued codes) ----------------
+ * dlmcq_export_codes: the integer codes of any form as one byte per element (int8 two's complement when
+ * qp->lo < 0, else uint8) or, with pack4 != 0 and a range that fits 4 bits, two codes per byte (low
+ * nibble = even element).  dlmcq_import_codes unpacks and dequantises: its output is bit-identical to
+ * dlmcq_fq_forward's y for the same qparams.  `layout->dtype` is the dtype of x / y. */
+int dlmcq_export_codes(const void* x, void* codes_out, const dlmcq_layout* layout, const dlmcq_qparams* qp,
+                       int pack4, void* stream);
+int dlmcq_import_codes(const void* codes, void* y, const dlmcq_layout* layout, const dlmcq_qparams* qp,
+                       int pack4, void* stream);
+
 /* ---- AdaRound weight form (FSPTQuant/base.py:69-79,136-141,151-152) -------------------
  * soft=1: codes = clamp(floor(w/s) + clamp(sigmoid(alpha)*1.2-0.1,0,1), lo, hi)
  * soft=0: codes = clamp(floor(w/s) + (alpha>=0), lo, hi);       y = codes*s

@@ -388,3 +388,31 @@ def test_deferred_finalize_equals_inline():
     for (dx, ds), (rdx, rds) in zip(outs, refs):
         assert torch.equal(dx, rdx)
         exact(ds, rds, "deferred dscale")
+
+
+@pytest.mark.parametrize("form,lo,hi,shape,ax", [(AFFINE, 0, 15, (3, 5, 7, 7), None), (SYM, -7, 7, (16, 27), 0),
+                                                  (ZP, 0, 255, (1001,), None), (A1, -127, 127, (8, 33), 0),
+                                                  (AFFINE, 0, 15, (2, 6, 5, 5), 1)])
+def test_integer_export_round_trip(form, lo, hi, shape, ax):
+    """packed int4 / int8 codes == the fp32-valued codes of the forward; import(export(x)) == fq_forward(x)."""
+    gen = torch.Generator().manual_seed(31 + form)
+    signed = lo < 0
+    x = torch.randn(shape, generator=gen) * (0.05 if signed else 1.5)
+    if not signed:
+        x = torch.relu(x)
+    _, _, scale, off = make_qparams(form, x, ax, signed, 4 if hi <= 15 else 8, gen)
+    g = R.lsq_g(x.numel(), hi)
+    y, codes = F().fq_forward(dev(x), dev(scale), dev(off), lo, hi, form, g=g, ch_axis=ax, want_codes=True)
+    for pack4 in ([False, True] if hi - lo <= 15 else [False]):
+        packed = F().export_codes(dev(x), dev(scale), dev(off), lo, hi, form, g=g, ch_axis=ax, pack4=pack4)
+        if pack4:
+            b = packed.cpu().to(torch.int32)
+            nib = torch.stack([b & 15, b >> 4], 1).reshape(-1)[: x.numel()]
+            ints = torch.where(nib > 7, nib - 16, nib) if signed else nib
+            assert packed.numel() == (x.numel() + 1) // 2
+        else:
+            ints = packed.cpu().to(torch.int32).reshape(-1)
+            assert packed.dtype == (torch.int8 if signed else torch.uint8)
+        assert torch.equal(ints, codes.cpu().reshape(-1).to(torch.int32)), "integer codes differ"
+        back = F().import_codes(packed, tuple(shape), dev(scale), dev(off), lo, hi, form, g=g, ch_axis=ax, pack4=pack4)
+        exact(back, y, "import(export(x)) vs fq_forward")
