@@ -205,18 +205,26 @@ def run_ours(args, rank, world, device):
     wl = Workload(args.batch, device, 2333 + rank)         # the reference's seed, per-rank offset
     wl.capture()
 
+    pending = [None]
+
     def step(ev=None):
         wl.g_fwd.replay()
         if ev:
             ev[0].record()
+        if pending[0] is not None:      # the previous step's all-reduce must be done before dscale is rewritten
+            pending[0].wait()
         wl.g_bwd.replay()
         if ev:
             ev[1].record()
         wl.g_wt.replay()
-        if world > 1:   # the path's one real exchange: scale gradients, one flat SUM all-reduce (NVLink)
-            dist.all_reduce(wl.dscale)
+        if world > 1:   # the path's one real exchange: scale gradients, one flat SUM all-reduce over NVLink,
+            #             issued asynchronously so that it overlaps the next step's forward (as DDP overlaps backward)
+            pending[0] = dist.all_reduce(wl.dscale, async_op=True)
 
     def fence():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -231,6 +239,8 @@ def run_ours(args, rank, world, device):
     t0.record()
     for k in range(args.steps):
         step(evs[k])
+    if pending[0] is not None:
+        pending[0].wait()               # the last all-reduce is inside the timed region
     t1.record()
     fence()
     clocks = sampler.stop()
