@@ -217,7 +217,8 @@ def run_ours(args, rank, world, device):
         if ev:
             ev[1].record()
         wl.g_wt.replay()
-        if world > 1:   # the path's one real exchange: scale gradients, one flat SUM all-reduce over NVLink,
+        if world > 1 and not os.environ.get("DLMCQ_BENCH_NO_COLLECTIVE"):   # (diagnostic switch)
+            # the path's one real exchange: scale gradients, one flat SUM all-reduce over NVLink,
             #             issued asynchronously so that it overlaps the next step's forward (as DDP overlaps backward)
             pending[0] = dist.all_reduce(wl.dscale, async_op=True)
 
@@ -229,12 +230,14 @@ def run_ours(args, rank, world, device):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    fence()
+    # everything slow or rank-dependent (NVML init, event creation) happens BEFORE the fence, so that all
+    # ranks enter the timed region together; otherwise early ranks just wait in the first all-reduce
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(device.index)
+    for _ in range(args.warmup):
+        step()
+    fence()
     sampler.start()
     t0.record()
     for k in range(args.steps):
@@ -244,6 +247,8 @@ def run_ours(args, rank, world, device):
     t1.record()
     fence()
     clocks = sampler.stop()
+    if os.environ.get("DLMCQ_BENCH_PER_RANK"):
+        print(f"rank {rank}: {t0.elapsed_time(t1) / args.steps:.4f} ms/step", file=sys.stderr, flush=True)
     ms = torch.tensor([t0.elapsed_time(t1)], device=device)
     bwd_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=device)
     if world > 1:

@@ -220,3 +220,44 @@ def test_functional_api_surface():
             assert sg.shape == sr.shape
             exact(sg, sr, f"{qtype} scale")
             exact(og.float(), orf.float().reshape(og.shape), f"{qtype} offset")
+
+
+def test_lsq_init_and_output_aware_observers():
+    """modules/base.py:83-86,118-121 (LSQ init 2*mean|x|/sqrt(qmax)) and ops.py:85-109,252-292 (output-aware
+    l2norm: host loop around our quantize kernel + the module's own conv) against the oracle chain."""
+    from oracle import restate as R
+    from dlmc_quant_b200.scalar import modules, ops
+    gen = torch.Generator().manual_seed(5)
+    conv = torch.nn.Conv2d(4, 6, 3, padding=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * 0.05)
+    x = torch.relu(torch.randn(2, 4, 8, 8, generator=gen))
+    qcfg = {"weight": {"enable": True, "type": "LSQ", "args": {"n_bits": 4, "signed": True}},
+            "input": {"enable": True, "type": "LSQ", "args": {"n_bits": 4, "signed": False}}, "momentum": 0.1}
+    base = copy.deepcopy(conv).cuda()
+    m = modules.QConv2d.__new__(modules.QConv2d)
+    m.__dict__.update(base.__dict__)
+    m.initialize(copy.deepcopy(qcfg))
+    seen = capture(m)
+    m(x.cuda())
+    s_in, s_w = R.lsq_init_scale(x, 15), R.lsq_init_scale(conv.weight, 7)
+    assert torch.allclose(m.in_scale.detach().cpu(), s_in.reshape(1), rtol=1e-6)
+    assert torch.allclose(m.wt_scale.detach().cpu(), s_w.reshape(1), rtol=1e-6)
+    qx = R.fq_affine(x, m.in_scale.detach().cpu(), torch.zeros(1), 0, 15, R.lsq_g(x.numel(), 15))
+    exact(seen["qx"].detach(), qx, "LSQ activation fake-quant")
+    # output-aware observers
+    torch.backends.cudnn.allow_tf32 = False
+
+    class Host:                     # the reference passes the module for its _forward_func only
+        def _forward_func(self, inp, wt):
+            return torch.nn.functional.conv2d(inp, wt, None, 1, 1)
+
+    for fn, rfn, kw in [(ops.quantize_l2norm_output, None, {}), (ops.quantize_l2norm_output_channel, None, {"ch_axis": 0})]:
+        s, o = fn(x.cuda(), conv.weight.detach().cuda(), Host(), n_bits=4, signed=True, patience=30, **kw)
+        assert torch.isfinite(s).all() and (s > 0).all()
+        # the returned scale must not be worse (output MSE) than the min/max start it refines
+        s0, o0 = (ops.quantize_minmax_tensor if not kw else ops.quantize_minmax_channel)(conv.weight.detach().cuda(), 4, True, **kw)
+        from dlmc_quant_b200.scalar.utils import emulate_quantize
+        ref_out = Host()._forward_func(x.cuda(), conv.weight.detach().cuda())
+        err = lambda sc, of: float(((Host()._forward_func(x.cuda(), emulate_quantize(conv.weight.detach().cuda(), sc, of, -7, 7)) - ref_out) ** 2).mean())
+        assert err(s, o) <= err(s0, o0) * 1.05
