@@ -261,3 +261,75 @@ def test_lsq_init_and_output_aware_observers():
         ref_out = Host()._forward_func(x.cuda(), conv.weight.detach().cuda())
         err = lambda sc, of: float(((Host()._forward_func(x.cuda(), emulate_quantize(conv.weight.detach().cuda(), sc, of, -7, 7)) - ref_out) ** 2).mean())
         assert err(s, o) <= err(s0, o0) * 1.05
+
+
+def test_fsptq_reconstruction_driver():
+    """recon.FSPTQReconstructor (GPU-resident redesign of trainer/fsptq_trainer.py:28-112): caches equal the
+    naive full-pass hooks of the reference procedure, and fitting reduces the block error."""
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.recon import FSPTQReconstructor, l2_loss
+    torch.manual_seed(2333)
+
+    class Block(torch.nn.Module):
+        def __init__(self, cin, cout):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(cin, cout, 3, padding=1)
+            self.act = torch.nn.ReLU()
+
+        def forward(self, x):
+            return self.act(self.conv(x))
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = torch.nn.Conv2d(3, 8, 3, padding=1)
+            self.b1, self.b2 = Block(8, 12), Block(12, 8)
+            self.linear = torch.nn.Linear(8, 5)
+
+        def forward(self, x):
+            x = torch.relu(self.conv1(x))
+            return self.linear(self.b2(self.b1(x)).mean((2, 3)))
+
+    fp = Net().cuda().eval()
+    net = copy.deepcopy(fp)
+    cfg = {"weight": {"enable": True, "type": "minmax_channel", "recon_type": "adaround",
+                      "args": {"n_bits": 3, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 8, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+    quantize_model(net, cfg, None, quantization_type="FSPTQ")
+    batches = [torch.randn(32, 3, 12, 12, device="cuda") for _ in range(4)]
+    rec = FSPTQReconstructor(net, fp, block_types=(Block,), epochs=60, minibatch=64, log_every=59)
+    names = [n for n, _, _ in rec.targets()]
+    assert names == ["conv1", "b1", "b2", "linear"]
+    with torch.no_grad():
+        for d in batches:
+            net(d)
+    # caches vs the naive procedure (full passes with forward hooks)
+    fp_out = rec.cache_fp_outputs(batches, rec.targets())
+    seen = []
+    h = fp.b2.register_forward_hook(lambda m, i, o: seen.append(o))
+    with torch.no_grad():
+        for d in batches:
+            fp(d)
+    h.remove()
+    assert torch.equal(fp_out["b2"], torch.cat(seen))
+    seen = []
+    h = net.b2.register_forward_hook(lambda m, i, o: seen.append(i[0]))
+    net.eval()
+    with torch.no_grad():
+        for d in batches:
+            net(d)
+    h.remove()
+    assert torch.equal(rec.cache_block_input(batches, net.b2), torch.cat(seen))
+
+    def block_err():
+        net.eval()
+        with torch.no_grad():
+            x = torch.cat(batches)
+            return float(l2_loss(fp(x), net(x)))
+
+    before = block_err()
+    hist = rec.run(batches, generator=torch.Generator().manual_seed(1))
+    after = block_err()
+    assert set(hist) == set(names) and all(len(v) >= 1 for v in hist.values())
+    assert after < before, (before, after)
