@@ -16,7 +16,7 @@ namespace dlmcq {
 
 constexpr int kThreads = 256;          // threads per CTA for the streaming kernels
 constexpr int kNumSmFallback = 148;    // B200
-constexpr int kMaxPartialBlocks = 2048;
+constexpr int kMaxPartialBlocks = 8192;
 constexpr int kRowWarps = 8;           // warps per CTA in the warp-per-row kernels
 
 int num_sms();
@@ -221,7 +221,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Persistent grid for a streaming kernel over `work_items` block-tiles.
 inline int stream_grid(int64_t tiles, int blocks_per_sm) {
   int64_t cap = static_cast<int64_t>(num_sms()) * blocks_per_sm;
-  if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+  if (cap > kMaxPartialBlocks && blocks_per_sm <= 16) cap = kMaxPartialBlocks;   // reductions size their partials by this
   int64_t g = tiles < cap ? tiles : cap;
   return g < 1 ? 1 : static_cast<int>(g);
 }

@@ -1,9 +1,11 @@
 // fq_kernels.cu - fused fake-quant forward / backward kernels and their C-ABI entry points.
 //
 // Two kernel shapes cover every layout:
-//   * flat   (channels == 1): persistent grid of 148*k CTAs, each thread keeps UNROLL 128-bit
-//            loads in flight, one pass over HBM.  Backward also block-reduces the scale
-//            gradient and the last CTA to finish combines the partials (fixed order).
+//   * flat   (channels == 1): each CTA streams contiguous 16 KB tiles, every thread keeps UNROLL
+//            128-bit loads in flight (forward: one tile per CTA; backward: a capped grid because
+//            every CTA contributes one partial sum).  Backward block-reduces the scale gradient
+//            and either the last CTA to finish combines the partials in a fixed order, or they
+//            are left for dlmcq_fq_finalize_many (one launch for all layers of a step).
 //   * rows   (per-channel): the tensor is rows = outer*channels of length `inner`; one warp
 //            owns one row segment (<= kRowSeg elements), so the channel's qparams are loaded
 //            once per warp and the per-channel scale gradient is a warp-shuffle reduction.
@@ -17,8 +19,8 @@ constexpr int kUnroll = 4;
 // ---------------------------------------------------------------------------------------
 // flat forward
 // ---------------------------------------------------------------------------------------
-template <int FORM, typename T>
-__global__ void __launch_bounds__(kThreads, 4)
+template <int FORM, typename T, int U = kUnroll, int MINB = 4, bool TILED = false>
+__global__ void __launch_bounds__(kThreads, MINB)
 fq_fwd_flat(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, int64_t n,
             const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
   using V = Vec<T>;
@@ -40,14 +42,29 @@ fq_fwd_flat(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, i
     if (y) st_stream(yv + idx, V::pack(fy));
     if (codes) st_stream(cv + idx, V::pack(fc));
   };
-  for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
-    raw r[kUnroll];
+  if (TILED) {
+    // each CTA iteration covers one contiguous tile of U*256 vectors (16 KB for fp32, U=4)
+    const int64_t tile_vecs = static_cast<int64_t>(U) * blockDim.x;
+    const int64_t ntiles = nvec / tile_vecs;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t b = t * tile_vecs + threadIdx.x;
+      raw r[U];
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) r[k] = ld_stream(xv + i + k * stride);
+      for (int k = 0; k < U; ++k) r[k] = ld_stream(xv + b + k * blockDim.x);
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) body(r[k], i + k * stride);
+      for (int k = 0; k < U; ++k) body(r[k], b + k * blockDim.x);
+    }
+    for (int64_t j = ntiles * tile_vecs + i; j < nvec; j += stride) body(ld_stream(xv + j), j);
+  } else {
+    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+      raw r[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) r[k] = ld_stream(xv + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < U; ++k) body(r[k], i + k * stride);
+    }
+    for (; i < nvec; i += stride) body(ld_stream(xv + i), i);
   }
-  for (; i < nvec; i += stride) body(ld_stream(xv + i), i);
   // ragged tail (< one vector)
   if (blockIdx.x == 0) {
     const int64_t t = nvec * V::N + threadIdx.x;
@@ -134,17 +151,21 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
       fq_vec_bwd<FORM, WANT_OFF, V::N>(fx, fg, p, lo, hi, fo, acc[0], acc[1]);
       st_stream(ov + idx, V::pack(fo));
     };
-    for (; i + (kUnroll - 1) * stride < nvec; i += kUnroll * stride) {
+    // each CTA iteration covers one contiguous tile of kUnroll*256 vectors of x and of dy
+    const int64_t tile_vecs = static_cast<int64_t>(kUnroll) * blockDim.x;
+    const int64_t ntiles = nvec / tile_vecs;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t b = t * tile_vecs + threadIdx.x;
       raw rx[kUnroll], rg[kUnroll];
 #pragma unroll
       for (int k = 0; k < kUnroll; ++k) {
-        rx[k] = ld_stream(xv + i + k * stride);
-        rg[k] = ld_stream(gv + i + k * stride);
+        rx[k] = ld_stream(xv + b + k * blockDim.x);
+        rg[k] = ld_stream(gv + b + k * blockDim.x);
       }
 #pragma unroll
-      for (int k = 0; k < kUnroll; ++k) body(rx[k], rg[k], i + k * stride);
+      for (int k = 0; k < kUnroll; ++k) body(rx[k], rg[k], b + k * blockDim.x);
     }
-    for (; i < nvec; i += stride) body(ld_stream(xv + i), ld_stream(gv + i), i);
+    for (int64_t j = ntiles * tile_vecs + i; j < nvec; j += stride) body(ld_stream(xv + j), ld_stream(gv + j), j);
     if (blockIdx.x == 0) {
       const int64_t t = nvec * V::N + threadIdx.x;
       if (t < n) dx[t] = from_f32<T>(fq_elem_bwd<FORM, WANT_OFF>(to_f32<T>(x[t]), to_f32<T>(dy[t]), p, lo, hi, acc[0], acc[1]));
@@ -382,7 +403,11 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
   if (l->channels == 1) {
     if (aligned16(x) && aligned16(y) && aligned16(codes)) {
       const int64_t tiles = (n / Vec<T>::N + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-      cudaError_t e = launch_pdl(fq_fwd_flat<FORM, T>, dim3(stream_grid(tiles, 8)), dim3(kThreads), 0, st,
+      // One contiguous 16 KB tile per CTA (grid-stride only beyond 148*1024 CTAs): measured 6.6-6.7 TB/s on
+      // 2^26..2^28 elements vs 5.9-6.0 for a persistent grid-stride grid (profiles/README.md).
+      auto kern = fq_fwd_flat<FORM, T, kUnroll, 4, true>;
+      const int bps = 1024;
+      cudaError_t e = launch_pdl(kern, dim3(stream_grid(tiles, bps)), dim3(kThreads), 0, st,
                                  static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale,
                                  qp->offset, qp->g, lo, hi);
       if (e != cudaSuccess) return set_cuda_error(e);
@@ -421,7 +446,10 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
     const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx);
     const int64_t per = vec ? Vec<T>::N : 1;
     int64_t tiles = (n / per + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-    const int grid = stream_grid(tiles, 6);
+    // CTAs = per-launch partial sums, so the grid is capped; larger tensors amortise more of them
+    int64_t cap = n < (int64_t(1) << 25) ? 888 : (n < (int64_t(1) << 27) ? 2048 : 4096);
+    if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    const int grid = static_cast<int>(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
     auto k = vec ? (doffset ? fq_bwd_flat<FORM, T, true, true, false> : fq_bwd_flat<FORM, T, true, false, false>)
                  : (doffset ? fq_bwd_flat<FORM, T, false, true, false> : fq_bwd_flat<FORM, T, false, false, false>);
     if (defer) k = vec ? fq_bwd_flat<FORM, T, true, false, true> : fq_bwd_flat<FORM, T, false, false, true>;

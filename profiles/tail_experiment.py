@@ -3,6 +3,7 @@ sys.path.insert(0, "/root/repo")
 from dlmc_quant_b200 import _lib, functional as F
 h=_lib.lib()
 def run(n, nbuf=24, iters=240):
+    nbuf = max(2, min(nbuf, int(3e9 // (n * 12)))); iters = nbuf * 6
     xs=[torch.relu(torch.randn(n,device="cuda")) for _ in range(nbuf)]
     dys=[torch.randn(n,device="cuda") for _ in range(nbuf)]
     ys=[torch.empty(n,device="cuda") for _ in range(nbuf)]
@@ -24,6 +25,6 @@ def run(n, nbuf=24, iters=240):
         a.record(); g.replay(); b.record(); torch.cuda.synchronize()
         out.append(a.elapsed_time(b)*1e3/iters)
     return out
-for n in (1605632, 3211264, 6422528, 12845056):
+for n in [int(a) for a in sys.argv[1:]] or (1605632, 3211264, 6422528, 12845056):
     f,b=run(n)
-    print(f"exp={os.environ.get('DLMCQ_EXPERIMENT','0')} n={n}: fwd {f:.2f} us ({8*n/f/1e6:.0f} GB/s)  bwd {b:.2f} us ({12*n/b/1e6:.0f} GB/s)")
+    print(f"tune={os.environ.get('DLMCQ_FWD_TUNE','0')} n={n}: fwd {f:.2f} us ({8*n/f/1e3:.0f} GB/s)  bwd {b:.2f} us ({12*n/b/1e3:.0f} GB/s)")
