@@ -238,14 +238,17 @@ rootq_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, const fl
       }
       st_stream(yv + idx, V::pack(o));
     };
-    for (; i + (kRqUnroll - 1) * stride < nvec; i += kRqUnroll * stride) {
+    const int64_t tile_vecs = static_cast<int64_t>(kRqUnroll) * blockDim.x;   // contiguous 16 KB tiles
+    const int64_t ntiles = nvec / tile_vecs;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t b = t * tile_vecs + threadIdx.x;
       raw r[kRqUnroll];
 #pragma unroll
-      for (int k = 0; k < kRqUnroll; ++k) r[k] = ld_stream(xv + i + k * stride);
+      for (int k = 0; k < kRqUnroll; ++k) r[k] = ld_stream(xv + b + k * blockDim.x);
 #pragma unroll
-      for (int k = 0; k < kRqUnroll; ++k) body(r[k], i + k * stride);
+      for (int k = 0; k < kRqUnroll; ++k) body(r[k], b + k * blockDim.x);
     }
-    for (; i < nvec; i += stride) body(ld_stream(xv + i), i);
+    for (int64_t j = ntiles * tile_vecs + i; j < nvec; j += stride) body(ld_stream(xv + j), j);
     if (blockIdx.x == 0) {
       const int64_t t = nvec * V::N + threadIdx.x;
       if (t < n) y[t] = from_f32<T>(f(to_f32<T>(x[t])));
@@ -295,17 +298,20 @@ rootq_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restric
       st_stream(ov + idx, V::pack(o));
     };
     constexpr int U = WEIGHT ? 2 : kRqUnroll;
-    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    const int64_t tile_vecs = static_cast<int64_t>(U) * blockDim.x;
+    const int64_t ntiles = nvec / tile_vecs;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int64_t b = t * tile_vecs + threadIdx.x;
       raw rx[U], rg[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        rx[k] = ld_stream(xv + i + k * stride);
-        rg[k] = ld_stream(gv + i + k * stride);
+        rx[k] = ld_stream(xv + b + k * blockDim.x);
+        rg[k] = ld_stream(gv + b + k * blockDim.x);
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k) body(rx[k], rg[k], i + k * stride);
+      for (int k = 0; k < U; ++k) body(rx[k], rg[k], b + k * blockDim.x);
     }
-    for (; i < nvec; i += stride) body(ld_stream(xv + i), ld_stream(gv + i), i);
+    for (int64_t j = ntiles * tile_vecs + i; j < nvec; j += stride) body(ld_stream(xv + j), ld_stream(gv + j), j);
     if (blockIdx.x == 0) {
       const int64_t t = nvec * V::N + threadIdx.x;
       if (t < n) dx[t] = from_f32<T>(f(to_f32<T>(x[t]), to_f32<T>(dy[t])));
@@ -349,9 +355,12 @@ rootq_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restric
   }
 }
 
+// forward: one tile per CTA; backward: capped (every CTA leaves one partial sum per reduced quantity)
 static inline int rq_grid(int64_t n, int per_thread, int blocks_per_sm) {
   const int64_t tiles = (n / per_thread + kThreads * kRqUnroll - 1) / (kThreads * kRqUnroll);
-  return stream_grid(tiles, blocks_per_sm);
+  if (blocks_per_sm >= 8) return stream_grid(tiles, 1024);
+  int64_t cap = n < (int64_t(1) << 25) ? 888 : 2048;
+  return static_cast<int>(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
 }
 
 }  // namespace dlmcq
