@@ -172,14 +172,14 @@ struct RowGeom {
   int64_t segs;   // segments per row
   int64_t seg;    // elements per segment (multiple of 512 -> 16-byte aligned cuts)
 };
-constexpr int64_t kRowSegMin = 4096;
-constexpr int64_t kRowItemsTarget = 32768;
-inline RowGeom make_geom(int64_t outer, int64_t channels, int64_t inner) {
+constexpr int64_t kRowSegMin = 2048;          // ~8 KB (fp32) per warp item: small enough for an even last wave
+constexpr int64_t kRowItemsTarget = 1 << 20;
+inline RowGeom make_geom(int64_t outer, int64_t channels, int64_t inner, int64_t seg_min = kRowSegMin) {
   RowGeom gm;
   gm.rows = outer * channels;
   gm.channels = channels;
   gm.inner = inner;
-  int64_t segs = (inner + kRowSegMin - 1) / kRowSegMin;
+  int64_t segs = (inner + seg_min - 1) / seg_min;
   int64_t cap = kRowItemsTarget / (gm.rows > 0 ? gm.rows : 1);
   if (cap < 1) cap = 1;
   if (segs > cap) segs = cap;
@@ -191,6 +191,33 @@ inline RowGeom make_geom(int64_t outer, int64_t channels, int64_t inner) {
   gm.segs = (inner + seg - 1) / seg;
   if (gm.segs < 1) gm.segs = 1;
   return gm;
+}
+
+// Channel-major geometry for per-channel ACTIVATIONS with short rows ([B, C, HW], HW < 256): one warp owns
+// (channel, a chunk of batch indices) and walks the flattened (b, e) index space of that channel.
+struct CmajGeom {
+  int64_t outer, channels, inner;
+  int32_t bc;        // batch indices per work item
+  int32_t chunks;    // work items per channel
+  uint32_t magic;    // floor(2^24 / inner) + 1: (t * magic) >> 24 == t / inner for t * inner < 2^24
+};
+constexpr int kCmajUnroll = 8;
+constexpr int64_t kCmajMaxInner = 256;
+
+// short rows, more than one batch index, and 32-bit element offsets inside one work item
+inline bool cmaj_ok(int64_t outer, int64_t channels, int64_t inner) {
+  return outer > 1 && inner >= 1 && inner < kCmajMaxInner && channels * 8192 < (int64_t(1) << 31);
+}
+inline CmajGeom make_cmaj(int64_t outer, int64_t channels, int64_t inner) {
+  CmajGeom g;
+  g.outer = outer; g.channels = channels; g.inner = inner;
+  int64_t bc = 8192 / (inner > 0 ? inner : 1);
+  if (bc < 1) bc = 1;
+  if (bc > outer) bc = outer;
+  g.bc = static_cast<int32_t>(bc);
+  g.chunks = static_cast<int32_t>((outer + bc - 1) / bc);
+  g.magic = static_cast<uint32_t>((1u << 24) / static_cast<uint32_t>(inner > 0 ? inner : 1)) + 1u;
+  return g;
 }
 
 // Programmatic dependent launch: consecutive kernels of one stream (the per-layer quantizer launches of a

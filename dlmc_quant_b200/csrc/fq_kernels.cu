@@ -252,71 +252,56 @@ fq_bwd_rows(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
 // warp-per-row kernel idle and pay the per-row setup 1.4 M times), and the per-channel scale gradient
 // stays in registers across the whole chunk.
 // ---------------------------------------------------------------------------------------
-struct CmajGeom {
-  int64_t outer, channels, inner;
-  int32_t bc;        // batch indices per work item
-  int32_t chunks;    // work items per channel
-  uint32_t magic;    // floor(2^24 / inner) + 1: (t * magic) >> 24 == t / inner for t * inner < 2^24
-};
-constexpr int kCmajUnroll = 4;
-constexpr int64_t kCmajMaxInner = 256;
-
-static inline CmajGeom make_cmaj(const dlmcq_layout* l) {
-  CmajGeom g;
-  g.outer = l->outer; g.channels = l->channels; g.inner = l->inner;
-  int64_t bc = 8192 / (l->inner > 0 ? l->inner : 1);
-  if (bc < 1) bc = 1;
-  if (bc > l->outer) bc = l->outer;
-  g.bc = static_cast<int32_t>(bc);
-  g.chunks = static_cast<int32_t>((l->outer + bc - 1) / bc);
-  g.magic = static_cast<uint32_t>((1u << 24) / static_cast<uint32_t>(l->inner > 0 ? l->inner : 1)) + 1u;
-  return g;
-}
-
 template <int FORM, typename T, bool BWD>
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, 4)
 fq_cmaj_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, T* __restrict__ codes,
                CmajGeom gm, const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo,
                float hi, float* __restrict__ dscale, float* __restrict__ part, int direct) {
   const int lane = threadIdx.x & 31;
   const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (item >= gm.channels * gm.chunks) return;
-  const int64_t c = item / gm.chunks, j = item - c * gm.chunks;
+  // consecutive warps own consecutive channels of the same batch chunk: the 8 warps of a CTA then read
+  // adjacent rows, so the 32-byte sectors that straddle two rows are fetched once
+  const int64_t j = item / gm.channels, c = item - j * gm.channels;
   const int64_t b0 = j * gm.bc;
   const int64_t nb = (gm.outer - b0) < gm.bc ? (gm.outer - b0) : gm.bc;
   const uint32_t total = static_cast<uint32_t>(nb * gm.inner);
   const uint32_t inner = static_cast<uint32_t>(gm.inner);
   const ChanParams p = make_params<FORM>(scale, offset, c, g, lo, hi);
-  const int64_t plane = gm.channels * gm.inner;
+  const uint32_t plane = static_cast<uint32_t>(gm.channels * gm.inner);   // bc * plane < 2^31 (make_cmaj)
   const int64_t base = (b0 * gm.channels + c) * gm.inner;
+  const T* xb = x + base;
+  const T* gb = BWD ? dy + base : nullptr;
+  T* ob = out ? out + base : nullptr;
+  T* cb = codes ? codes + base : nullptr;
   float as = 0.f, ao = 0.f;
   for (uint32_t t0 = 0; t0 < total; t0 += 32 * kCmajUnroll) {
     float v[kCmajUnroll], gq[kCmajUnroll];
-    int64_t off[kCmajUnroll];
+    uint32_t off[kCmajUnroll];
     bool ok[kCmajUnroll];
 #pragma unroll
     for (int u = 0; u < kCmajUnroll; ++u) {
       const uint32_t t = t0 + u * 32 + lane;
       ok[u] = t < total;
       const uint32_t bl = static_cast<uint32_t>((static_cast<uint64_t>(t) * gm.magic) >> 24);
-      off[u] = base + static_cast<int64_t>(bl) * plane + (t - bl * inner);
-      v[u] = ok[u] ? to_f32<T>(x[off[u]]) : 0.f;
-      if (BWD) gq[u] = ok[u] ? to_f32<T>(dy[off[u]]) : 0.f;
+      off[u] = bl * plane + (t - bl * inner);
+      v[u] = ok[u] ? to_f32<T>(xb[off[u]]) : 0.f;
+      if (BWD) gq[u] = ok[u] ? to_f32<T>(gb[off[u]]) : 0.f;
     }
     if (BWD) {
       float d[kCmajUnroll];
       fq_vec_bwd<FORM, false, kCmajUnroll>(v, gq, p, lo, hi, d, as, ao);
 #pragma unroll
       for (int u = 0; u < kCmajUnroll; ++u)
-        if (ok[u]) out[off[u]] = from_f32<T>(d[u]);
+        if (ok[u]) ob[off[u]] = from_f32<T>(d[u]);
     } else {
       float cd[kCmajUnroll], y[kCmajUnroll];
       fq_vec<FORM, kCmajUnroll>(v, p, lo, hi, cd, y);
 #pragma unroll
       for (int u = 0; u < kCmajUnroll; ++u) {
         if (ok[u]) {
-          if (out) out[off[u]] = from_f32<T>(y[u]);
-          if (codes) codes[off[u]] = from_f32<T>(cd[u]);
+          if (ob) ob[off[u]] = from_f32<T>(y[u]);
+          if (cb) cb[off[u]] = from_f32<T>(cd[u]);
         }
       }
     }
@@ -325,43 +310,36 @@ fq_cmaj_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict_
     as = warp_sum(as);
     if (lane == 0) {
       if (direct) dscale[c] = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? as * g : as;
-      else part[item] = as;
+      else part[c * gm.chunks + j] = as;
     }
   }
 }
 
-// one warp per channel: fixed-order sum of that channel's chunk partials
-__global__ void __launch_bounds__(kRowWarps * 32)
-cmaj_finalize(const float* __restrict__ part, int64_t channels, int chunks, float gmul, float* __restrict__ dscale) {
-  const int lane = threadIdx.x & 31;
-  const int64_t ch = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
-  if (ch >= channels) return;
-  double s = 0.0;
-  for (int k = lane; k < chunks; k += 32) s += static_cast<double>(part[ch * chunks + k]);
-  s = warp_sum(s);
-  if (lane == 0) dscale[ch] = static_cast<float>(s) * gmul;
-}
-
-// one warp per channel: sum the partials of (outer, segs) in a fixed order
-__global__ void __launch_bounds__(kRowWarps * 32)
-rows_finalize(const float* __restrict__ part, RowGeom gm, int64_t outer, float gmul,
+// one CTA per channel: fixed-order sum (in double) of that channel's `per` partials, WIDTH floats each, at
+// part[WIDTH * ((k / inner_n) * stride_o + ch * inner_n + k % inner_n)]  (rows: k = (b, seg), inner_n = segs,
+// stride_o = C * segs; channel-major: inner_n = chunks, stride_o = 0)
+template <int WIDTH>
+__global__ void __launch_bounds__(128)
+chan_finalize(const float* __restrict__ part, int64_t per, int64_t inner_n, int64_t stride_o, float gmul,
               float* __restrict__ dscale, float* __restrict__ doffset) {
-  const int lane = threadIdx.x & 31;
-  const int64_t ch = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
-  if (ch >= gm.channels) return;
+  __shared__ double sh[2][4];
+  const int64_t ch = blockIdx.x;
   double s = 0.0, o = 0.0;
-  const int64_t per = outer * gm.segs;
-  for (int64_t k = lane; k < per; k += 32) {
-    const int64_t b = k / gm.segs, sg = k - b * gm.segs;
-    const int64_t item = (b * gm.channels + ch) * gm.segs + sg;
-    s += static_cast<double>(part[2 * item]);
-    o += static_cast<double>(part[2 * item + 1]);
+  for (int64_t k = threadIdx.x; k < per; k += blockDim.x) {
+    const int64_t q = k / inner_n, i = k - q * inner_n;
+    const int64_t item = q * stride_o + ch * inner_n + i;
+    s += static_cast<double>(part[WIDTH * item]);
+    if (WIDTH == 2) o += static_cast<double>(part[WIDTH * item + 1]);
   }
   s = warp_sum(s);
   o = warp_sum(o);
-  if (lane == 0) {
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = o; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+    o = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
     dscale[ch] = static_cast<float>(s) * gmul;
-    if (doffset) doffset[ch] = static_cast<float>(o);
+    if (WIDTH == 2 && doffset) doffset[ch] = static_cast<float>(o);
   }
 }
 
@@ -416,8 +394,8 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
       fq_fwd_flat_unaligned<FORM, T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
           static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale, qp->offset, qp->g, lo, hi);
     }
-  } else if (l->outer > 1 && l->inner < kCmajMaxInner) {
-    const CmajGeom cg = make_cmaj(l);
+  } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
+    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner);
     const int64_t blocks = (cg.channels * cg.chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
     fq_cmaj_kernel<FORM, T, false><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
@@ -457,8 +435,8 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
                                static_cast<const T*>(dy), static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi,
                                dscale, doffset, ws);
     if (e != cudaSuccess) return set_cuda_error(e);
-  } else if (l->outer > 1 && l->inner < kCmajMaxInner && doffset == nullptr && n > 0) {
-    const CmajGeom cg = make_cmaj(l);
+  } else if (cmaj_ok(l->outer, l->channels, l->inner) && doffset == nullptr && n > 0) {
+    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner);
     const int64_t blocks = (cg.channels * cg.chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
     const int direct = cg.chunks == 1 ? 1 : 0;
@@ -468,9 +446,8 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
     if (!direct) {
       DLMCQ_LAUNCH_CHECK();
       const float gmul = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? qp->g : 1.f;
-      const int64_t fb = (cg.channels + kRowWarps - 1) / kRowWarps;
-      cmaj_finalize<<<static_cast<unsigned>(fb), kRowWarps * 32, 0, st>>>(ws_partials(ws), cg.channels, cg.chunks, gmul,
-                                                                        dscale);
+      chan_finalize<1><<<static_cast<unsigned>(cg.channels), 128, 0, st>>>(ws_partials(ws), cg.chunks, cg.chunks, 0,
+                                                                           gmul, dscale, nullptr);
     }
   } else {
     const RowGeom gm = make_geom(l);
@@ -485,9 +462,8 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
     if (!direct) {
       DLMCQ_LAUNCH_CHECK();
       const float gmul = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? qp->g : 1.f;
-      const int64_t fb = (gm.channels + kRowWarps - 1) / kRowWarps;
-      rows_finalize<<<static_cast<unsigned>(fb), kRowWarps * 32, 0, st>>>(ws_partials(ws), gm, l->outer, gmul,
-                                                                          dscale, doffset);
+      chan_finalize<2><<<static_cast<unsigned>(gm.channels), 128, 0, st>>>(
+          ws_partials(ws), l->outer * gm.segs, gm.segs, gm.channels * gm.segs, gmul, dscale, doffset);
     }
   }
   DLMCQ_LAUNCH_CHECK();

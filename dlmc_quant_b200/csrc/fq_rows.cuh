@@ -19,21 +19,29 @@ __device__ __forceinline__ void fwd_row_segment(const T* __restrict__ xr, T* __r
     const int64_t nvec = len / V::N;
     const raw* xv = reinterpret_cast<const raw*>(xr);
     constexpr int U = 4;                       // 128-bit loads in flight per lane
-    for (int64_t j = lane; j < nvec; j += 32 * U) {
+    auto one = [&](const raw& r, int64_t idx) {
+      float f[V::N], fy[V::N], fc[V::N];
+      V::unpack(r, f);
+      fq_vec<FORM, V::N>(f, p, lo, hi, fc, fy);
+      if (yr) st_stream(reinterpret_cast<raw*>(yr) + idx, V::pack(fy));
+      if (cr) st_stream(reinterpret_cast<raw*>(cr) + idx, V::pack(fc));
+    };
+    int64_t j = lane;
+    for (; j + 32 * (U - 1) < nvec; j += 32 * U) {
+      raw r[U];
+#pragma unroll
+      for (int h = 0; h < U; ++h) r[h] = ld_stream(xv + j + 32 * h);
+#pragma unroll
+      for (int h = 0; h < U; ++h) one(r[h], j + 32 * h);
+    }
+    if (j < nvec) {                            // last, partial block: still all loads first
       raw r[U];
 #pragma unroll
       for (int h = 0; h < U; ++h)
         if (j + 32 * h < nvec) r[h] = ld_stream(xv + j + 32 * h);
 #pragma unroll
-      for (int h = 0; h < U; ++h) {
-        if (j + 32 * h < nvec) {
-          float f[V::N], fy[V::N], fc[V::N];
-          V::unpack(r[h], f);
-          fq_vec<FORM, V::N>(f, p, lo, hi, fc, fy);
-          if (yr) st_stream(reinterpret_cast<raw*>(yr) + j + 32 * h, V::pack(fy));
-          if (cr) st_stream(reinterpret_cast<raw*>(cr) + j + 32 * h, V::pack(fc));
-        }
-      }
+      for (int h = 0; h < U; ++h)
+        if (j + 32 * h < nvec) one(r[h], j + 32 * h);
     }
     done = nvec * V::N;
   }
@@ -60,19 +68,37 @@ __device__ __forceinline__ void bwd_row_segment(const T* __restrict__ xr, const 
     const int64_t nvec = len / V::N;
     const raw* xv = reinterpret_cast<const raw*>(xr);
     const raw* gv = reinterpret_cast<const raw*>(gr);
-    for (int64_t j = lane; j < nvec; j += 64) {
-      const bool two = (j + 32) < nvec;
-      raw x0 = ld_stream(xv + j), g0 = ld_stream(gv + j), x1 = x0, g1 = g0;
-      if (two) { x1 = ld_stream(xv + j + 32); g1 = ld_stream(gv + j + 32); }
+    constexpr int U = 4;                       // 2 x 4 128-bit loads in flight per lane
+    auto one = [&](const raw& rx, const raw& rg, int64_t idx) {
+      float fx[V::N], fg[V::N], fo[V::N];
+      V::unpack(rx, fx);
+      V::unpack(rg, fg);
+      fq_vec_bwd<FORM, true, V::N>(fx, fg, p, lo, hi, fo, as, ao);
+      st_stream(reinterpret_cast<raw*>(dr) + idx, V::pack(fo));
+    };
+    int64_t j = lane;
+    for (; j + 32 * (U - 1) < nvec; j += 32 * U) {
+      raw rx[U], rg[U];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !two) break;
-        float fx[V::N], fg[V::N], fo[V::N];
-        V::unpack(h ? x1 : x0, fx);
-        V::unpack(h ? g1 : g0, fg);
-        fq_vec_bwd<FORM, true, V::N>(fx, fg, p, lo, hi, fo, as, ao);
-        st_stream(reinterpret_cast<raw*>(dr) + j + 32 * h, V::pack(fo));
+      for (int h = 0; h < U; ++h) {
+        rx[h] = ld_stream(xv + j + 32 * h);
+        rg[h] = ld_stream(gv + j + 32 * h);
       }
+#pragma unroll
+      for (int h = 0; h < U; ++h) one(rx[h], rg[h], j + 32 * h);
+    }
+    if (j < nvec) {                            // last, partial block: still all loads first
+      raw rx[U], rg[U];
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        if (j + 32 * h < nvec) {
+          rx[h] = ld_stream(xv + j + 32 * h);
+          rg[h] = ld_stream(gv + j + 32 * h);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < U; ++h)
+        if (j + 32 * h < nvec) one(rx[h], rg[h], j + 32 * h);
     }
     done = nvec * V::N;
   }

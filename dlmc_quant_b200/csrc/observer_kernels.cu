@@ -141,11 +141,34 @@ stats_rows_kernel(const T* __restrict__ x, RowGeom gm, float* __restrict__ stats
   if ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {
     const int64_t nvec = len / V::N;
     const raw* xv = reinterpret_cast<const raw*>(xr);
-    for (int64_t j = lane; j < nvec; j += 32) {
-      float f[V::N];
-      V::unpack(ld_stream(xv + j), f);
+    constexpr int U = 4;                                     // 128-bit loads in flight per lane
+    int64_t j = lane;
+    for (; j + 32 * (U - 1) < nvec; j += 32 * U) {
+      raw r[U];
 #pragma unroll
-      for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
+      for (int h = 0; h < U; ++h) r[h] = ld_stream(xv + j + 32 * h);
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        float f[V::N];
+        V::unpack(r[h], f);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
+      }
+    }
+    if (j < nvec) {                                          // last, partial block: still all loads first
+      raw r[U];
+#pragma unroll
+      for (int h = 0; h < U; ++h)
+        if (j + 32 * h < nvec) r[h] = ld_stream(xv + j + 32 * h);
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        if (j + 32 * h < nvec) {
+          float f[V::N];
+          V::unpack(r[h], f);
+#pragma unroll
+          for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
+        }
+      }
     }
     done = nvec * V::N;
   }
@@ -157,20 +180,62 @@ stats_rows_kernel(const T* __restrict__ x, RowGeom gm, float* __restrict__ stats
   }
 }
 
+// channel-major statistics for per-channel activations with short rows (see fq_cmaj_kernel): one warp per
+// (channel, batch chunk) walks the flattened (b, e) index space; partial [channel][chunk].
+template <typename T, bool ABS>
 __global__ void __launch_bounds__(kRowWarps * 32)
-stats_rows_finalize(const Stat4* __restrict__ part, RowGeom gm, int64_t outer, float* __restrict__ stats) {
+stats_cmaj_kernel(const T* __restrict__ x, CmajGeom gm, Stat4* __restrict__ part) {
   const int lane = threadIdx.x & 31;
-  const int64_t ch = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
-  if (ch >= gm.channels) return;
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (item >= gm.channels * gm.chunks) return;
+  const int64_t jc = item / gm.channels, c = item - jc * gm.channels;   // adjacent warps: adjacent channels
+  const int64_t b0 = jc * gm.bc;
+  const int64_t nb = (gm.outer - b0) < gm.bc ? (gm.outer - b0) : gm.bc;
+  const uint32_t total = static_cast<uint32_t>(nb * gm.inner);
+  const uint32_t inner = static_cast<uint32_t>(gm.inner);
+  const uint32_t plane = static_cast<uint32_t>(gm.channels * gm.inner);
+  const T* xb = x + (b0 * gm.channels + c) * gm.inner;
   Stat4 s;
   stat_init(s);
-  const int64_t per = outer * gm.segs;
-  for (int64_t k = lane; k < per; k += 32) {
-    const int64_t b = k / gm.segs, sg = k - b * gm.segs;
-    stat_merge(s, part[(b * gm.channels + ch) * gm.segs + sg]);
+  constexpr int U = 8;
+  for (uint32_t t0 = 0; t0 < total; t0 += 32 * U) {
+    float v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t t = t0 + u * 32 + lane;
+      ok[u] = t < total;
+      const uint32_t bl = static_cast<uint32_t>((static_cast<uint64_t>(t) * gm.magic) >> 24);
+      v[u] = ok[u] ? to_f32<T>(xb[bl * plane + (t - bl * inner)]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (ok[u]) stat_add<ABS>(s, v[u]);
   }
   s = stat_warp(s);
-  if (lane == 0) stat_store(stats + 4 * ch, s);
+  if (lane == 0) part[c * gm.chunks + jc] = s;
+}
+
+// one CTA per channel: merge that channel's `per` partials at part[(k / inner_n) * stride_o + ch * inner_n +
+// (k % inner_n)] (rows: k = (b, seg), stride_o = C * segs, inner_n = segs; channel-major: stride_o = 0).
+__global__ void __launch_bounds__(128)
+stats_finalize_kernel(const Stat4* __restrict__ part, int64_t per, int64_t inner_n, int64_t stride_o,
+                      float* __restrict__ stats) {
+  __shared__ Stat4 sh[4];
+  const int64_t ch = blockIdx.x;
+  Stat4 s;
+  stat_init(s);
+  for (int64_t k = threadIdx.x; k < per; k += blockDim.x) {
+    const int64_t o = k / inner_n, i = k - o * inner_n;
+    stat_merge(s, part[o * stride_o + ch * inner_n + i]);
+  }
+  s = stat_warp(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w) stat_merge(s, sh[w]);
+    stat_store(stats + 4 * ch, s);
+  }
 }
 
 // ops.py:20-34 / 121-140
@@ -229,8 +294,61 @@ __device__ __forceinline__ float sweep_err2_fast(float x, const FastDiv& fd, flo
   return d * d;
 }
 
-constexpr int kSweepElems = 8;   // elements a thread holds in registers per tile (fp32: two 128-bit loads)
+// ---- fast candidate evaluation ---------------------------------------------------------------
+// With an integer zero-point zp and integer bounds, clamp(rint(q) + zp, 0, qmax) - zp ==
+// rint(clamp(q, -zp, qmax - zp)) (rint is monotonic and integers are its fixed points), and for |c| < 2^22
+// rint(c) == (c + 1.5*2^23) - 1.5*2^23.  That removes the half-rate FRND and two adds per element; what is
+// left per candidate-element is: 3 (exact division) + 2 (max.NaN/min.NaN) + 2 (round) + 1 (x scale) +
+// 1 (- x) + 1 (fma into the running sum) = 10 instructions, 8 of them on the fp32 pipe.  The fp32-pipe ops
+// are issued as packed f32x2 instructions (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE-RN results per lane per
+// issue slot), which is what the sweep - issue-bound once x sits in registers - is limited by.
+// Valid when the candidate scale is in the fast-division domain, |zp| <= 2^21 and qmax <= 2^21; every
+// per-element value is bit-identical to sweep_err2, only the summation order differs.
+struct SweepCand {
+  float ns;   // -scale
+  float r;    // RN(1 / scale)
+  float a;    // -zp
+  float b;    // qmax - zp
+};
+__device__ __forceinline__ bool sweep_cand_fast(float sc, float zp, float qmax, SweepCand& c) {
+  const FastDiv fd = make_fastdiv(sc);
+  c.ns = -sc;
+  c.r = fd.r;
+  c.a = -zp;
+  c.b = qmax - zp;
+  return fd.ok && (fabsf(zp) <= 0x1p21f) && (qmax <= 0x1p21f);   // NaN zp -> false
+}
+__device__ __forceinline__ float2 sweep_pair_fast(float2 x, const SweepCand& c, float2 acc) {
+  const float2 r2 = make_float2(c.r, c.r), ns2 = make_float2(c.ns, c.ns);
+  const float2 q0 = __fmul2_rn(x, r2);
+  const float2 e = __ffma2_rn(ns2, q0, x);
+  const float2 q = __ffma2_rn(e, r2, q0);
+  float2 k;
+  k.x = min_nan(max_nan(q.x, c.a), c.b);
+  k.y = min_nan(max_nan(q.y, c.a), c.b);
+  const float2 t = __fadd2_rn(k, make_float2(kRoundMagic, kRoundMagic));
+  const float2 rr = __fadd2_rn(t, make_float2(-kRoundMagic, -kRoundMagic));
+  // -(code - zp) * scale with two scalar mul.rn: ptxas contracts a mul.rn.f32x2 feeding an add.rn.f32x2
+  // into one FFMA2 (it never does for scalar mul.rn), which would skip the reference's rounding of the
+  // dequantised value.
+  const float2 ny = make_float2(__fmul_rn(rr.x, c.ns), __fmul_rn(rr.y, c.ns));
+  const float2 d = __fadd2_rn(x, ny);               // x - y: same square as y - x
+  return __ffma2_rn(d, d, acc);
+}
+__device__ __forceinline__ float sweep_one_fast(float x, const SweepCand& c, float acc) {
+  const float q0 = __fmul_rn(x, c.r);
+  const float e = __fmaf_rn(c.ns, q0, x);
+  const float q = __fmaf_rn(e, c.r, q0);
+  const float k = min_nan(max_nan(q, c.a), c.b);
+  const float rr = (k + kRoundMagic) - kRoundMagic;
+  const float d = x + rr * c.ns;
+  return __fmaf_rn(d, d, acc);
+}
 
+constexpr int kSweepElems = 16;  // elements a thread holds in registers per tile (fp32: four 128-bit loads)
+
+// Per-thread running sums live in shared memory ([candidate][thread], conflict-free): one LDS + STS per
+// candidate per tile instead of a 10-instruction warp reduction; the block reduces them once at the end.
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 sweep_tensor_kernel(const T* __restrict__ x, int64_t n, const float* __restrict__ stats, float qmax, int allow_offset,
@@ -239,19 +357,21 @@ sweep_tensor_kernel(const T* __restrict__ x, int64_t n, const float* __restrict_
   using raw = typename V::raw;
   constexpr int NV = kSweepElems / V::N >= 1 ? kSweepElems / V::N : 1;   // vectors per thread per tile
   constexpr int NE = NV * V::N;
-  __shared__ float c_sc[kNC], c_zp[kNC], c_rc[kNC];
-  __shared__ int c_ok[kNC];
-  __shared__ float w_acc[kThreads / 32][kNC];
+  extern __shared__ __align__(16) float w_acc[];                          // [kNC][kThreads]
+  __shared__ float c_sc[kNC], c_zp[kNC];
+  __shared__ __align__(16) SweepCand c_par[kNC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int ok = 1;
   if (threadIdx.x < kNC) {
     const float lo = allow_offset ? stats[0] : 0.f;
     sweep_candidate(threadIdx.x, lo, stats[1], qmax, c_sc[threadIdx.x], c_zp[threadIdx.x]);
-    const FastDiv fd = make_fastdiv(c_sc[threadIdx.x]);
-    c_rc[threadIdx.x] = fd.r;
-    c_ok[threadIdx.x] = fd.ok ? 1 : 0;
+    SweepCand c;
+    ok = sweep_cand_fast(c_sc[threadIdx.x], c_zp[threadIdx.x], qmax, c) ? 1 : 0;
+    c_par[threadIdx.x] = c;
   }
-  for (int k = threadIdx.x; k < (kThreads / 32) * kNC; k += blockDim.x) (&w_acc[0][0])[k] = 0.f;
-  __syncthreads();
+  for (int k = threadIdx.x; k < kNC * kThreads; k += kThreads) w_acc[k] = 0.f;
+  const bool all_fast = __syncthreads_and(ok) != 0;
+  float* my_acc = w_acc + threadIdx.x;
 
   const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
   const int64_t nvec = vec ? n / V::N : 0;
@@ -259,54 +379,58 @@ sweep_tensor_kernel(const T* __restrict__ x, int64_t n, const float* __restrict_
   const raw* xv = reinterpret_cast<const raw*>(x);
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     float f[NE];
+    raw r[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) r[v] = ld_stream(xv + (t * NV + v) * kThreads + threadIdx.x);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       float tmp[V::N];
-      V::unpack(ld_stream(xv + (t * NV + v) * kThreads + threadIdx.x), tmp);
+      V::unpack(r[v], tmp);
 #pragma unroll
       for (int e = 0; e < V::N; ++e) f[v * V::N + e] = tmp[e];
     }
     float m = 0.f;
 #pragma unroll
     for (int e = 0; e < NE; ++e) m = fmaxf(m, fabsf(f[e]));
-    const bool tile_ok = m <= kFastDivMaxX;      // inf / huge values: literal chain for this thread's tile
+    if (all_fast && m <= kFastDivMaxX) {         // inf / huge values: literal chain for this thread's tile
 #pragma unroll 2
-    for (int c = 0; c < kNC; ++c) {
-      const float sc = c_sc[c], zp = c_zp[c];
-      float a = 0.f;
-      if (tile_ok && c_ok[c]) {
-        FastDiv fd;
-        fd.s = sc; fd.r = c_rc[c]; fd.ok = true;
+      for (int c = 0; c < kNC; ++c) {
+        const SweepCand cp = c_par[c];
+        float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < NE; ++e) a += sweep_err2_fast(f[e], fd, zp, qmax);
-      } else {
+        for (int e = 0; e < NE; e += 4) {
+          a0 = sweep_pair_fast(make_float2(f[e], f[e + 1]), cp, a0);
+          a1 = sweep_pair_fast(make_float2(f[e + 2], f[e + 3]), cp, a1);
+        }
+        my_acc[c * kThreads] += (a0.x + a0.y) + (a1.x + a1.y);
+      }
+    } else {
+      for (int c = 0; c < kNC; ++c) {
+        const float sc = c_sc[c], zp = c_zp[c];
+        float a = 0.f;
 #pragma unroll
         for (int e = 0; e < NE; ++e) a += sweep_err2(f[e], sc, zp, qmax);
+        my_acc[c * kThreads] += a;
       }
-      a = warp_sum(a);
-      if (lane == 0) w_acc[warp][c] += a;
     }
   }
   // remainder (elements past the last full tile, or everything when x is unaligned): block 0
   if (blockIdx.x == 0) {
     const int64_t start = tiles * kThreads * NE;
-    for (int64_t j = start + threadIdx.x; j < start + ((n - start + kThreads - 1) / kThreads) * kThreads; j += kThreads) {
-      const bool ok = j < n;
-      const float v = ok ? to_f32<T>(x[j]) : 0.f;
-      for (int c = 0; c < kNC; ++c) {
-        float a = ok ? sweep_err2(v, c_sc[c], c_zp[c], qmax) : 0.f;
-        a = warp_sum(a);
-        if (lane == 0) w_acc[warp][c] += a;
-      }
+    for (int64_t j = start + threadIdx.x; j < n; j += kThreads) {
+      const float v = to_f32<T>(x[j]);
+      for (int c = 0; c < kNC; ++c) my_acc[c * kThreads] += sweep_err2(v, c_sc[c], c_zp[c], qmax);
     }
   }
   __syncthreads();
+  // block reduction: warp w sums candidates w, w+8, ... over the 256 per-thread sums in a fixed order
   float* part = ws_partials(ws);
-  if (threadIdx.x < kNC) {
+  for (int c = warp; c < kNC; c += kThreads / 32) {
     float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) a += w_acc[w][threadIdx.x];
-    part[static_cast<int64_t>(blockIdx.x) * kNC + threadIdx.x] = a;
+    for (int k = 0; k < kThreads / 32; ++k) a += w_acc[c * kThreads + k * 32 + lane];
+    a = warp_sum(a);
+    if (lane == 0) part[static_cast<int64_t>(blockIdx.x) * kNC + c] = a;
   }
   if (take_last_ticket(ws_counter(ws), gridDim.x)) {
     if (threadIdx.x < kNC) {
@@ -342,51 +466,87 @@ __global__ void sweep_tensor_finalize_kernel(const float* __restrict__ sse, cons
 }
 
 // ---------------------------------------------------------------------------------------
-// 80-candidate sweep, per channel: one warp per row, row staged in shared memory by TMA
+// 80-candidate sweep, per channel: `wpr` warps per row (1, 2, 4 or 8 - chosen on the host so that few-row
+// tensors still fill the GPU), the row staged ONCE in shared memory by a bulk async copy (TMA 1-D:
+// cp.async.bulk + mbarrier, SASS UBLKCP) and swept 80 times on chip.  The reference's accept rule is
+// sequential (ops.py:191-194 and its aliasing of min_val with the offset vector), so every candidate's
+// sum is reduced across the row's warps before the next candidate's scale is known: warp shuffle ->
+// shared memory -> named barrier of the row's warps only, double-buffered by parity.
 // ---------------------------------------------------------------------------------------
-constexpr int kSweepRowCap = 6144;            // floats of shared memory per warp (24 KB)
-constexpr int kSweepWarps = 8;                // 8 x 24 KB = 192 KB of the 227 KB per CTA
+constexpr int kSweepWarps = 8;                 // warps per CTA
+constexpr int kSweepSmemFloats = 50 * 1024;    // 200 KB of row staging per CTA at most
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct SweepRowGroup {
+  float* red;      // [2][kSweepWarps] exchange slots of this row's warps
+  int wpr, wig, lane, bar_id;
+  int parity;
+  // all-reduce over the row's warps; every thread of the group returns the same value (fixed order)
+  template <typename Op>
+  __device__ __forceinline__ float all(float v, Op op) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (wpr == 1) return v;
+    float* slot = red + parity * kSweepWarps;
+    parity ^= 1;
+    if (lane == 0) slot[wig] = v;
+    group_bar(bar_id, wpr * 32);
+    float t = slot[0];
+    for (int w = 1; w < wpr; ++w) t = op(t, slot[w]);
+    return t;
+  }
+};
 
 template <typename T>
-__global__ void __launch_bounds__(kSweepWarps * 32, 1)
+__global__ void __launch_bounds__(kSweepWarps * 32)
 sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, float qmax, float signed_div,
-                     int is_signed, float* __restrict__ scale, float* __restrict__ offset) {
+                     int is_signed, float* __restrict__ scale, float* __restrict__ offset, int wpr, int row_floats,
+                     int staged) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) unsigned long long bars[kSweepWarps];
+  __shared__ float red_all[kSweepWarps][2][kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * kSweepWarps + warp;
-  if (row >= channels) return;                 // whole warp exits together; no block-wide sync below
-  float* buf = reinterpret_cast<float*>(dyn_smem) + static_cast<size_t>(warp) * kSweepRowCap;
+  const int group = warp / wpr, wig = warp - group * wpr;
+  const int rows_per_cta = kSweepWarps / wpr;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * rows_per_cta + group;
+  if (row >= channels) return;                 // a whole row group exits together; barriers are per group
+  const int tg = wig * 32 + lane, gt = wpr * 32;
+  SweepRowGroup grp{&red_all[group][0][0], wpr, wig, lane, group + 1, 0};
+  float* buf = reinterpret_cast<float*>(dyn_smem) + static_cast<size_t>(group) * row_floats;
   const T* xr = x + row * inner;
-  const bool staged = inner <= kSweepRowCap - 8;
-  const float* src = nullptr;                  // fp32 view of the row: shared-memory copy when it fits
+  const float* src = nullptr;                  // fp32 view of the row in shared memory (element j at src[j])
+  int64_t h = 0, body = 0;                     // [h, h+body) is the 16-byte aligned interior
   if (staged) {
+    float* dst = buf + 4;
     if (sizeof(T) == 4) {
-      // 16-byte aligned interior by one bulk async copy; the <=3 head / tail elements by plain loads.
+      // aligned interior by one bulk async copy issued by the group's first thread; the <=3 head and
+      // tail elements by plain loads.  dst + h is 16-byte aligned in shared memory like xr + h in global.
       const uintptr_t a = reinterpret_cast<uintptr_t>(xr);
-      const int head = static_cast<int>(((16 - (a & 15u)) & 15u) / 4);       // elements before alignment
-      const int64_t h = head < inner ? head : inner;
-      const int64_t body = ((inner - h) / 4) * 4;                             // multiple of 16 bytes
-      float* dst = buf + 4 - h;                                               // dst+h is 16-byte aligned
-      const uint32_t bar = smem_u32(&bars[warp]);
-      if (lane == 0) {
+      const int head = static_cast<int>(((16 - (a & 15u)) & 15u) / 4);
+      h = head < inner ? head : inner;
+      body = ((inner - h) / 4) * 4;
+      dst = buf + 4 - h;
+      const uint32_t bar = smem_u32(&bars[group]);
+      if (tg == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
-      __syncwarp();
-      if (body > 0 && lane == 0) {
+      if (wpr == 1) __syncwarp(); else group_bar(grp.bar_id, gt);
+      if (body > 0 && tg == 0) {
         const uint32_t bytes = static_cast<uint32_t>(body * 4);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(dst + h)), "l"(reinterpret_cast<const float*>(xr) + h), "r"(bytes), "r"(bar)
                      : "memory");
       }
-      for (int64_t j = lane; j < h; j += 32) dst[j] = to_f32<T>(xr[j]);
-      for (int64_t j = h + body + lane; j < inner; j += 32) dst[j] = to_f32<T>(xr[j]);
+      for (int64_t j = tg; j < h; j += gt) dst[j] = to_f32<T>(xr[j]);
+      for (int64_t j = h + body + tg; j < inner; j += gt) dst[j] = to_f32<T>(xr[j]);
       if (body > 0) {
         uint32_t ok = 0;
         while (!ok) {
@@ -394,26 +554,30 @@ sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, f
                        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
         }
       }
-      __syncwarp();
-      src = dst;
     } else {
-      for (int64_t j = lane; j < inner; j += 32) buf[j] = to_f32<T>(xr[j]);   // bf16: convert while staging
-      __syncwarp();
-      src = buf;
+      for (int64_t j = tg; j < inner; j += gt) dst[j] = to_f32<T>(xr[j]);   // bf16: convert while staging
+      body = (inner / 4) * 4;
     }
+    if (wpr == 1) __syncwarp(); else group_bar(grp.bar_id, gt);
+    src = dst;
   }
   auto at = [&](int64_t j) -> float { return staged ? src[j] : to_f32<T>(xr[j]); };
+  const int64_t nvec = staged ? body / 4 : 0;
+  const float4* sv = reinterpret_cast<const float4*>(src + h);
+  const int64_t n_edge = staged ? inner - body : 0;       // head + tail elements, handled one per thread
 
   // row statistics (ops.py:171 -> quantize_minmax_channel)
-  float mn = INFINITY, mx = -INFINITY, am = 0.f;
-  bool nan = false;
-  for (int64_t j = lane; j < inner; j += 32) {
+  float mn = INFINITY, mx = -INFINITY, am = 0.f, nanf_ = 0.f;
+  for (int64_t j = tg; j < inner; j += gt) {
     const float v = at(j);
-    nan |= (v != v);
+    nanf_ = (v != v) ? 1.f : nanf_;
     mn = fminf(mn, v); mx = fmaxf(mx, v); am = fmaxf(am, fabsf(v));
   }
-  mn = warp_min(mn); mx = warp_max(mx); am = warp_max(am);
-  nan = __any_sync(0xffffffffu, nan);
+  auto fmin_op = [](float a, float b) { return fminf(a, b); };
+  auto fmax_op = [](float a, float b) { return fmaxf(a, b); };
+  auto add_op = [](float a, float b) { return a + b; };
+  mn = grp.all(mn, fmin_op); mx = grp.all(mx, fmax_op); am = grp.all(am, fmax_op);
+  const bool nan = grp.all(nanf_, fmax_op) != 0.f;
   const bool row_fast = am <= kFastDivMaxX;      // no inf / huge value in the row
   if (nan) mn = mx = am = NAN;
   float cur_scale, cur_off;
@@ -425,14 +589,24 @@ sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, f
   for (int i = 0; i < kNC; ++i) {
     float sc, zp;
     sweep_candidate(i, min_v, max_v, qmax, sc, zp);                        // ops.py:179-185
+    SweepCand cp;
+    const bool fast = sweep_cand_fast(sc, zp, qmax, cp) && row_fast;
     float a = 0.f;
-    const FastDiv fd = make_fastdiv(sc);
-    if (fd.ok && row_fast) {
-      for (int64_t j = lane; j < inner; j += 32) a += sweep_err2_fast(at(j), fd, zp, qmax);
+    if (fast && staged) {
+      float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+      for (int64_t v = tg; v < nvec; v += gt) {
+        const float4 q = sv[v];
+        a0 = sweep_pair_fast(make_float2(q.x, q.y), cp, a0);
+        a1 = sweep_pair_fast(make_float2(q.z, q.w), cp, a1);
+      }
+      a = (a0.x + a0.y) + (a1.x + a1.y);
+      if (tg < n_edge) a = sweep_one_fast(src[tg < h ? tg : body + tg], cp, a);
+    } else if (fast) {
+      for (int64_t j = tg; j < inner; j += gt) a = sweep_one_fast(at(j), cp, a);
     } else {
-      for (int64_t j = lane; j < inner; j += 32) a += sweep_err2(at(j), sc, zp, qmax);
+      for (int64_t j = tg; j < inner; j += gt) a += sweep_err2(at(j), sc, zp, qmax);
     }
-    a = warp_sum(a);
+    a = grp.all(a, add_op);
     if (best > a) {                                                        // ops.py:191-194
       cur_scale = sc;
       cur_off = zp;
@@ -440,12 +614,32 @@ sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, f
       best = a;
     }
   }
-  if (lane == 0) { scale[row] = cur_scale; offset[row] = cur_off; }
+  if (tg == 0) { scale[row] = cur_scale; offset[row] = cur_off; }
 }
 
 // ---------------------------------------------------------------------------------------
 // l2norm fixed point: one iteration
 // ---------------------------------------------------------------------------------------
+// Inner product terms of one iteration on the fast path (packed f32x2, 6 issue slots per element):
+//   code = clamp(rint(q), lo, hi) == rint(clamp(q, lo, hi)) for integer bounds == (c + 1.5*2^23) - 1.5*2^23;
+//   a += x * code ; b += code * code + 1e-7 (code^2 is exact, so fma(code, code, 1e-7) is the reference's
+//   rounded sum).  The sign of a zero code is not kept - it cannot change either dot product.
+__device__ __forceinline__ void l2norm_pair_fast(float2 x, const ChanParams& p, float lo, float hi, float2& a,
+                                                 float2& b) {
+  const float2 r2 = make_float2(p.fd.r, p.fd.r), ns2 = make_float2(-p.div, -p.div);
+  const float2 num = __fadd2_rn(x, make_float2(-p.off, -p.off));
+  const float2 q0 = __fmul2_rn(num, r2);
+  const float2 e = __ffma2_rn(ns2, q0, num);
+  const float2 q = __ffma2_rn(e, r2, q0);
+  float2 k;
+  k.x = min_nan(max_nan(q.x, lo), hi);
+  k.y = min_nan(max_nan(q.y, lo), hi);
+  const float2 t = __fadd2_rn(k, make_float2(kRoundMagic, kRoundMagic));
+  const float2 code = __fadd2_rn(t, make_float2(-kRoundMagic, -kRoundMagic));
+  a = __ffma2_rn(x, code, a);
+  b = __fadd2_rn(b, __ffma2_rn(code, code, make_float2(1e-7f, 1e-7f)));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kRowWarps * 32)
 l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict__ scale,
@@ -463,13 +657,23 @@ l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict_
   const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
   const T* xr = x + row * gm.inner + beg;
   float a = 0.f, b = 0.f;
+  float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
+  const bool fast_p = p.fd.ok && fabsf(p.off) <= 0x1p59f;
   auto add_vec = [&](const float (&f)[V::N]) {
-    float code[V::N], y[V::N];
-    fq_vec<DLMCQ_FORM_A1, V::N>(f, p, lo, hi, code, y);   // ops.py:78,206 quantize()
+    float m = 0.f;
 #pragma unroll
-    for (int e = 0; e < V::N; ++e) {
-      a += f[e] * code[e];                                 // (tensor * tensor_q).sum()
-      b += code[e] * code[e] + 1e-7f;                      // (tensor_q * tensor_q + 1e-7).sum()
+    for (int e = 0; e < V::N; ++e) m = fmaxf(m, fabsf(f[e]));
+    if (fast_p && m <= 0x1p59f) {                            // |x - off| <= 2^60: the verified division domain
+#pragma unroll
+      for (int e = 0; e < V::N; e += 2) l2norm_pair_fast(make_float2(f[e], f[e + 1]), p, lo, hi, a2, b2);
+    } else {
+      float code[V::N], y[V::N];
+      fq_vec<DLMCQ_FORM_A1, V::N>(f, p, lo, hi, code, y);   // ops.py:78,206 quantize()
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) {
+        a += f[e] * code[e];                                 // (tensor * tensor_q).sum()
+        b += code[e] * code[e] + 1e-7f;                      // (tensor_q * tensor_q + 1e-7).sum()
+      }
     }
   };
   auto add = [&](float v) {
@@ -482,21 +686,38 @@ l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict_
   if ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {
     const int64_t nvec = len / V::N;
     const raw* xv = reinterpret_cast<const raw*>(xr);
-    for (int64_t j = lane; j < nvec; j += 64) {
-      const bool two = (j + 32) < nvec;
-      raw r0 = ld_stream(xv + j), r1 = r0;
-      if (two) r1 = ld_stream(xv + j + 32);
-      float f[V::N];
-      V::unpack(r0, f);
-      add_vec(f);
-      if (two) {
-        V::unpack(r1, f);
+    constexpr int U = 4;                                     // 128-bit loads in flight per lane
+    int64_t j = lane;
+    for (; j + 32 * (U - 1) < nvec; j += 32 * U) {
+      raw r[U];
+#pragma unroll
+      for (int h = 0; h < U; ++h) r[h] = ld_stream(xv + j + 32 * h);
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        float f[V::N];
+        V::unpack(r[h], f);
         add_vec(f);
+      }
+    }
+    if (j < nvec) {                                          // last, partial block: still all loads first
+      raw r[U];
+#pragma unroll
+      for (int h = 0; h < U; ++h)
+        if (j + 32 * h < nvec) r[h] = ld_stream(xv + j + 32 * h);
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        if (j + 32 * h < nvec) {
+          float f[V::N];
+          V::unpack(r[h], f);
+          add_vec(f);
+        }
       }
     }
     fin = nvec * V::N;
   }
   for (int64_t j = fin + lane; j < len; j += 32) add(to_f32<T>(xr[j]));
+  a += a2.x + a2.y;
+  b += b2.x + b2.y;
   a = warp_sum(a);
   b = warp_sum(b);
   if (lane == 0) { part[2 * item] = a; part[2 * item + 1] = b; }
@@ -567,6 +788,53 @@ l2norm_finalize_kernel(const float* __restrict__ part, RowGeom gm, float* __rest
   }
 }
 
+// Per-channel variant: one thread per channel over ceil(C / 256) CTAs; the CTA that draws the last ticket
+// combines the per-CTA (|ds|^2, |s|^2) sums in a fixed order and sets the convergence flag (ops.py:207-210).
+__global__ void __launch_bounds__(kThreads)
+l2norm_finalize_channels_kernel(const float* __restrict__ part, RowGeom gm, float* __restrict__ scale,
+                                float* __restrict__ diff, int32_t* __restrict__ done, int32_t* __restrict__ iters,
+                                double* __restrict__ cta_part, unsigned int* __restrict__ counter) {
+  __shared__ double sh[2][kThreads / 32];
+  if (*done) return;        // only the last CTA of an iteration ever sets it, after every CTA passed this test
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  double num = 0.0, den = 0.0;
+  if (c < gm.channels) {
+    double a = 0.0, b = 0.0;
+    for (int64_t sg = 0; sg < gm.segs; ++sg) {
+      a += part[2 * (c * gm.segs + sg)];
+      b += part[2 * (c * gm.segs + sg) + 1];
+    }
+    const float s_old = scale[c];
+    const float s_new = static_cast<float>(a) / static_cast<float>(b);
+    scale[c] = s_new;
+    const float d = s_new - s_old;
+    num = static_cast<double>(d * d);
+    den = static_cast<double>(s_old * s_old);
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  if (lane == 0) { sh[0][warp] = num; sh[1][warp] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tn = 0.0, td = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { tn += sh[0][w]; td += sh[1][w]; }
+    cta_part[2 * blockIdx.x] = tn;
+    cta_part[2 * blockIdx.x + 1] = td;
+  }
+  if (take_last_ticket(counter, gridDim.x)) {
+    if (threadIdx.x == 0) {
+      double tn = 0.0, td = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) { tn += cta_part[2 * b]; td += cta_part[2 * b + 1]; }
+      const float df = sqrtf(static_cast<float>(tn)) / sqrtf(static_cast<float>(td));   // ops.py:209
+      diff[0] = df;
+      if (iters) iters[0] += 1;
+      if (!(df > 1e-5f)) done[0] = 1;
+      *counter = 0u;
+    }
+  }
+}
+
 template <typename T, bool ABS>
 static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = l->outer * l->channels * l->inner;
@@ -574,6 +842,14 @@ static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* w
   if (l->channels == 1) {
     const int64_t tiles = (n / Vec<T>::N + kThreads * 4 - 1) / (kThreads * 4);
     stats_flat_kernel<T, ABS><<<stream_grid(tiles, 8), kThreads, 0, st>>>(x, n, stats, ws);
+  } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
+    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner);
+    const int64_t blocks = (cg.channels * cg.chunks + kRowWarps - 1) / kRowWarps;
+    if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+    Stat4* part = reinterpret_cast<Stat4*>(ws_partials(ws));
+    stats_cmaj_kernel<T, ABS><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(x, cg, part);
+    DLMCQ_LAUNCH_CHECK();
+    stats_finalize_kernel<<<static_cast<unsigned>(cg.channels), 128, 0, st>>>(part, cg.chunks, cg.chunks, 0, stats);
   } else {
     const RowGeom gm = make_geom(l->outer, l->channels, l->inner);
     const int64_t items = gm.rows * gm.segs;
@@ -584,8 +860,8 @@ static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* w
     stats_rows_kernel<T, ABS><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(x, gm, stats, part, direct);
     if (!direct) {
       DLMCQ_LAUNCH_CHECK();
-      const int64_t fb = (gm.channels + kRowWarps - 1) / kRowWarps;
-      stats_rows_finalize<<<static_cast<unsigned>(fb), kRowWarps * 32, 0, st>>>(part, gm, l->outer, stats);
+      stats_finalize_kernel<<<static_cast<unsigned>(gm.channels), 128, 0, st>>>(part, l->outer * gm.segs, gm.segs,
+                                                                                 gm.channels * gm.segs, stats);
     }
   }
   DLMCQ_LAUNCH_CHECK();
@@ -645,14 +921,23 @@ extern "C" int dlmcq_obs_sweep_tensor_sse(const void* x, int64_t numel, int dtyp
   const float qmax = static_cast<float>((1 << n_bits) - 1);
   const int64_t tiles = (numel + kThreads * kSweepElems - 1) / (kThreads * kSweepElems);
   const int grid = stream_grid(tiles, 2);
-  if (dtype == DLMCQ_F32)
-    sweep_tensor_kernel<float><<<grid, kThreads, 0, st>>>(static_cast<const float*>(x), numel, stats, qmax,
-                                                          allow_offset, sse, workspace);
-  else if (dtype == DLMCQ_BF16)
-    sweep_tensor_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), numel, stats,
-                                                                  qmax, allow_offset, sse, workspace);
-  else
+  const size_t smem = static_cast<size_t>(kNC) * kThreads * sizeof(float);   // per-thread running sums
+  cudaError_t e;
+  if (dtype == DLMCQ_F32) {
+    e = cudaFuncSetAttribute(sweep_tensor_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    sweep_tensor_kernel<float><<<grid, kThreads, smem, st>>>(static_cast<const float*>(x), numel, stats, qmax,
+                                                             allow_offset, sse, workspace);
+  } else if (dtype == DLMCQ_BF16) {
+    e = cudaFuncSetAttribute(sweep_tensor_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    sweep_tensor_kernel<__nv_bfloat16><<<grid, kThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), numel,
+                                                                     stats, qmax, allow_offset, sse, workspace);
+  } else {
     return DLMCQ_EINVAL;
+  }
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
 }
@@ -671,27 +956,37 @@ extern "C" int dlmcq_obs_sweep_tensor_finalize(const float* sse, const float* st
 extern "C" int dlmcq_obs_sweep_channel(const void* x, int64_t channels, int64_t inner, int dtype, int n_bits,
                                        int is_signed, float* scale, float* offset, void* stream) {
   if (!x || !scale || !offset || channels < 1 || inner < 1 || n_bits < 1 || n_bits > 24) return DLMCQ_EINVAL;
+  if (dtype != DLMCQ_F32 && dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float qmax = static_cast<float>((1 << n_bits) - 1);
   const float sdiv = static_cast<float>((1 << (n_bits - 1)) - 1);
-  const size_t smem = static_cast<size_t>(kSweepWarps) * kSweepRowCap * sizeof(float);
-  const int64_t blocks = (channels + kSweepWarps - 1) / kSweepWarps;
+  // warps per row: enough warps to fill the GPU (>= 16 per SM) when the tensor has few rows, but at
+  // least 128 elements per warp; fewer rows per CTA when the staged rows would not fit in shared memory
+  int wpr = 1;
+  const int64_t want_warps = static_cast<int64_t>(num_sms()) * 16;
+  while (wpr < kSweepWarps && channels * wpr < want_warps && inner >= 256LL * wpr) wpr *= 2;
+  const int64_t row_floats = ((inner + 8 + 3) / 4) * 4;
+  while (wpr < kSweepWarps && (kSweepWarps / wpr) * row_floats > kSweepSmemFloats) wpr *= 2;
+  const int staged = (kSweepWarps / wpr) * row_floats <= kSweepSmemFloats ? 1 : 0;
+  const int rows_per_cta = kSweepWarps / wpr;
+  const size_t smem = staged ? static_cast<size_t>(rows_per_cta) * row_floats * sizeof(float) : 0;
+  const int64_t blocks = (channels + rows_per_cta - 1) / rows_per_cta;
   if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
   cudaError_t e;
   if (dtype == DLMCQ_F32) {
     e = cudaFuncSetAttribute(sweep_channel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
+                             static_cast<int>(kSweepSmemFloats * sizeof(float)));
     if (e != cudaSuccess) return set_cuda_error(e);
     sweep_channel_kernel<float><<<static_cast<unsigned>(blocks), kSweepWarps * 32, smem, st>>>(
-        static_cast<const float*>(x), channels, inner, qmax, sdiv, is_signed, scale, offset);
-  } else if (dtype == DLMCQ_BF16) {
+        static_cast<const float*>(x), channels, inner, qmax, sdiv, is_signed, scale, offset, wpr,
+        static_cast<int>(row_floats), staged);
+  } else {
     e = cudaFuncSetAttribute(sweep_channel_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
+                             static_cast<int>(kSweepSmemFloats * sizeof(float)));
     if (e != cudaSuccess) return set_cuda_error(e);
     sweep_channel_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), kSweepWarps * 32, smem, st>>>(
-        static_cast<const __nv_bfloat16*>(x), channels, inner, qmax, sdiv, is_signed, scale, offset);
-  } else {
-    return DLMCQ_EINVAL;
+        static_cast<const __nv_bfloat16*>(x), channels, inner, qmax, sdiv, is_signed, scale, offset, wpr,
+        static_cast<int>(row_floats), staged);
   }
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
@@ -704,7 +999,10 @@ extern "C" int dlmcq_obs_l2norm_step(const void* x, int64_t channels, int64_t in
   dlmcq_layout l = {1, channels, inner, dtype};
   if (workspace_bytes < dlmcq_workspace_bytes(&l)) return DLMCQ_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const RowGeom gm = make_geom(1, channels, inner);
+  // few long rows (per-tensor): cap the number of (row, segment) partials the single finalising CTA sums
+  int64_t seg_min = kRowSegMin;
+  while (channels * ((inner + seg_min - 1) / seg_min) > 8192 && seg_min < (int64_t(1) << 40)) seg_min *= 2;
+  const RowGeom gm = make_geom(1, channels, inner, seg_min);
   const int64_t items = gm.rows * gm.segs;
   const int64_t blocks = (items + kRowWarps - 1) / kRowWarps;
   if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
@@ -719,7 +1017,16 @@ extern "C" int dlmcq_obs_l2norm_step(const void* x, int64_t channels, int64_t in
   else
     return DLMCQ_EINVAL;
   DLMCQ_LAUNCH_CHECK();
-  l2norm_finalize_kernel<<<1, kThreads, 0, st>>>(part, gm, scale, diff, done, iters);
+  if (channels == 1) {
+    l2norm_finalize_kernel<<<1, kThreads, 0, st>>>(part, gm, scale, diff, done, iters);
+  } else {
+    // per-CTA partial sums live behind the (row, segment) partials: 2 * items floats are used of the 4 * items
+    // the workspace guarantees
+    double* cta_part = reinterpret_cast<double*>(part + 2 * items);
+    const unsigned fb = static_cast<unsigned>((channels + kThreads - 1) / kThreads);
+    l2norm_finalize_channels_kernel<<<fb, kThreads, 0, st>>>(part, gm, scale, diff, done, iters, cta_part,
+                                                            ws_counter(workspace, 1));
+  }
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
 }
