@@ -30,6 +30,17 @@ class GroupItem(C.Structure):
                 ("form", C.c_int32), ("lo", C.c_int32), ("hi", C.c_int32), ("g", C.c_float)]
 
 
+class FoldItem(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("w", "bias", "gamma", "beta", "mean", "var", "w1", "gamma1", "beta1", "mean1",
+                                           "var1", "gamma_id", "beta_id", "mean_id", "var_id", "w_out", "bias_out",
+                                           "stats")] +
+                [("channels", C.c_int64), ("inner", C.c_int64), ("cin_g", C.c_int32), ("ksize", C.c_int32),
+                 ("mode", C.c_int32), ("eps", C.c_float), ("eps1", C.c_float), ("eps_id", C.c_float)])
+
+
+FOLD_MERGE_BN, FOLD_REPVGG = 0, 1
+
+
 class FinalizeItem(C.Structure):
     _fields_ = [("partials", C.c_void_p), ("dscale", C.c_void_p)]
 
@@ -78,6 +89,7 @@ SIGNATURES = {
     "dlmcq_obs_l2norm_step": (_I, [_P, _L, _L, _I, _P, _P, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "dlmcq_fq_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
     "dlmcq_fq_backward_grouped": (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),
+    "dlmcq_fold_grouped": (_I, [_P, _P, _I, _L, _P]),
     "dlmcq_host_staging_bytes": (_Z, [_L, _I]),
     "dlmcq_host_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
     "dlmcq_host_fq_forward_backward_async": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),

@@ -262,6 +262,37 @@ int dlmcq_fq_backward_grouped(const dlmcq_group_item* items, const int64_t* unit
                               const int64_t* chan_prefix, int n_items, int64_t total_units,
                               int64_t total_channels, int dtype, float* partials, void* stream);
 
+/* ---- BN folding / RepVGG re-parameterisation feeding the per-channel observers ----------
+ * dlmc/utils/merge_bn.py:84-100 (mode MERGE_BN) and model/classification/repvgg.py:92-123
+ * (mode REPVGG), for every layer of a model in ONE launch: one warp per (layer, output channel)
+ * writes the folded weight row and bias and - when `stats` is set - the row's
+ * {min, max, max|w|, sum|w|}, i.e. the input of dlmcq_obs_minmax_finalize (ops.py:121-140), so the
+ * observer never re-reads the folded weights.  fp32 only; w_out may alias w (merge_bn folds in place).
+ *   MERGE_BN: var = running_var + 1e-7; w' = (w*gamma)/sqrt(var); b' = (gamma*(b-mean))/sqrt(var) + beta
+ *             (bias == NULL: zeros, merge_bn.py:92-94).
+ *   REPVGG:   std_k = sqrt(var_k + eps_k), t_k = gamma_k/std_k, bias_k = beta_k - (mean_k*gamma_k)/std_k;
+ *             w' = (k3*t3 + pad(k1*t1)) + id*t_id; b' = (bias3 + bias1) + bias_id; gamma_id == NULL when
+ *             the block has no identity branch (the reference then adds the integer 0). */
+typedef enum { DLMCQ_FOLD_MERGE_BN = 0, DLMCQ_FOLD_REPVGG = 1 } dlmcq_fold_mode;
+typedef struct {
+  const float* w;      /* [channels, inner] conv weight (RepVGG: the 3x3 branch) */
+  const float* bias;   /* [channels] or NULL (MERGE_BN only) */
+  const float *gamma, *beta, *mean, *var;             /* BatchNorm of w */
+  const float* w1;     /* REPVGG: [channels, cin_g] 1x1-branch weight */
+  const float *gamma1, *beta1, *mean1, *var1;         /* REPVGG: BatchNorm of the 1x1 branch */
+  const float *gamma_id, *beta_id, *mean_id, *var_id; /* REPVGG: identity BatchNorm, or all NULL */
+  float* w_out;        /* [channels, inner] */
+  float* bias_out;     /* [channels] */
+  float* stats;        /* [channels, 4] or NULL */
+  int64_t channels, inner; /* inner = cin_g * ksize * ksize */
+  int32_t cin_g, ksize;    /* REPVGG: input channels per group, 3 */
+  int32_t mode;            /* dlmcq_fold_mode */
+  float eps, eps1, eps_id; /* REPVGG: the BatchNorms' eps */
+} dlmcq_fold_item;
+/* items: n_items descriptors (DEVICE); chan_prefix[k] = sum_{j<k} channels_j, k = 0..n_items (DEVICE). */
+int dlmcq_fold_grouped(const dlmcq_fold_item* items, const int64_t* chan_prefix, int n_items,
+                       int64_t total_channels, void* stream);
+
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------
  * Same arithmetic as dlmcq_fq_forward + dlmcq_fq_backward on a per-tensor-scale tensor that
  * lives in (pinned) HOST memory: x, dy in; y, dx and dscale out.  Chunks are pipelined

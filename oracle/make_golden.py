@@ -384,6 +384,90 @@ def golden_observers(ns, gen):
     b.save()
 
 
+def _randomize_bn(bn, gen, tiny_var=False):
+    c = bn.num_features
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(c, generator=gen))            # negative gammas included
+        bn.bias.copy_(torch.randn(c, generator=gen) * 0.5)
+        bn.running_mean.copy_(torch.randn(c, generator=gen) * 0.3)
+        bn.running_var.copy_(torch.rand(c, generator=gen) * 2 + 0.01)
+        if tiny_var:
+            bn.running_var[0] = 1e-8                                # exercises the +1e-7 / +eps
+            bn.running_var[1] = 0.0
+    return bn
+
+
+def _bn_pack(bn):
+    return dict(gamma=bn.weight.detach().clone(), beta=bn.bias.detach().clone(),
+                mean=bn.running_mean.detach().clone(), var=bn.running_var.detach().clone())
+
+
+def golden_reparam(gen):
+    """merge_bn (dlmc/utils/merge_bn.py:45-113) and RepVGGBlock.switch_to_deploy (repvgg.py:92-147) run by the
+    reference's own code; the folded kernels also go through the reference's per-channel min/max observer."""
+    rp = ref_shim.load_reparam()
+    ns = ref_shim.load()
+    b = Book("reparam")
+    nn = torch.nn
+    # ---- merge_bn: "0"/"1" naming (case 1) and conv1/bn1 naming (case 2), bias / no bias / groups
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(3, 8, 3, bias=True)
+            self.bn1 = nn.BatchNorm2d(8)
+            self.conv2 = nn.Conv2d(8, 12, 3, groups=2, bias=False)
+            self.bn2 = nn.BatchNorm2d(12)
+            self.block = nn.Sequential(nn.Conv2d(12, 6, 1, bias=False), nn.BatchNorm2d(6))
+    torch.manual_seed(SEED)
+    net = Net()
+    pairs = [("conv1", "bn1"), ("conv2", "bn2"), ("block.0", "block.1")]
+    from operator import attrgetter
+    for k, (cn, bnn) in enumerate(pairs):
+        _randomize_bn(attrgetter(bnn)(net), gen, tiny_var=(k == 0))
+    with torch.no_grad():
+        net.conv1.weight[0, 0, 0, 0] = -0.0
+        net.conv2.weight[3].zero_()
+    inputs = {}
+    for cn, bnn in pairs:
+        conv, bn = attrgetter(cn)(net), attrgetter(bnn)(net)
+        inputs[cn] = dict(w=conv.weight.detach().clone(),
+                          bias=None if conv.bias is None else conv.bias.detach().clone(), **_bn_pack(bn))
+    with contextlib.redirect_stdout(io.StringIO()):
+        merged = rp.merge_bn.merge_bn(net)           # inplace=False modifies `net` itself (merge_bn.py:61-62)
+    assert merged is net
+    for cn, bnn in pairs:
+        conv = attrgetter(cn)(net)
+        assert isinstance(attrgetter(bnn)(net), nn.Identity)
+        inp = {k: v for k, v in inputs[cn].items() if v is not None}
+        so, oo = ns.ops.quantize_minmax_channel(conv.weight.detach(), n_bits=8, signed=True, ch_axis=0)
+        b.add(f"merge_bn.{cn}", {"has_bias": inputs[cn]["bias"] is not None}, inp,
+              {"w": conv.weight.detach(), "bias": conv.bias.detach(), "obs_scale": so, "obs_offset": oo})
+    # ---- RepVGG blocks: identity / no identity / grouped
+    for name, (cin, cout, stride, groups) in {"id": (8, 8, 1, 1), "noid": (4, 8, 2, 1), "grouped": (8, 8, 1, 2)}.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            blk = rp.repvgg.RepVGGBlock(cin, cout, 3, stride=stride, padding=1, groups=groups)
+        _randomize_bn(blk.rbr_dense.bn, gen, tiny_var=(name == "id"))
+        _randomize_bn(blk.rbr_1x1.bn, gen)
+        if blk.rbr_identity is not None:
+            _randomize_bn(blk.rbr_identity, gen)
+        with torch.no_grad():
+            blk.rbr_dense.conv.weight[1, 0, 1, 1] = -0.0
+            blk.rbr_dense.conv.weight[2, 1, 0, 0] = -0.0
+        inp = {"k3": blk.rbr_dense.conv.weight.detach().clone(), "k1": blk.rbr_1x1.conv.weight.detach().clone()}
+        for tag, bn in (("bn3", blk.rbr_dense.bn), ("bn1", blk.rbr_1x1.bn), ("bnid", blk.rbr_identity)):
+            if bn is not None:
+                for k, v in _bn_pack(bn).items():
+                    inp[f"{tag}_{k}"] = v
+        eps = blk.rbr_dense.bn.eps
+        blk.eval()
+        blk.switch_to_deploy()
+        w, bias = blk.rbr_reparam.weight.detach(), blk.rbr_reparam.bias.detach()
+        so, oo = ns.ops.quantize_minmax_channel(w, n_bits=8, signed=True, ch_axis=0)
+        b.add(f"repvgg.{name}", {"groups": groups, "eps": eps, "has_id": "bnid_gamma" in inp}, inp,
+              {"w": w, "bias": bias, "obs_scale": so, "obs_offset": oo})
+    b.save()
+
+
 def main():
     ns = ref_shim.load()
     torch.manual_seed(SEED)
@@ -395,6 +479,7 @@ def main():
     golden_rootq(ns, gen)
     golden_fsptq(ns, gen)
     golden_observers(ns, gen)
+    golden_reparam(torch.Generator().manual_seed(SEED + 7))
 
 
 if __name__ == "__main__":

@@ -15,6 +15,7 @@ Why a shim is needed:
     the real directories, so trainer/loss/loss.py itself loads unmodified.
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -66,4 +67,33 @@ def load():
     ns.modules_function = importlib.import_module("dlmc.quantization.scalar.modules.function")
     ns.FSPTQuant = importlib.import_module("dlmc.quantization.scalar.FSPTQuant")
     _loaded = ns
+    return ns
+
+
+_reparam = None
+
+
+def load_reparam():
+    """The reference's weight-space re-parameterisation code, unmodified:
+    .merge_bn  = dlmc/utils/merge_bn.py   (its `dlmc.utils` package __init__ pulls in timm / BitMixer /
+                 MetaQuant, none of which exist here -> `dlmc.utils` is pre-seeded as a namespace stub and
+                 `dlmc.quantization.scalar.BitMixer` as a stub carrying the two imported names)
+    .repvgg    = model/classification/repvgg.py (imports only torch / numpy; loaded by path because
+                 model/classification/__init__.py imports timm)."""
+    global _reparam
+    if _reparam is not None:
+        return _reparam
+    load()
+    if "dlmc.utils" not in sys.modules:
+        u = _stub("dlmc.utils")
+        u.__path__ = [os.path.join(REFERENCE_ROOT, "dlmc", "utils")]
+    if "dlmc.quantization.scalar.BitMixer" not in sys.modules:
+        _stub("dlmc.quantization.scalar.BitMixer", BitMixerBatchNorm=None, BitMixerSwitchableBatchNorm=None)
+    ns = types.SimpleNamespace()
+    ns.merge_bn = importlib.import_module("dlmc.utils.merge_bn")
+    spec = importlib.util.spec_from_file_location(
+        "_ref_repvgg", os.path.join(REFERENCE_ROOT, "model", "classification", "repvgg.py"))
+    ns.repvgg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ns.repvgg)
+    _reparam = ns
     return ns

@@ -451,6 +451,55 @@ OBSERVERS = {
 }
 
 
+# --------------------------------------------------------------------------- #
+# weight-space re-parameterisation
+# --------------------------------------------------------------------------- #
+def sqrt_ieee(t):
+    """Correctly rounded fp32 square root (the hardware instruction, via numpy) - what `Tensor.sqrt()`
+    computes on CUDA.  torch's CPU `sqrt` goes through MKL VML, which is only faithfully rounded: e.g.
+    sqrt(0x1.17783ep+0) returns 0x1.0b7a40p+0 there, the correctly rounded value is 0x1.0b7a42p+0 [probed,
+    torch 2.11.0 + MKL 2024.2].  About 3 % of random inputs differ by that one ulp, so a reference run on
+    the CPU can differ from its own CUDA run (and from this oracle) by 1 ulp of std in those channels."""
+    import numpy as np
+    return torch.from_numpy(np.sqrt(t.detach().cpu().numpy()))
+
+
+def merge_bn_fold(w, bias, gamma, beta, mean, running_var):
+    """dlmc/utils/merge_bn.py:84-100 - fold a BatchNorm2d into the preceding Conv2d.
+    var = running_var + 1e-7 (NOT the module's eps); a missing conv bias is zeros (:92-94)."""
+    var = running_var + 1e-7
+    cout = w.shape[0]
+    if bias is None:
+        bias = torch.zeros(cout)
+    new_bias = gamma * (bias - mean) / sqrt_ieee(var) + beta
+    new_w = (w.reshape(cout, -1) * gamma.reshape(-1, 1) / sqrt_ieee(var).reshape(-1, 1)).reshape(w.shape)
+    return new_w, new_bias
+
+
+def _repvgg_branch(kernel, gamma, beta, mean, var, eps):
+    """model/classification/repvgg.py:121-123."""
+    std = sqrt_ieee(var + eps)
+    t = (gamma / std).reshape(-1, 1, 1, 1)
+    return kernel * t, beta - mean * gamma / std
+
+
+def repvgg_fuse(k3, bn3, k1, bn1, bn_id, groups=1):
+    """repvgg.py:92-123 get_equivalent_kernel_bias.  bn* = (gamma, beta, running_mean, running_var, eps);
+    bn_id is None when the block has no identity branch (the reference then adds the integer 0)."""
+    kernel3, bias3 = _repvgg_branch(k3, *bn3)
+    kernel1, bias1 = _repvgg_branch(k1, *bn1)
+    if bn_id is None:
+        kernel_id, bias_id = 0, 0
+    else:
+        in_channels = k3.shape[1] * groups
+        input_dim = in_channels // groups                              # repvgg.py:108
+        id_tensor = torch.zeros(in_channels, input_dim, 3, 3)
+        for i in range(in_channels):
+            id_tensor[i, i % input_dim, 1, 1] = 1                      # :110-111
+        kernel_id, bias_id = _repvgg_branch(id_tensor, *bn_id)
+    return kernel3 + F.pad(kernel1, [1, 1, 1, 1]) + kernel_id, bias3 + bias1 + bias_id
+
+
 def get_qparams_tensor(t, qtype, **kwargs):
     """ops.py:15-18 - name dispatch."""
     return OBSERVERS[qtype](t, **kwargs)

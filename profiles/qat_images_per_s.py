@@ -122,6 +122,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(device)
+    torch.backends.cudnn.benchmark = True        # example/benchmark/benchmark.py:203-205 (benchmark.yaml:14 cudnn: true)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
