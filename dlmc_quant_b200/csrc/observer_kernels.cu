@@ -960,11 +960,13 @@ extern "C" int dlmcq_obs_sweep_channel(const void* x, int64_t channels, int64_t 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float qmax = static_cast<float>((1 << n_bits) - 1);
   const float sdiv = static_cast<float>((1 << (n_bits - 1)) - 1);
-  // warps per row: enough warps to fill the GPU (>= 16 per SM) when the tensor has few rows, but at
-  // least 128 elements per warp; fewer rows per CTA when the staged rows would not fit in shared memory
+  // warps per row: enough warps to fill the GPU (>= 8 per SM) when the tensor has few rows - every warp of
+  // a row repeats the per-candidate prologue (candidate scale, zero-point, reciprocal: ~100 instructions),
+  // so more warps per row than that only add issue slots - and at least 256 elements per warp; fewer rows
+  // per CTA when the staged rows would not fit in shared memory
   int wpr = 1;
-  const int64_t want_warps = static_cast<int64_t>(num_sms()) * 16;
-  while (wpr < kSweepWarps && channels * wpr < want_warps && inner >= 256LL * wpr) wpr *= 2;
+  const int64_t want_warps = static_cast<int64_t>(num_sms()) * 8;
+  while (wpr < kSweepWarps && channels * wpr < want_warps && inner >= 512LL * wpr) wpr *= 2;
   const int64_t row_floats = ((inner + 8 + 3) / 4) * 4;
   while (wpr < kSweepWarps && (kSweepWarps / wpr) * row_floats > kSweepSmemFloats) wpr *= 2;
   const int staged = (kSweepWarps / wpr) * row_floats <= kSweepSmemFloats ? 1 : 0;

@@ -5,12 +5,14 @@ Activations shard by batch and weights are replicated, so the fake-quant kernels
 collective.  What must agree across ranks is O(channels) data:
   * observer statistics  - [C,4] = (min, max, max|x|, sum|x|): MIN / MAX / SUM all-reduces,
   * sweep partial sums   - 80 squared-error sums per tensor: SUM,
-  * scale gradients      - one flat buffer per step: SUM (DDP averages parameter grads itself).
+  * scale gradients      - one flat buffer per step: SUM (DDP averages parameter grads itself),
+  * per-channel WEIGHT observers (replicated weights, e.g. the 80-candidate sweep): each rank computes the
+    qparams of a contiguous block of ceil(C / world) output channels and the blocks are all-gathered.
 At world size 1 every function is the identity, i.e. bit-identical to the reference."""
 import torch
 import torch.distributed as dist
 
-__all__ = ["world_size", "sync_stats", "sync_sse", "allreduce_grads_"]
+__all__ = ["world_size", "sync_stats", "sync_sse", "allreduce_grads_", "row_block", "rows_sharded"]
 
 _enabled = True
 
@@ -65,3 +67,40 @@ def allreduce_grads_(flat, average=False, group=None):
     if average:
         flat.div_(w)
     return flat
+
+
+def row_block(channels, rank, world):
+    """Contiguous block of output channels owned by `rank`: [start, stop) with ceil(C / world) rows per rank."""
+    per = (channels + world - 1) // world
+    start = min(rank * per, channels)
+    return start, min(start + per, channels)
+
+
+def rows_sharded(rows2d, fn, group=None, min_rows_per_rank=64):
+    """Per-channel observer over REPLICATED rows, sharded by output channel: every rank runs
+    `fn(block) -> tuple of [rows_in_block] tensors` on its block of rows and the results are all-gathered, so
+    each row is computed once per job instead of once per rank.  Rows are independent and the weights are
+    identical on all ranks, hence the gathered vectors equal fn(rows2d) bit for bit.  Falls back to the local
+    computation at world size 1 or when the tensor is too small to be worth an exchange."""
+    w = world_size(group)
+    channels = rows2d.shape[0]
+    if w == 1 or channels < w * min_rows_per_rank:
+        return fn(rows2d)
+    rank = dist.get_rank(group)
+    per = (channels + w - 1) // w
+    start, stop = row_block(channels, rank, w)
+    mine = fn(rows2d[start:stop]) if stop > start else None
+    out = []
+    n_out = len(mine) if mine is not None else None
+    if n_out is None:                       # an empty block still has to take part in the collectives
+        probe = fn(rows2d[:1])
+        n_out = len(probe)
+        mine = tuple(p[:0] for p in probe)
+    for k in range(n_out):
+        pad = torch.zeros(per, dtype=mine[k].dtype, device=rows2d.device)
+        pad[:stop - start] = mine[k].reshape(-1)
+        gathered = torch.empty(per * w, dtype=pad.dtype, device=rows2d.device)
+        dist.all_gather_into_tensor(gathered, pad, group=group) if rows2d.is_cuda else \
+            dist.all_gather(list(gathered.split(per)), pad, group=group)
+        out.append(gathered[:channels])
+    return tuple(out)

@@ -77,9 +77,31 @@ def _workspace(device, nbytes):
     return ws
 
 
+_ws_bytes = {}
+
+
 def _ws_for(t, lay):
-    n = _lib.lib().dlmcq_workspace_bytes(C.byref(lay))
+    key = (lay.outer, lay.channels, lay.inner)
+    n = _ws_bytes.get(key)
+    if n is None:
+        n = _ws_bytes[key] = _lib.lib().dlmcq_workspace_bytes(C.byref(lay))
     return _workspace(t.device, n), n
+
+
+class _NoCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def _on(device):
+    """Device guard for a launch; free when `device` already is the current device (the per-layer hot path)."""
+    return _NOCTX if device.index == torch.cuda.current_device() else torch.cuda.device(device)
 
 
 # --------------------------------------------------------------------------------------
@@ -93,7 +115,7 @@ def fq_forward(x, scale, offset, lo, hi, form, g=0.0, ch_axis=None, want_codes=F
     y = torch.empty_like(x) if want_y else None
     codes = torch.empty_like(x) if want_codes else None
     qp = QParams(form, int(lo), int(hi), float(g), s.data_ptr(), o.data_ptr() if o is not None else None)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.lib().dlmcq_fq_forward(_ptr(x), _ptr(y), _ptr(codes), C.byref(lay), C.byref(qp), _stream_ptr()))
     if want_y and want_codes:
         return y, codes
@@ -115,7 +137,7 @@ def fq_backward(x, dy, scale, offset, lo, hi, form, g=0.0, ch_axis=None, want_do
     ds = torch.empty(lay.channels, dtype=torch.float32, device=x.device)
     do = torch.empty(lay.channels, dtype=torch.float32, device=x.device) if want_doffset else None
     qp = QParams(form, int(lo), int(hi), float(g), s.data_ptr(), o.data_ptr() if o is not None else None)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         ws, n = _ws_for(x, lay)
         _lib.check(_lib.lib().dlmcq_fq_backward(_ptr(x), _ptr(dy), _ptr(dx), _ptr(ds), _ptr(do), C.byref(lay),
                                                 C.byref(qp), _ptr(ws), n, _stream_ptr()))

@@ -95,10 +95,14 @@ def quantize_l2loss_tensor(tensor, n_bits, signed, allow_offset=True):
 
 
 def quantize_l2loss_channel(tensor, n_bits, signed, ch_axis=0):
-    """ops.py:169-196: per-channel sweep, rows staged once in shared memory.  Per-channel work needs no
-    cross-rank exchange (weights are replicated under data parallelism)."""
+    """ops.py:169-196: per-channel sweep, rows staged once in shared memory.  Under data parallelism the
+    weights are replicated, so the rows are split over the ranks (ceil(C / world) each) and the per-channel
+    (scale, offset) pairs all-gathered - each row is swept once per job, not once per rank."""
     rows, new_shape = _process_channel(tensor, ch_axis)
-    scale, offset = F.sweep_channel(rows, n_bits, signed)
+    if ch_axis == 0:        # replicated weights: shard the rows over the ranks and all-gather the qparams
+        scale, offset = qdist.rows_sharded(rows, lambda blk: F.sweep_channel(blk, n_bits, signed))
+    else:                   # activations differ per rank: local (the reference's per-rank behaviour)
+        scale, offset = F.sweep_channel(rows, n_bits, signed)
     return scale.reshape(new_shape), offset.reshape(new_shape)
 
 

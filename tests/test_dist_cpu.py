@@ -82,3 +82,51 @@ def test_single_process_is_identity():
     assert qdist.world_size() == 1 and qdist.sync_stats(s) is s
     sse, rows = qdist.sync_sse(s, 3.0)
     assert sse is s and rows == 3.0
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dlmc_quant_b200 import dist as qdist
+        gen = torch.Generator().manual_seed(2333)
+        calls = []
+
+        def fn(block):              # stand-in for a per-channel observer: (scale, offset) per row
+            calls.append(block.shape[0])
+            return block.abs().max(1)[0] / 7, block.min(1)[0]
+        oks = []
+        for channels in (131, 128, 3):          # uneven split, even split, too small to shard
+            rows = torch.randn(channels, 37, generator=gen)
+            calls.clear()
+            s, o = qdist.rows_sharded(rows, fn, min_rows_per_rank=16)
+            ws, wo = rows.abs().max(1)[0] / 7, rows.min(1)[0]
+            start, stop = qdist.row_block(channels, rank, world)
+            sharded = channels >= world * 16
+            oks.append(torch.equal(s, ws) and torch.equal(o, wo) and calls == [stop - start if sharded else channels])
+        q.put((rank, *oks))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_per_channel_observer_rows_are_sharded_and_gathered_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in results:
+        assert all(r[1:]), f"rank {r[0]}: uneven/even/small = {r[1:]}"
+
+
+def test_row_block_partition_covers_all_rows():
+    from dlmc_quant_b200 import dist as qdist
+    for channels, world in ((131, 2), (27560, 8), (5, 8), (64, 4)):
+        blocks = [qdist.row_block(channels, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == channels
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
