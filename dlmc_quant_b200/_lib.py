@@ -86,6 +86,7 @@ SIGNATURES = {
     "dlmcq_obs_sweep_tensor_sse": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _Z, _P]),
     "dlmcq_obs_sweep_tensor_finalize": (_I, [_P, _P, _D, _I, _I, _P, _P, _P, _P]),
     "dlmcq_obs_sweep_channel": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P]),
+    "dlmcq_obs_sweep_channel_geom": (_I, [_P, _L, _L, _I, _I, _I, _L, _P, _P, _P]),
     "dlmcq_obs_l2norm_step": (_I, [_P, _L, _L, _I, _P, _P, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "dlmcq_fq_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
     "dlmcq_fq_backward_grouped": (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),

@@ -13,6 +13,8 @@
 //
 // Rooflines: stats / l2norm are HBM-bound (4 B/elem fp32).  The sweeps are fp32-issue-bound once
 // staged (80 x ~20 instructions per element against 4 B of traffic).
+#include <cstdlib>
+
 #include "fq_math.cuh"
 
 namespace dlmcq {
@@ -955,18 +957,32 @@ extern "C" int dlmcq_obs_sweep_tensor_finalize(const float* sse, const float* st
 
 extern "C" int dlmcq_obs_sweep_channel(const void* x, int64_t channels, int64_t inner, int dtype, int n_bits,
                                        int is_signed, float* scale, float* offset, void* stream) {
+  return dlmcq_obs_sweep_channel_geom(x, channels, inner, dtype, n_bits, is_signed, channels, scale, offset, stream);
+}
+
+extern "C" int dlmcq_obs_sweep_channel_geom(const void* x, int64_t channels, int64_t inner, int dtype, int n_bits,
+                                            int is_signed, int64_t geom_channels, float* scale, float* offset,
+                                            void* stream) {
   if (!x || !scale || !offset || channels < 1 || inner < 1 || n_bits < 1 || n_bits > 24) return DLMCQ_EINVAL;
+  if (geom_channels < channels) return DLMCQ_EINVAL;
   if (dtype != DLMCQ_F32 && dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float qmax = static_cast<float>((1 << n_bits) - 1);
   const float sdiv = static_cast<float>((1 << (n_bits - 1)) - 1);
   // warps per row: enough warps to fill the GPU (>= 8 per SM) when the tensor has few rows - every warp of
   // a row repeats the per-candidate prologue (candidate scale, zero-point, reciprocal: ~100 instructions),
-  // so more warps per row than that only add issue slots - and at least 256 elements per warp; fewer rows
+  // so more warps per row than that only add issue slots - and at least 256-512 elements per warp; fewer rows
   // per CTA when the staged rows would not fit in shared memory
   int wpr = 1;
   const int64_t want_warps = static_cast<int64_t>(num_sms()) * 8;
-  while (wpr < kSweepWarps && channels * wpr < want_warps && inner >= 512LL * wpr) wpr *= 2;
+  // geom_channels (>= channels): the row count of the whole matrix when `x` is one rank's block of it - the
+  // warps-per-row choice fixes the summation order, so a row gets the same qparams whoever sweeps it
+  const int64_t min_per_warp = geom_channels <= num_sms() ? 256 : 512;   // measured: profiles/README.md
+  while (wpr < kSweepWarps && geom_channels * wpr < want_warps && inner >= min_per_warp * wpr) wpr *= 2;
+  if (const char* ov = getenv("DLMCQ_SWEEP_WPR")) {           // tuning aid (profiles/sweep_wpr_table.py)
+    const int v = atoi(ov);
+    if (v == 1 || v == 2 || v == 4 || v == 8) wpr = v;
+  }
   const int64_t row_floats = ((inner + 8 + 3) / 4) * 4;
   while (wpr < kSweepWarps && (kSweepWarps / wpr) * row_floats > kSweepSmemFloats) wpr *= 2;
   const int staged = (kSweepWarps / wpr) * row_floats <= kSweepSmemFloats ? 1 : 0;

@@ -76,12 +76,16 @@ def row_block(channels, rank, world):
     return start, min(start + per, channels)
 
 
-def rows_sharded(rows2d, fn, group=None, min_rows_per_rank=64):
+def rows_sharded(rows2d, fn, group=None, min_rows_per_rank=2048):
     """Per-channel observer over REPLICATED rows, sharded by output channel: every rank runs
     `fn(block) -> tuple of [rows_in_block] tensors` on its block of rows and the results are all-gathered, so
     each row is computed once per job instead of once per rank.  Rows are independent and the weights are
-    identical on all ranks, hence the gathered vectors equal fn(rows2d) bit for bit.  Falls back to the local
-    computation at world size 1 or when the tensor is too small to be worth an exchange."""
+    identical on all ranks, hence the gathered vectors equal fn(rows2d) bit for bit (fn must not let its
+    launch geometry depend on the block size: F.sweep_channel takes the full row count for that).  Falls back
+    to the local computation at world size 1 or when the matrix is too small to be worth an exchange:
+    measured on 4 B200s (profiles/r01_sharded_observer_n4.json), sharding each of ResNet-50's 54 weight
+    tensors (<= 2048 rows) costs 108 all-gathers and takes 5.97 ms against 3.51 ms for sweeping everything
+    on every rank - the sweep of a CNN layer is launch-latency-bound - hence the high default threshold."""
     w = world_size(group)
     channels = rows2d.shape[0]
     if w == 1 or channels < w * min_rows_per_rank:

@@ -278,16 +278,18 @@ def sweep_tensor(x, n_bits, allow_offset=True, reduce_stats=None, reduce_sse=Non
     return sweep_tensor_pick(sse, stats, rows, n_bits, allow_offset)
 
 
-def sweep_channel(rows2d, n_bits, signed):
-    """ops.py:169-196 on a contiguous [channels, inner] matrix -> (scale[C], offset[C])."""
+def sweep_channel(rows2d, n_bits, signed, geom_channels=None):
+    """ops.py:169-196 on a contiguous [channels, inner] matrix -> (scale[C], offset[C]).  geom_channels: the
+    row count of the whole matrix when rows2d is one rank's block of it (dist.rows_sharded)."""
     _require_cuda(rows2d, "tensor")
     rows2d = rows2d.detach().contiguous()
     ch, inner = rows2d.shape
     scale = torch.empty(ch, dtype=torch.float32, device=rows2d.device)
     offset = torch.empty(ch, dtype=torch.float32, device=rows2d.device)
     with torch.cuda.device(rows2d.device):
-        _lib.check(_lib.lib().dlmcq_obs_sweep_channel(_ptr(rows2d), ch, inner, _dtype_code(rows2d), int(n_bits),
-                                                      int(bool(signed)), _ptr(scale), _ptr(offset), _stream_ptr()))
+        _lib.check(_lib.lib().dlmcq_obs_sweep_channel_geom(_ptr(rows2d), ch, inner, _dtype_code(rows2d), int(n_bits),
+                                                           int(bool(signed)), int(geom_channels or ch), _ptr(scale),
+                                                           _ptr(offset), _stream_ptr()))
     return scale, offset
 
 

@@ -100,7 +100,7 @@ def quantize_l2loss_channel(tensor, n_bits, signed, ch_axis=0):
     (scale, offset) pairs all-gathered - each row is swept once per job, not once per rank."""
     rows, new_shape = _process_channel(tensor, ch_axis)
     if ch_axis == 0:        # replicated weights: shard the rows over the ranks and all-gather the qparams
-        scale, offset = qdist.rows_sharded(rows, lambda blk: F.sweep_channel(blk, n_bits, signed))
+        scale, offset = qdist.rows_sharded(rows, lambda blk: F.sweep_channel(blk, n_bits, signed, rows.shape[0]))
     else:                   # activations differ per rank: local (the reference's per-rank behaviour)
         scale, offset = F.sweep_channel(rows, n_bits, signed)
     return scale.reshape(new_shape), offset.reshape(new_shape)

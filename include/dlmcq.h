@@ -226,6 +226,13 @@ int dlmcq_obs_sweep_tensor_finalize(const float* sse, const float* stats, double
  * and its disregard of `signed` in the search. */
 int dlmcq_obs_sweep_channel(const void* x, int64_t channels, int64_t inner, int dtype,
                             int n_bits, int is_signed, float* scale, float* offset, void* stream);
+/* Same, for one rank's block of `channels` rows out of a matrix of `geom_channels` rows (per-channel
+ * observers sharded by output channel): the launch geometry - and with it the order in which
+ * a row's squared errors are summed - is chosen from geom_channels, so every row gets bit-identical qparams
+ * whichever rank sweeps it. */
+int dlmcq_obs_sweep_channel_geom(const void* x, int64_t channels, int64_t inner, int dtype, int n_bits,
+                                 int is_signed, int64_t geom_channels, float* scale, float* offset,
+                                 void* stream);
 
 /* ops.py:71-83,198-215 l2norm fixed point, one iteration over rows [channels, inner]
  * (channels=1 for the per-tensor form):

@@ -31,21 +31,23 @@ def main():
     weights = [m.weight.detach().to(device) for m in model.modules()
                if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
 
-    def sweep_all(sharded):
-        qdist.set_enabled(sharded)
-        out = [ops.quantize_l2loss_channel(w, n_bits=4, signed=True, ch_axis=0) for w in weights]
-        qdist.set_enabled(True)
-        return out
+    def sweep_one(w, mode):
+        rows = w.reshape(w.shape[0], -1)
+        if mode == "local":
+            return F.sweep_channel(rows, 4, True)
+        thr = 64 if mode == "forced" else 2048               # "default" = the library's threshold
+        return qdist.rows_sharded(rows, lambda blk: F.sweep_channel(blk, 4, True, rows.shape[0]), min_rows_per_rank=thr)
 
-    def timed(sharded, reps=5):
-        sweep_all(sharded)
+    def timed(tensors, mode, reps=5):
+        run = lambda: [sweep_one(w, mode) for w in tensors]
+        run()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
-            sweep_all(sharded)
+            run()
         b.record()
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b) / reps], device=device)
@@ -53,15 +55,23 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    local, shard = sweep_all(False), sweep_all(True)
-    same = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(local, shard))
-    t_local, t_shard = timed(False), timed(True)
+    def same(tensors, mode):
+        return all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+                   for a, b in ((sweep_one(w, "local"), sweep_one(w, mode)) for w in tensors))
+
+    big = [torch.randn(32768, 1152, device=device) * 0.02]     # an embedding / large-FC sized matrix (37.7 M elements)
+    out = {"op": "quantize_l2loss_channel (W4 signed, 80 candidates), rows sharded by output channel + all-gather",
+           "n_gpus": world,
+           "resnet50_54_tensors": {"rows": sum(w.shape[0] for w in weights), "elements": sum(w.numel() for w in weights),
+                                   "bit_identical_forced_sharding": same(weights, "forced"),
+                                   "ms_every_rank_sweeps_all": round(timed(weights, "local"), 3),
+                                   "ms_forced_sharding_108_allgathers": round(timed(weights, "forced"), 3),
+                                   "ms_library_default": round(timed(weights, "default"), 3)},
+           "matrix_32768x1152": {"bit_identical": same(big, "default"),
+                                 "ms_every_rank_sweeps_all": round(timed(big, "local"), 3),
+                                 "ms_sharded_allgather": round(timed(big, "default"), 3)}}
     if rank == 0:
-        print(json.dumps({"op": "quantize_l2loss_channel over the 54 ResNet-50 weight tensors (W4, 80 candidates)",
-                          "n_gpus": world, "rows": sum(w.shape[0] for w in weights),
-                          "elements": sum(w.numel() for w in weights), "bit_identical_to_unsharded": same,
-                          "ms_unsharded_per_rank": round(t_local, 3), "ms_sharded_allgather": round(t_shard, 3),
-                          "speedup": round(t_local / t_shard, 2)}), flush=True)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
