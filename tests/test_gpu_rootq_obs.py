@@ -302,3 +302,66 @@ def test_host_pipeline_matches_device_path():
         assert torch.equal(yk, F().fq_forward(dev(x), sd, o, 0, 15, 1, g=g).cpu())
         dxd, dsd = F().fq_backward(dev(x), dev(dy), sd, o, 0, 15, 1, g=g)
         assert torch.equal(dxk, dxd.cpu()) and abs(float(dsk) - float(dsd)) <= 1e-5 * abs(float(dsd)) + 1e-7
+
+
+# --------------------------------------------------------------------------------------
+# geometry coverage of the observer kernels added in the second half of round 1
+def test_sweep_channel_unstaged_rows_bf16_and_block_geometry():
+    gen = torch.Generator().manual_seed(21)
+    # a row longer than the shared-memory staging cap (200 KB) is swept from global memory
+    t = torch.rand(2, 60000, generator=gen) * 3 + 0.5
+    s, o = F().sweep_channel(dev(t), 4, False)
+    rs, ro = R.obs_l2loss_channel(t.clone(), 4, False)
+    _sweep_rows_equivalent(t, s.cpu(), o.cpu(), rs.reshape(-1), ro.reshape(-1), 4)
+    # bf16 rows: converted while staging, fp32 arithmetic on the up-converted values
+    tb = (torch.rand(24, 1152, generator=gen) * 2 + 0.25).to(torch.bfloat16)
+    s, o = F().sweep_channel(dev(tb), 8, False)
+    rs, ro = R.obs_l2loss_channel(tb.float(), 8, False)
+    _sweep_rows_equivalent(tb.float(), s.cpu(), o.cpu(), rs.reshape(-1), ro.reshape(-1), 8)
+    # one rank's block of rows, swept with the geometry of the whole matrix, gets the same bits as the
+    # unsharded sweep (dist.rows_sharded relies on this)
+    w = torch.randn(64, 2304, generator=gen) * 0.02
+    s_all, o_all = F().sweep_channel(dev(w), 4, True)
+    for lo_r, hi_r in ((0, 32), (32, 64), (5, 6)):
+        s_b, o_b = F().sweep_channel(dev(w[lo_r:hi_r]), 4, True, geom_channels=64)
+        assert torch.equal(s_b, s_all[lo_r:hi_r]) and torch.equal(o_b, o_all[lo_r:hi_r])
+
+
+def test_channel_major_kernels_with_several_batch_chunks():
+    """[B, C, 7, 7] activations with B*49 > 8192: every channel is covered by several (channel, batch chunk)
+    work items whose partial statistics / scale gradients are combined by the CTA-per-channel finalisers."""
+    gen = torch.Generator().manual_seed(22)
+    x = torch.relu(torch.randn(400, 6, 7, 7, generator=gen)) * 1.5
+    dy = torch.randn(x.shape, generator=gen)
+    st = F().obs_stats(dev(x), ch_axis=1).cpu()
+    rows = x.transpose(0, 1).reshape(6, -1)
+    assert torch.equal(st[:, 0], rows.min(1)[0]) and torch.equal(st[:, 1], rows.max(1)[0])
+    assert torch.equal(st[:, 2], rows.abs().max(1)[0]) and torch.allclose(st[:, 3], rows.abs().sum(1), rtol=1e-5)
+    xn = x.clone()
+    xn[399, 4, 6, 6] = float("nan")
+    stn = F().obs_stats(dev(xn), ch_axis=1).cpu()
+    assert torch.isnan(stn[4]).all() and not torch.isnan(stn[[0, 1, 2, 3, 5]]).any()
+    scale, off = R.obs_minmax_channel(x, 4, False, ch_axis=1)
+    g = R.lsq_g(x.numel(), 15)
+    xs, ss = x.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+    y_ref = R.fq_affine(xs, ss, off, 0, 15, g)
+    dx_ref, ds_ref = torch.autograd.grad(y_ref, (xs, ss), dy)
+    y = F().fq_forward(dev(x), dev(scale), dev(off), 0, 15, 1, g=g, ch_axis=1)
+    exact(y, y_ref.detach(), "y")
+    dx, ds = F().fq_backward(dev(x), dev(dy), dev(scale), dev(off), 0, 15, 1, g=g, ch_axis=1)
+    assert torch.equal(dx.cpu() == 0, dx_ref == 0) and torch.allclose(dx.cpu(), dx_ref, rtol=1e-6, atol=0)
+    red_close(ds, ds_ref.reshape(-1), abs_sum=dy.abs().sum(dim=(0, 2, 3)) * 15 * g)
+
+
+def test_l2norm_per_channel_multi_cta_finalise():
+    """More than 256 channels: the new scales, the global stopping rule and the done flag are produced by
+    several finalising CTAs plus a last-ticket combination."""
+    gen = torch.Generator().manual_seed(23)
+    w = torch.randn(600, 96, generator=gen) * 0.05
+    lo, hi = R.qrange(True, 4)
+    rs, ro, ref_iters = R.obs_l2norm_channel(w, 4, True, return_iters=True)
+    stats = F().obs_stats(dev(w), ch_axis=0)
+    s0, o0 = F().minmax_from_stats(stats, 4, True)
+    s, iters, done = F().l2norm_fixed_point(dev(w), s0, o0, lo, hi)
+    assert done and abs(int(iters) - ref_iters) <= 2, (int(iters), ref_iters)
+    assert torch.allclose(s.cpu(), rs.reshape(-1), rtol=2e-4)
