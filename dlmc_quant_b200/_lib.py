@@ -83,6 +83,11 @@ SIGNATURES = {
     "dlmcq_obs_stats": (_I, [_P, _P, _LP, _I, _P, _Z, _P]),
     "dlmcq_obs_minmax_finalize": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
     "dlmcq_obs_absmean_finalize": (_I, [_P, _P, _L, _D, _D, _D, _I, _P]),
+    "dlmcq_obs_kth_state_bytes": (_Z, []),
+    "dlmcq_obs_kth_begin": (_I, [_P, _L, _L, _P]),
+    "dlmcq_obs_kth_hist": (_I, [_P, _L, _I, _I, _I, _P, _P]),
+    "dlmcq_obs_kth_select": (_I, [_I, _P, _P]),
+    "dlmcq_obs_kth_values": (_I, [_P, _P, _P]),
     "dlmcq_obs_sweep_tensor_sse": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _Z, _P]),
     "dlmcq_obs_sweep_tensor_finalize": (_I, [_P, _P, _D, _I, _I, _P, _P, _P, _P]),
     "dlmcq_obs_sweep_channel": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P]),

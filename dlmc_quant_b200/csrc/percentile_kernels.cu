@@ -1,0 +1,218 @@
+// percentile_kernels.cu - exact order statistics (k-th smallest value) of a tensor by a 3-pass radix select,
+// the building block of the percentile-clipping observer.
+//
+// The north star lists a percentile observer next to min/max and the MSE sweep; the reference itself
+// (dlmc/quantization/scalar/ops.py) has none, so the semantics are defined here and pinned against
+// torch.kthvalue: value_j = the ranks[j]-th smallest element (1-based) of x, or of |x|.  Exact - no sampling, no
+// histogram interpolation - so that the qparams derived from it are reproducible bit for bit.
+//
+//   key(x)    order-preserving uint32 image of the fp32 value (NaN last, like torch.sort; -0 == +0)
+//   pass p    histogram of key digit p (11, 11, 10 bits from the top) over the elements whose higher digits
+//             equal the prefix selected so far; one read of x per pass (3 x 4 B/elem fp32, 3 x 2 B/elem bf16)
+//   select    the digit whose bin holds the wanted rank; prefix <- prefix.digit, rank <- rank - (elements below)
+// Up to two ranks are tracked at once (lower and upper percentile share the passes).  Multi-GPU callers
+// all-reduce (SUM) the histogram between `hist` and `select`, which yields the order statistic of the union.
+// Roofline: HBM (three streaming reads); the shared-memory histogram uses warp-aggregated atomics because real
+// activations put half of their elements into one bin (post-ReLU zeros).
+#include "common.cuh"
+
+namespace dlmcq {
+
+constexpr int kRadixBins = 2048;
+__host__ __device__ inline int radix_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+__host__ __device__ inline unsigned radix_mask(int pass) { return pass == 2 ? 1023u : 2047u; }
+
+struct RadixState {
+  unsigned long long rank[2];   // remaining 1-based rank inside the selected prefix
+  unsigned int prefix[2];       // selected high digits, right-aligned
+  unsigned int n_ranks;
+  unsigned int pad;
+};
+
+__device__ __forceinline__ unsigned int radix_key(float v, bool abs_input) {
+  if (abs_input) v = fabsf(v);
+  if (v != v) return 0xffffffffu;                  // NaN sorts last
+  if (v == 0.f) v = 0.f;                           // -0 and +0 are the same value
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float radix_unkey(unsigned int k) {
+  if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+  const unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// one atomic per distinct bin per warp
+__device__ __forceinline__ void warp_hist_add(unsigned int* hist, unsigned int bin, bool active) {
+  const unsigned int live = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const unsigned int peers = __match_any_sync(live, bin);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + bin, static_cast<unsigned int>(__popc(peers)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4)
+radix_hist_kernel(const T* __restrict__ x, int64_t n, int abs_input, int pass, const RadixState* __restrict__ state,
+                  unsigned int* __restrict__ hist /* [2][kRadixBins] */) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  __shared__ unsigned int sh[2][kRadixBins];
+  for (int k = threadIdx.x; k < 2 * kRadixBins; k += blockDim.x) (&sh[0][0])[k] = 0u;
+  __syncthreads();
+  const RadixState st = *state;
+  const int shift = radix_shift(pass);
+  const unsigned int mask = radix_mask(pass);
+  const int up = pass == 0 ? 32 : radix_shift(pass - 1);      // bits above this digit belong to the prefix
+  const bool two = st.n_ranks > 1 && pass > 0 && st.prefix[0] != st.prefix[1];
+  auto add = [&](float v, bool ok) {
+    const unsigned int key = radix_key(v, abs_input != 0);
+    const unsigned int hi = pass == 0 ? 0u : (key >> up);
+    const unsigned int bin = (key >> shift) & mask;
+    warp_hist_add(sh[0], bin, ok && (pass == 0 || hi == st.prefix[0]));
+    if (two) warp_hist_add(sh[1], bin, ok && hi == st.prefix[1]);
+  };
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    const int64_t nvec = n / V::N;
+    const raw* xv = reinterpret_cast<const raw*>(x);
+    constexpr int U = 4;
+    const int64_t full = nvec / (U * stride) * (U * stride);   // every thread of the grid takes part in these
+    for (; i < full; i += U * stride) {
+      raw r[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) r[k] = ld_stream(xv + i + k * stride);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        float f[V::N];
+        V::unpack(r[k], f);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) add(f[e], true);
+      }
+    }
+    // tail: whole warps iterate together (warp_hist_add is a warp-collective), inactive lanes are masked
+    const int64_t tail_iters = (nvec - full + stride - 1) / stride;
+    for (int64_t t = 0; t < tail_iters; ++t, i += stride) {
+      const bool ok = i < nvec;
+      float f[V::N];
+      if (ok) V::unpack(ld_stream(xv + i), f);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) add(ok ? f[e] : 0.f, ok);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+      const int64_t t = nvec * V::N + threadIdx.x;
+      add(t < n ? to_f32<T>(x[t]) : 0.f, t < n);
+    }
+  } else {
+    const int64_t iters = (n + stride - 1) / stride;
+    for (int64_t t = 0; t < iters; ++t, i += stride) add(i < n ? to_f32<T>(x[i]) : 0.f, i < n);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 2 * kRadixBins; k += blockDim.x) {
+    const unsigned int c = (&sh[0][0])[k];
+    if (c) atomicAdd(hist + k, c);
+  }
+}
+
+// one warp per rank: locate the bin that holds the rank, descend into it
+__global__ void __launch_bounds__(64)
+radix_select_kernel(const unsigned int* __restrict__ hist, int pass, RadixState* __restrict__ state) {
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int p0 = state->prefix[0], p1 = state->prefix[1], nr = state->n_ranks;
+  __syncthreads();                                             // both warps have read the prefixes before either writes
+  if (j >= static_cast<int>(nr)) return;
+  const bool own = j == 1 && pass > 0 && p0 != p1;
+  const unsigned int* h = hist + (own ? kRadixBins : 0);
+  const int bins = static_cast<int>(radix_mask(pass)) + 1;
+  const int per = bins / 32;
+  unsigned long long mine = 0;
+  for (int b = 0; b < per; ++b) mine += h[lane * per + b];
+  unsigned long long incl = mine;                              // inclusive prefix over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned long long rank = state->rank[j];
+  const unsigned long long before = incl - mine;
+  const bool here = rank > before && rank <= incl;             // exactly one lane (rank <= total by construction)
+  const unsigned int who = __ballot_sync(0xffffffffu, here);
+  if (who == 0) {                                              // rank beyond the population: clamp to the last bin
+    if (lane == 31) { state->prefix[j] = (pass == 0 ? 0u : state->prefix[j] << (pass == 2 ? 10 : 11)) | (bins - 1); }
+    return;
+  }
+  if (here) {
+    unsigned long long cum = before;
+    int b = 0;
+    for (; b < per; ++b) {
+      const unsigned int c = h[lane * per + b];
+      if (rank <= cum + c) break;
+      cum += c;
+    }
+    if (b == per) b = per - 1;
+    const unsigned int digit = static_cast<unsigned int>(lane * per + b);
+    state->prefix[j] = (pass == 0 ? 0u : state->prefix[j] << (pass == 2 ? 10 : 11)) | digit;
+    state->rank[j] = rank - cum;
+  }
+}
+
+__global__ void radix_init_kernel(RadixState* state, unsigned long long r0, unsigned long long r1, unsigned int n) {
+  state->rank[0] = r0; state->rank[1] = r1; state->prefix[0] = 0u; state->prefix[1] = 0u; state->n_ranks = n; state->pad = 0u;
+}
+__global__ void radix_values_kernel(const RadixState* __restrict__ state, float* __restrict__ values) {
+  if (threadIdx.x < state->n_ranks) values[threadIdx.x] = radix_unkey(state->prefix[threadIdx.x]);
+}
+
+}  // namespace dlmcq
+
+using namespace dlmcq;
+
+extern "C" size_t dlmcq_obs_kth_state_bytes(void) { return 256 + 2 * kRadixBins * sizeof(unsigned int); }
+
+extern "C" int dlmcq_obs_kth_begin(void* state, int64_t rank0, int64_t rank1, void* stream) {
+  if (!state || rank0 < 1 || rank1 < 0) return DLMCQ_EINVAL;
+  radix_init_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<RadixState*>(state), static_cast<unsigned long long>(rank0), static_cast<unsigned long long>(rank1),
+      rank1 > 0 ? 2u : 1u);
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_kth_hist(const void* x, int64_t numel, int dtype, int flags, int pass, void* state,
+                                  void* stream) {
+  if (!x || !state || numel < 1 || pass < 0 || pass > 2) return DLMCQ_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(static_cast<char*>(state) + 256);
+  cudaError_t e = cudaMemsetAsync(hist, 0, 2 * kRadixBins * sizeof(unsigned int), st);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  const int abs_input = (flags & DLMCQ_STATS_ABS_INPUT) ? 1 : 0;
+  const RadixState* rs = static_cast<const RadixState*>(state);
+  if (dtype == DLMCQ_F32) {
+    const int64_t tiles = (numel / 4 + kThreads * 4 - 1) / (kThreads * 4);
+    radix_hist_kernel<float><<<stream_grid(tiles, 8), kThreads, 0, st>>>(static_cast<const float*>(x), numel, abs_input,
+                                                                         pass, rs, hist);
+  } else if (dtype == DLMCQ_BF16) {
+    const int64_t tiles = (numel / 8 + kThreads * 4 - 1) / (kThreads * 4);
+    radix_hist_kernel<__nv_bfloat16><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), numel, abs_input, pass, rs, hist);
+  } else {
+    return DLMCQ_EINVAL;
+  }
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_kth_select(int pass, void* state, void* stream) {
+  if (!state || pass < 0 || pass > 2) return DLMCQ_EINVAL;
+  const unsigned int* hist = reinterpret_cast<const unsigned int*>(static_cast<char*>(state) + 256);
+  radix_select_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(hist, pass, static_cast<RadixState*>(state));
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_kth_values(const void* state, float* values, void* stream) {
+  if (!state || !values) return DLMCQ_EINVAL;
+  radix_values_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const RadixState*>(state), values);
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}

@@ -13,7 +13,7 @@ from ._lib import (BF16, F32, FORM_A1, FORM_AFFINE, FORM_SYM, FORM_ZP, ROOTQ_STA
                    SWEEP_CANDIDATES, DlmcqError, Layout, QParams)
 
 __all__ = ["fq_forward", "fq_backward", "dequantize", "obs_stats", "minmax_from_stats", "absmean_from_stats",
-           "sweep_tensor", "sweep_channel", "l2norm_fixed_point", "adaround_forward", "adaround_backward",
+           "sweep_tensor", "sweep_channel", "kth_values", "l2norm_fixed_point", "adaround_forward", "adaround_backward",
            "adaround_init_alpha", "rootq_act_prepare", "rootq_act_forward", "rootq_act_backward", "rootq_wt_prepare",
            "rootq_wt_forward", "rootq_wt_backward", "GroupedFakeQuant", "HostFakeQuant", "layout_of"]
 
@@ -240,6 +240,31 @@ def absmean_from_stats(stats, count, mul_a, mul_b, mode):
         _lib.check(_lib.lib().dlmcq_obs_absmean_finalize(_ptr(stats), _ptr(out), ch, float(count), float(mul_a),
                                                          float(mul_b), int(mode), _stream_ptr()))
     return out
+
+
+def kth_values(x, ranks, abs_input=False, reduce_hist=None):
+    """Exact order statistics: the ranks[j]-th smallest elements (1-based, at most two ranks) of x or |x| by a
+    3-pass radix select - equal to torch.kthvalue.  reduce_hist (multi-GPU): called on the int32 histogram of each
+    pass (e.g. an all-reduce SUM) so that the result is the order statistic of the union of all ranks' tensors."""
+    _require_cuda(x, "x")
+    x = x.detach().contiguous()
+    ranks = [int(r) for r in ranks]
+    if not 1 <= len(ranks) <= 2 or min(ranks) < 1:
+        raise DlmcqError("kth_values takes one or two ranks >= 1")
+    h = _lib.lib()
+    state = torch.zeros(h.dlmcq_obs_kth_state_bytes(), dtype=torch.uint8, device=x.device)
+    values = torch.empty(2, dtype=torch.float32, device=x.device)
+    flags = 1 if abs_input else 0
+    with torch.cuda.device(x.device):
+        st = _stream_ptr()
+        _lib.check(h.dlmcq_obs_kth_begin(_ptr(state), ranks[0], ranks[1] if len(ranks) > 1 else 0, st))
+        for p in range(3):
+            _lib.check(h.dlmcq_obs_kth_hist(_ptr(x), x.numel(), _dtype_code(x), flags, p, _ptr(state), st))
+            if reduce_hist is not None:
+                reduce_hist(state[256:].view(torch.int32))
+            _lib.check(h.dlmcq_obs_kth_select(p, _ptr(state), st))
+        _lib.check(h.dlmcq_obs_kth_values(_ptr(state), _ptr(values), st))
+    return values[:len(ranks)]
 
 
 def sweep_tensor_sse(x, stats, n_bits, allow_offset=True):

@@ -21,7 +21,8 @@ from .utils import get_qrange, quantize
 
 __all__ = ["get_qparams_tensor", "get_qparams_output", "quantize_minmax_tensor", "quantize_minmax_channel",
            "quantize_minmax_pixel", "quantize_l2loss_tensor", "quantize_l2loss_channel", "quantize_l2norm_tensor",
-           "quantize_l2norm_channel", "quantize_l2norm_output", "quantize_l2norm_output_channel"]
+           "quantize_l2norm_channel", "quantize_l2norm_output", "quantize_l2norm_output_channel",
+           "quantize_percentile_tensor"]
 
 
 def get_qparams_output(input, weight, module, qtype, **kwargs):
@@ -81,6 +82,41 @@ def quantize_minmax_pixel(tensor, n_bits, signed, allow_offset=True):
         _check_nonneg(stats)
     scale, offset = F.minmax_from_stats(stats, n_bits, signed, allow_offset)
     return scale.reshape(new_shape), offset.reshape(new_shape)
+
+
+def percentile_ranks(numel, percentile):
+    """1-based ranks of the upper / lower clipping points: k_hi = ceil(p/100 * N), k_lo = N + 1 - k_hi."""
+    k_hi = min(numel, max(1, math.ceil(percentile / 100.0 * numel)))
+    return numel + 1 - k_hi, k_hi
+
+
+def quantize_percentile_tensor(tensor, n_bits, signed, percentile=99.99, allow_offset=True):
+    """Percentile-clipping observer - an EXTENSION named by the project's north star; dlmc's ops.py has no such
+    function (dispatchable as qtype "percentile_tensor" like the others).  Exact order statistics (3-pass radix
+    select, == torch.kthvalue) instead of min/max, then the min/max formulas of ops.py:20-34:
+      signed:   scale = kth(|x|, k_hi) / (2^(n-1) - 1), offset = 0
+      unsigned: scale = (kth(x, k_hi) - lo) / (2^n - 1), offset = lo, lo = kth(x, k_lo) (0 if not allow_offset).
+    Under torch.distributed the per-pass histograms are all-reduced: the statistics of the union of all ranks."""
+    n = tensor.numel()
+    reduce_hist = None
+    w = qdist.world_size()
+    if w > 1:
+        import torch.distributed as dist
+        cnt = torch.tensor([n], dtype=torch.int64, device=tensor.device)
+        dist.all_reduce(cnt)
+        n = int(cnt)
+        reduce_hist = lambda h: dist.all_reduce(h)
+    k_lo, k_hi = percentile_ranks(n, percentile)
+    if signed:
+        a = F.kth_values(tensor, [k_hi], abs_input=True, reduce_hist=reduce_hist)
+        stats = torch.stack([a[0], a[0], a[0], a[0]]).reshape(1, 4)
+    else:
+        v = F.kth_values(tensor, [k_lo, k_hi], reduce_hist=reduce_hist)
+        stats = torch.stack([v[0], v[1], v[1].abs(), v[1]]).reshape(1, 4)
+        if not allow_offset:
+            _check_nonneg(stats)
+    scale, offset = F.minmax_from_stats(stats.contiguous(), n_bits, signed, allow_offset)
+    return scale.reshape(()), offset.reshape(())
 
 
 def quantize_l2loss_tensor(tensor, n_bits, signed, allow_offset=True):

@@ -209,6 +209,22 @@ int dlmcq_obs_minmax_finalize(const float* stats, float* scale, float* offset, i
 int dlmcq_obs_absmean_finalize(const float* stats, float* out, int64_t channels, double count,
                                double mul_a, double mul_b, int mode, void* stream);
 
+/* Percentile-clipping observer (named by the north star; the reference's ops.py has no counterpart, so the
+ * semantics are defined here and pinned against torch.kthvalue): EXACT order statistics by a 3-pass radix
+ * select - value_j = the rank_j-th smallest element (1-based) of x, or of |x| with DLMCQ_STATS_ABS_INPUT;
+ * NaN sorts last, -0 == +0.  Up to two ranks share the passes (lower / upper percentile).
+ *   dlmcq_obs_kth_begin(state, rank0, rank1 /0 = unused/)
+ *   for pass in 0,1,2:  dlmcq_obs_kth_hist(x, ..., pass, state)   one read of x; histogram of key digit `pass`
+ *                       [multi-GPU: all-reduce(SUM) the 2*2048 uint32 counters at state+256]
+ *                       dlmcq_obs_kth_select(pass, state)
+ *   dlmcq_obs_kth_values(state, values[2])
+ * state: dlmcq_obs_kth_state_bytes() bytes of DEVICE memory; no host synchronisation anywhere. */
+size_t dlmcq_obs_kth_state_bytes(void);
+int dlmcq_obs_kth_begin(void* state, int64_t rank0, int64_t rank1, void* stream);
+int dlmcq_obs_kth_hist(const void* x, int64_t numel, int dtype, int flags, int pass, void* state, void* stream);
+int dlmcq_obs_kth_select(int pass, void* state, void* stream);
+int dlmcq_obs_kth_values(const void* state, float* values, void* stream);
+
 /* ops.py:36-68 quantize_l2loss_tensor (unsigned branch): 80-candidate clip-ratio sweep.
  * Pass 1 (dlmcq_obs_stats) gives min/max; this pass accumulates the 80 squared-error sums
  * sse[80] in one read of x; the finalize picks the first strict minimum below 1000 of

@@ -440,6 +440,22 @@ def obs_l2norm_channel(t, n_bits, signed, ch_axis=0, return_iters=False):
     return out + (iters,) if return_iters else out
 
 
+def obs_percentile_tensor(t, n_bits, signed, percentile=99.99, allow_offset=True):
+    """EXTENSION without a reference counterpart (the north star names a percentile observer; ops.py has none):
+    exact order statistics via torch.kthvalue, then the min/max formulas of ops.py:20-34.  Parity for this one
+    observer is pinned to torch.kthvalue, not to the reference."""
+    flat = t.detach().float().flatten()
+    n = flat.numel()
+    k_hi = min(n, max(1, math.ceil(percentile / 100.0 * n)))
+    k_lo = n + 1 - k_hi
+    if signed:
+        a = flat.abs().kthvalue(k_hi)[0]
+        return a / (2 ** (n_bits - 1) - 1), torch.tensor(0)
+    hi = flat.kthvalue(k_hi)[0]
+    lo = flat.kthvalue(k_lo)[0] if allow_offset else torch.zeros(())
+    return (hi - lo) / (2 ** n_bits - 1), lo
+
+
 OBSERVERS = {
     "minmax_tensor": obs_minmax_tensor,
     "minmax_channel": obs_minmax_channel,

@@ -11,6 +11,9 @@ Arms:  ours  - torchvision resnet50 with every Conv2d/Linear swapped by dlmc_qua
                modules/base.py:96-102,131-133 differentiated by autograd, on the same GPU
                ("PyTorch eager on B200").  Test infrastructure, uses oracle/restate.py.
        fp32  - the un-quantised model, for scale.
+       bf16 / ours_bf16 - (opt-in: --arm bf16,ours_bf16) the same two models under torch.autocast(bfloat16):
+               bf16 activations go through the bf16 kernels (fp32 arithmetic, one RNE rounding on store,
+               fp32 scale gradients); an extension beyond the fp32-only reference, reported separately.
 The convolutions are cuDNN library calls in all arms; only the fake-quant path differs."""
 import argparse
 import copy
@@ -74,7 +77,8 @@ def run(arm, args, device, world):
     import torchvision
     torch.manual_seed(2333)
     model = torchvision.models.resnet50().to(device)
-    if arm == "ours":
+    amp = arm.endswith("bf16")
+    if arm in ("ours", "ours_bf16"):
         from dlmc_quant_b200 import quantize_model
         quantize_model(model, copy.deepcopy(CFG), None)
     elif arm == "eager":
@@ -82,8 +86,8 @@ def run(arm, args, device, world):
     x = torch.randn(args.batch, 3, 224, 224, device=device)
     t = torch.randint(0, 1000, (args.batch,), device=device)
     model.train()
-    with torch.no_grad():       # lazy observer init before DDP wraps the parameters (shapes may change)
-        model(x[:8])
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        model(x[:8])            # lazy observer init before DDP wraps the parameters (shapes may change)
     if world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True)
@@ -91,7 +95,8 @@ def run(arm, args, device, world):
 
     def step():
         opt.zero_grad(set_to_none=True)
-        loss = crit(model(x), t)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            loss = crit(model(x), t)
         loss.backward()
         opt.step()
         return loss
@@ -128,7 +133,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     out = {"model": "torchvision resnet50, W4 per-channel / A4 per-tensor QAT, fp32 (TF32 convs: torch default)",
            "per_gpu_batch": args.batch, "n_gpus": world, "steps": args.steps, "data": "synthetic 3x224x224"}
-    for arm in (["fp32", "eager", "ours"] if args.arm == "all" else [args.arm]):
+    for arm in (["fp32", "eager", "ours"] if args.arm == "all" else args.arm.split(",")):
         ips, ms = run(arm, args, device, world)
         out[arm] = {"images_per_s": round(ips, 1), "ms_per_step": round(ms, 2)}
         torch.cuda.empty_cache()

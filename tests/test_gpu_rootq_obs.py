@@ -365,3 +365,56 @@ def test_l2norm_per_channel_multi_cta_finalise():
     s, iters, done = F().l2norm_fixed_point(dev(w), s0, o0, lo, hi)
     assert done and abs(int(iters) - ref_iters) <= 2, (int(iters), ref_iters)
     assert torch.allclose(s.cpu(), rs.reshape(-1), rtol=2e-4)
+
+
+# --------------------------------------------------------------------------------------
+# percentile observer (north-star extension): exact order statistics == torch.kthvalue
+@pytest.mark.parametrize("n", [1, 7, 1000, (1 << 20) + 13])
+@pytest.mark.parametrize("kind", ["randn", "relu", "const", "special"])
+def test_kth_values_equal_torch_kthvalue(n, kind):
+    gen = torch.Generator().manual_seed(31 + n)
+    x = torch.randn(n, generator=gen) * 3
+    if kind == "relu":
+        x = torch.relu(x)                          # half of the elements in one histogram bin
+    elif kind == "const":
+        x = torch.full((n,), -1.25)
+    elif kind == "special":
+        x[::5] = 0.0
+        x[1::7] = -0.0
+        if n > 20:
+            x[3], x[4], x[11], x[12] = float("inf"), float("-inf"), 1e-45, -1e-45
+    for dtype in (torch.float32, torch.bfloat16):
+        xd = x.to(dtype)
+        ranks = sorted({1, n, (n + 1) // 2, max(1, n - n // 1000), min(n, 1 + n // 1000)})
+        for i in range(0, len(ranks), 2):
+            pair = ranks[i:i + 2]
+            got = F().kth_values(dev(xd), pair).cpu()
+            want = torch.stack([xd.float().kthvalue(k)[0] for k in pair])
+            assert torch.equal(got, want), (n, kind, dtype, pair, got, want)
+            got_abs = F().kth_values(dev(xd), pair, abs_input=True).cpu()
+            want_abs = torch.stack([xd.float().abs().kthvalue(k)[0] for k in pair])
+            assert torch.equal(got_abs, want_abs), (n, kind, dtype, pair, got_abs, want_abs)
+
+
+def test_kth_values_nan_sorts_last_and_multidim():
+    x = torch.tensor([[3.0, float("nan")], [-2.0, 5.0]])
+    got = F().kth_values(dev(x), [3, 4]).cpu()
+    assert got[0] == 5.0 and torch.isnan(got[1])                       # like torch.sort: NaN is the largest
+    t = torch.randn(4, 8, 14, 14, generator=torch.Generator().manual_seed(5))
+    assert F().kth_values(dev(t), [100]).cpu()[0] == t.flatten().kthvalue(100)[0]
+
+
+@pytest.mark.parametrize("signed,bits,pct", [(False, 4, 99.9), (False, 8, 99.99), (True, 4, 99.0), (True, 8, 100.0)])
+def test_percentile_observer_vs_oracle(signed, bits, pct):
+    from dlmc_quant_b200.scalar import ops
+    gen = torch.Generator().manual_seed(41)
+    t = torch.randn(16, 32, 28, 28, generator=gen) * 2
+    if not signed:
+        t = torch.relu(t) + 0.125
+    s, o = ops.get_qparams_tensor(dev(t), "percentile_tensor", n_bits=bits, signed=signed, percentile=pct)
+    rs, ro = R.obs_percentile_tensor(t, bits, signed, pct)
+    exact(s.reshape(1), rs.reshape(1), "scale")
+    exact(o.reshape(1), ro.reshape(1).float(), "offset")
+    if pct == 100.0:                                                    # degenerates to the min/max observer
+        ms, mo = ops.quantize_minmax_tensor(dev(t), bits, signed)
+        assert torch.equal(ms, s) and torch.equal(mo.float(), o.float())
