@@ -31,27 +31,47 @@ def _dtype_code(t):
     raise DlmcqError(f"unsupported dtype {t.dtype}: fp32 and bf16 only")
 
 
+def _raw_stream(index=None):
+    """Current CUDA stream handle as an int, without building a torch.cuda.Stream object (per-layer hot path)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if index is None else index)
+
+
 def _stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(_raw_stream())
 
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_layouts = {}
+
+
 def layout_of(t, ch_axis=None):
-    """[outer, channels, inner] view of a contiguous tensor (see include/dlmcq.h)."""
+    """[outer, channels, inner] view of a contiguous tensor (see include/dlmcq.h).  Cached per
+    (shape, axis, dtype): the structs are read-only for the library."""
+    key = (t.shape, ch_axis, t.dtype)
+    lay = _layouts.get(key)
+    if lay is not None:
+        return lay
     if ch_axis is None:
-        return Layout(1, 1, t.numel(), _dtype_code(t))
-    shape = list(t.shape)
-    ch_axis = ch_axis % len(shape)
-    return Layout(math.prod(shape[:ch_axis]), shape[ch_axis], math.prod(shape[ch_axis + 1:]), _dtype_code(t))
+        lay = Layout(1, 1, t.numel(), _dtype_code(t))
+    else:
+        shape = list(t.shape)
+        ax = ch_axis % len(shape)
+        lay = Layout(math.prod(shape[:ax]), shape[ax], math.prod(shape[ax + 1:]), _dtype_code(t))
+    if len(_layouts) < 4096:
+        _layouts[key] = lay
+    return lay
 
 
 def _qvec(v, channels, device, name):
     """scale / offset as a float32 device vector of `channels` entries (no sync when already on device)."""
     if v is None:
         return None
+    if (isinstance(v, torch.Tensor) and v.dtype is torch.float32 and v.device == device and v.numel() == channels
+            and v.is_contiguous()):
+        return v                                   # parameters / buffers already in kernel form: only data_ptr is read
     if not isinstance(v, torch.Tensor):
         v = torch.full((channels,), float(v), dtype=torch.float32, device=device)
     if v.device != device or v.dtype != torch.float32:
@@ -69,7 +89,7 @@ _workspaces = {}
 
 def _workspace(device, nbytes):
     """Zero-initialised scratch, one per (device, stream); kernels leave it zeroed."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, _raw_stream(device.index))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -105,10 +125,22 @@ def _on(device):
 
 
 # --------------------------------------------------------------------------------------
+def dense_as_is(x, ch_axis):
+    """True when the kernels can index x's storage directly: contiguous, or a dense channels_last 4-D tensor
+    quantised per tensor / per dim-0 channel (dim 0 stays outermost, and within one tensor or one row the
+    element order does not matter) - so channels_last models are served without a layout copy."""
+    return x.is_contiguous() or (x.dim() == 4 and (ch_axis is None or ch_axis == 0) and
+                                 x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _dense(x, ch_axis):
+    return x if dense_as_is(x, ch_axis) else x.contiguous()
+
+
 def fq_forward(x, scale, offset, lo, hi, form, g=0.0, ch_axis=None, want_codes=False, want_y=True):
-    """Fused fake-quant forward -> y (and/or the integer codes as a float tensor)."""
+    """Fused fake-quant forward -> y (and/or the integer codes as a float tensor), in x's memory format."""
     _require_cuda(x, "x")
-    x = x.detach().contiguous()
+    x = _dense(x.detach(), ch_axis)
     lay = layout_of(x, ch_axis)
     s = _qvec(scale, lay.channels, x.device, "scale")
     o = _qvec(offset, lay.channels, x.device, "offset")
@@ -126,10 +158,12 @@ def fq_backward(x, dy, scale, offset, lo, hi, form, g=0.0, ch_axis=None, want_do
     """Fused backward: one pass over (x, dy) -> dx, dscale[channels] (, doffset[channels])."""
     _require_cuda(x, "x")
     _require_cuda(dy, "dy")
-    x = x.detach().contiguous()
-    dy = dy.detach().contiguous()
+    x = _dense(x.detach(), ch_axis)
+    dy = dy.detach()
     if dy.dtype != x.dtype or dy.shape != x.shape:
         raise DlmcqError("dy must match x in dtype and shape")
+    if dy.stride() != x.stride() or not dense_as_is(dy, ch_axis):      # same element order as x
+        dy = dy.contiguous() if x.is_contiguous() else dy.contiguous(memory_format=torch.channels_last)
     lay = layout_of(x, ch_axis)
     s = _qvec(scale, lay.channels, x.device, "scale")
     o = _qvec(offset, lay.channels, x.device, "offset")

@@ -10,7 +10,7 @@ import torch
 
 from ... import functional as F
 from ..._lib import FORM_A1, FORM_AFFINE, FORM_SYM, FORM_ZP  # noqa: F401
-from ..utils import _view3
+from ..utils import _view3, infer_ch_axis
 
 __all__ = ["FakeQuantFunction", "fake_quantize", "FunUniformQ", "FunLSQ", "FunRootQ", "FunLQ"]
 
@@ -30,12 +30,19 @@ class FakeQuantFunction(torch.autograd.Function):
         x, scale, offset = ctx.saved_tensors
         lo, hi, form, g, ch_axis = ctx.cfg
         dx, ds = F.fq_backward(x, dy, scale, offset, lo, hi, form, g=g, ch_axis=ch_axis)
-        return dx, ds.reshape(scale.shape).to(scale.dtype), None, None, None, None, None, None
+        if ds.shape != scale.shape:
+            ds = ds.reshape(scale.shape)
+        return dx, ds if ds.dtype is scale.dtype else ds.to(scale.dtype), None, None, None, None, None, None
 
 
 def fake_quantize(x, scale, offset, lo, hi, form, g=0.0):
     """Differentiable fake-quant; the channel axis is inferred from the scale's broadcast shape."""
-    v, ax = _view3(x if x.is_contiguous() else x.contiguous(), scale)
+    run = infer_ch_axis(x, scale)
+    if run is None or run[0] == run[1]:                      # the common cases: no reshape, no extra autograd node
+        ax = None if run is None else run[0]
+        v = x if (x.is_contiguous() or F.dense_as_is(x, ax)) else x.contiguous()   # channels_last passes through
+        return FakeQuantFunction.apply(v, scale, offset, lo, hi, form, g, ax)
+    v, ax = _view3(x.contiguous(), scale)
     return FakeQuantFunction.apply(v, scale, offset, lo, hi, form, g, ax).reshape(x.shape)
 
 

@@ -1,0 +1,30 @@
+"""Timing of the exact k-th-value selection (percentile observer) on 2^26 elements; torch.kthvalue beside it."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dlmc_quant_b200 import functional as F  # noqa: E402
+
+n = 1 << 26
+for name, x in (("relu(randn)*2", torch.relu(torch.randn(n, device="cuda")) * 2), ("randn", torch.randn(n, device="cuda")),
+                ("bf16 randn", torch.randn(n, device="cuda").bfloat16())):
+    ranks = [n // 10000, n - n // 10000]
+    for _ in range(2):
+        F.kth_values(x, ranks)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        v = F.kth_values(x, ranks)
+    b.record()
+    torch.cuda.synchronize()
+    t = a.elapsed_time(b) / 10
+    es = x.element_size()
+    a.record()
+    w = torch.stack([x.float().kthvalue(k)[0] for k in ranks])
+    b.record()
+    torch.cuda.synchronize()
+    print(f"kth_values {name:14s} two ranks: {t * 1e3:7.1f} us = {3 * es * n / t / 1e6:6.0f} GB/s over three reads; "
+          f"equal to torch.kthvalue: {torch.equal(v, w)} (torch: {a.elapsed_time(b) * 1e3:.0f} us)")

@@ -84,6 +84,9 @@ def run(arm, args, device, world):
     elif arm == "eager":
         make_eager(model)
     x = torch.randn(args.batch, 3, 224, 224, device=device)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
     t = torch.randint(0, 1000, (args.batch,), device=device)
     model.train()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
@@ -122,6 +125,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--arm", default="all")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="model and input in channels_last memory format (all arms); the fake-quant kernels index "
+                         "dense channels_last tensors directly")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -132,7 +138,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     out = {"model": "torchvision resnet50, W4 per-channel / A4 per-tensor QAT, fp32 (TF32 convs: torch default)",
-           "per_gpu_batch": args.batch, "n_gpus": world, "steps": args.steps, "data": "synthetic 3x224x224"}
+           "per_gpu_batch": args.batch, "n_gpus": world, "steps": args.steps, "data": "synthetic 3x224x224",
+           "memory_format": "channels_last" if args.channels_last else "contiguous (NCHW)"}
     for arm in (["fp32", "eager", "ours"] if args.arm == "all" else args.arm.split(",")):
         ips, ms = run(arm, args, device, world)
         out[arm] = {"images_per_s": round(ips, 1), "ms_per_step": round(ms, 2)}

@@ -370,3 +370,45 @@ def test_fsptq_reconstruction_driver():
         torch.optim.Adam([p for n, p in module.named_parameters() if n.endswith(("alpha", "scale"))], lr=5e-3))
     hist2 = rec2.run(batches, generator=torch.Generator().manual_seed(2))
     assert hist2["b1"][-1] < hist2["b1"][0], hist2["b1"]
+
+
+def test_channels_last_tensors_pass_through_without_copy():
+    """Per-tensor activations and per-dim-0-channel weights in channels_last memory format: the kernels index
+    the storage directly; values, gradients and the output's memory format match the contiguous path."""
+    from dlmc_quant_b200 import functional as F
+    from dlmc_quant_b200._lib import FORM_AFFINE
+    from dlmc_quant_b200.scalar.modules.function import fake_quantize
+    gen = torch.Generator().manual_seed(77)
+    x = (torch.relu(torch.randn(4, 16, 9, 9, generator=gen)) * 2).cuda()
+    dy = torch.randn(4, 16, 9, 9, generator=gen).cuda()
+    scale = torch.tensor([0.21], device="cuda", requires_grad=True)
+    off = torch.zeros(1, device="cuda")
+    g = 1 / (x.numel() * 15) ** 0.5
+
+    def run(inp, grad):
+        inp = inp.clone().requires_grad_(True)
+        s = scale.detach().clone().requires_grad_(True)
+        y = fake_quantize(inp, s, off, 0, 15, FORM_AFFINE, g)
+        y.backward(grad)
+        return y.detach(), inp.grad, s.grad
+
+    y0, dx0, ds0 = run(x, dy)
+    xc, dyc = x.contiguous(memory_format=torch.channels_last), dy.contiguous(memory_format=torch.channels_last)
+    y1, dx1, ds1 = run(xc, dyc)
+    assert y1.is_contiguous(memory_format=torch.channels_last) and dx1.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y0, y1) and torch.equal(dx0, dx1)
+    assert torch.allclose(ds0, ds1, rtol=1e-5, atol=1e-7)               # summation order differs
+    y2, dx2, _ = run(xc, dy)                                            # gradient arrives in the other format
+    assert torch.equal(y0, y2) and torch.equal(dx0, dx2)
+    # weights [Cout, Cin, kh, kw], per output channel
+    w = (torch.randn(8, 16, 3, 3, generator=gen) * 0.05).cuda()
+    ws = (w.abs().amax(dim=(1, 2, 3)) / 7).reshape(-1, 1, 1, 1)
+    wc = w.contiguous(memory_format=torch.channels_last)
+    assert F.dense_as_is(wc, 0) and not wc.is_contiguous()
+    yw0 = F.fq_forward(w, ws, None, -7, 7, 3, ch_axis=0)
+    yw1 = F.fq_forward(wc, ws, None, -7, 7, 3, ch_axis=0)
+    assert yw1.is_contiguous(memory_format=torch.channels_last) and torch.equal(yw0, yw1)
+    # per-channel ACTIVATIONS (ch_axis=1) in channels_last need the NCHW order: copied, still correct
+    s1 = (x.amax(dim=(0, 2, 3)) / 15 + 1e-3).reshape(1, -1, 1, 1)
+    o1 = torch.zeros_like(s1)
+    assert torch.equal(F.fq_forward(x, s1, o1, 0, 15, 1, ch_axis=1), F.fq_forward(xc, s1, o1, 0, 15, 1, ch_axis=1))
