@@ -114,3 +114,27 @@ def l2norm_tensor(x, n_bits, signed, max_iters=1000):
     it = lib().orc_l2norm_tensor(_p(x), C.c_int64(x.size), C.c_int(n_bits), C.c_int(int(signed)), C.c_int(max_iters),
                                  C.byref(s), C.byref(o))
     return s.value, o.value, it
+
+
+def merge_bn(w, bias, gamma, beta, mean, var):
+    w = _f(w)
+    c = w.shape[0]
+    inner = w.size // c
+    wo, bo = np.empty_like(w), np.empty(c, np.float32)
+    b = None if bias is None else _f(bias)
+    lib().orc_merge_bn(_p(w), _p(b), _p(_f(gamma)), _p(_f(beta)), _p(_f(mean)), _p(_f(var)), C.c_int64(c),
+                       C.c_int64(inner), _p(wo), _p(bo))
+    return wo, bo
+
+
+def repvgg_fuse(k3, bn3, k1, bn1, bn_id, eps):
+    """bn* = (gamma, beta, mean, var); bn_id None when the block has no identity branch."""
+    k3, k1 = _f(k3), _f(k1)
+    c, cin_g = k3.shape[0], k3.shape[1]
+    wo, bo = np.empty_like(k3), np.empty(c, np.float32)
+    a3 = [_f(t) for t in bn3]
+    a1 = [_f(t) for t in bn1]
+    ai = [None] * 4 if bn_id is None else [_f(t) for t in bn_id]
+    lib().orc_repvgg_fuse(_p(k3), *[_p(t) for t in a3], C.c_float(eps), _p(k1), *[_p(t) for t in a1], C.c_float(eps),
+                          *[_p(t) for t in ai], C.c_float(eps), C.c_int64(c), C.c_int64(cin_g), _p(wo), _p(bo))
+    return wo, bo

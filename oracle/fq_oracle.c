@@ -253,3 +253,50 @@ int orc_l2norm_tensor(const float* x, int64_t n, int n_bits, int is_signed, int 
   }
   return it;
 }
+
+/* ---- weight-space re-parameterisation -----------------------------------------
+ * sqrtf here is the correctly rounded IEEE square root (what torch computes on CUDA; torch's CPU sqrt goes
+ * through MKL VML and is only faithfully rounded - see oracle/restate.py::sqrt_ieee). */
+
+/* dlmc/utils/merge_bn.py:84-100: var = running_var + 1e-7; w' = (w*gamma)/sqrt(var);
+ * b' = (gamma*(b-mean))/sqrt(var) + beta; bias == NULL -> zeros (:92-94) */
+void orc_merge_bn(const float* w, const float* bias, const float* gamma, const float* beta, const float* mean,
+                  const float* var, int64_t channels, int64_t inner, float* w_out, float* bias_out) {
+  for (int64_t c = 0; c < channels; ++c) {
+    const float v = var[c] + 1e-7f;
+    const float sd = sqrtf(v);
+    for (int64_t j = 0; j < inner; ++j) w_out[c * inner + j] = (w[c * inner + j] * gamma[c]) / sd;
+    const float b = bias ? bias[c] : 0.f;
+    bias_out[c] = (gamma[c] * (b - mean[c])) / sd + beta[c];
+  }
+}
+
+/* model/classification/repvgg.py:92-123: bn* = gamma, beta, mean, var arrays (bn_id_gamma == NULL: no identity
+ * branch, the reference then adds the integer 0); k3 [C, cin_g, 3, 3], k1 [C, cin_g] */
+void orc_repvgg_fuse(const float* k3, const float* g3, const float* b3, const float* m3, const float* v3, float eps3,
+                     const float* k1, const float* g1, const float* b1, const float* m1, const float* v1, float eps1,
+                     const float* gi, const float* bi, const float* mi, const float* vi, float epsi,
+                     int64_t channels, int64_t cin_g, float* w_out, float* bias_out) {
+  for (int64_t c = 0; c < channels; ++c) {
+    const float std3 = sqrtf(v3[c] + eps3), t3 = g3[c] / std3;
+    const float bias3 = b3[c] - (m3[c] * g3[c]) / std3;
+    const float std1 = sqrtf(v1[c] + eps1), t1 = g1[c] / std1;
+    const float bias1 = b1[c] - (m1[c] * g1[c]) / std1;
+    float tid = 0.f, biasid = 0.f;
+    if (gi) {
+      const float stdi = sqrtf(vi[c] + epsi);
+      tid = gi[c] / stdi;
+      biasid = bi[c] - (mi[c] * gi[c]) / stdi;
+    }
+    for (int64_t ci = 0; ci < cin_g; ++ci) {
+      for (int p = 0; p < 9; ++p) {
+        const int64_t j = (c * cin_g + ci) * 9 + p;
+        const float a = k3[j] * t3;
+        const float b = (p == 4) ? k1[c * cin_g + ci] * t1 : 0.f;                 /* F.pad(kernel1x1, [1,1,1,1]) */
+        const float d = gi ? ((p == 4 && ci == c % cin_g) ? 1.f : 0.f) * tid : 0.f;  /* id_tensor * t, or + 0 */
+        w_out[j] = (a + b) + d;
+      }
+    }
+    bias_out[c] = (bias3 + bias1) + biasid;
+  }
+}

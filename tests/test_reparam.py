@@ -238,3 +238,21 @@ def test_repvgg_model_convert_matches_oracle_and_keeps_the_function():
         (s_got, _), = P.observe_folded(stats[str(i)], [w.shape[0]], 8, True)
         assert G.bits_equal(s_got.cpu(), s)
     assert torch.allclose(deploy(x.cuda()).cpu(), want, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ plain-C oracle
+@pytest.mark.parametrize("name", MERGE + REPVGG)
+def test_c_oracle_fold_matches_reference(name):
+    """The torch-free C restatement (IEEE sqrtf) against the fixtures minted from the reference."""
+    from oracle import c_oracle
+    c = CASES[name]
+    n = lambda t: t.numpy()
+    if name in MERGE:
+        w, b = c_oracle.merge_bn(n(c.inp["w"]), n(c.inp["bias"]) if "bias" in c.inp else None, n(c.inp["gamma"]),
+                                 n(c.inp["beta"]), n(c.inp["mean"]), n(c.inp["var"]))
+    else:
+        pack = lambda tag: tuple(n(t) for t in _bn_of(c, tag))
+        w, b = c_oracle.repvgg_fuse(n(c.inp["k3"]), pack("bn3"), n(c.inp["k1"]), pack("bn1"),
+                                    pack("bnid") if c.meta["has_id"] else None, c.meta["eps"])
+    assert G.bits_equal(torch.from_numpy(w), c.out["w"]), G.first_mismatch(torch.from_numpy(w), c.out["w"])
+    assert G.bits_equal(torch.from_numpy(b), c.out["bias"])
