@@ -41,6 +41,20 @@ class FoldItem(C.Structure):
 FOLD_MERGE_BN, FOLD_REPVGG = 0, 1
 
 
+class RootqPrep(C.Structure):
+    _fields_ = [("param_a", C.c_void_p), ("param_b", C.c_void_p), ("alpha", C.c_void_p), ("run_a", C.c_void_p),
+                ("run_b", C.c_void_p), ("state", C.c_void_p), ("momentum", C.c_double), ("g", C.c_double),
+                ("lo", C.c_int32), ("hi", C.c_int32), ("training", C.c_int32), ("is_weight", C.c_int32)]
+
+
+class RootqItem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("dy", C.c_void_p), ("state", C.c_void_p),
+                ("grads", C.c_void_p), ("numel", C.c_int64)]
+
+
+ROOTQ_UNIT = 2048
+
+
 class FinalizeItem(C.Structure):
     _fields_ = [("partials", C.c_void_p), ("dscale", C.c_void_p)]
 
@@ -80,6 +94,9 @@ SIGNATURES = {
     "dlmcq_rootq_wt_prepare": (_I, [_P, _P, _P, _P, _P, _D, _D, _I, _I, _I, _P, _P]),
     "dlmcq_rootq_wt_forward": (_I, [_P, _P, _L, _I, _P, _P]),
     "dlmcq_rootq_wt_backward": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _Z, _P]),
+    "dlmcq_rootq_prepare_many": (_I, [_P, _I, _P]),
+    "dlmcq_rootq_wt_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
+    "dlmcq_rootq_wt_backward_grouped": (_I, [_P, _P, _I, _L, _I, _P, _P]),
     "dlmcq_obs_stats": (_I, [_P, _P, _LP, _I, _P, _Z, _P]),
     "dlmcq_obs_minmax_finalize": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
     "dlmcq_obs_absmean_finalize": (_I, [_P, _P, _L, _D, _D, _D, _I, _P]),

@@ -355,6 +355,153 @@ rootq_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restric
   }
 }
 
+// ---- grouped (multi-tensor) launches --------------------------------------------------------------
+// The RootQ weight tensors of a CNN are <= 9.4 MB each and every quantizer has a scalar prologue: 21 layers
+// of cifar ResNet-18 cost 126 launches per training step when run one by one.  Here ONE launch prepares all
+// quantizers (activation and weight), ONE quantises all weight tensors and ONE differentiates them
+// (+ a small finalisation): work units of DLMCQ_ROOTQ_UNIT elements, one warp each, located by a binary
+// search over the unit prefix.  Same per-element device functions as the single-tensor kernels.
+__global__ void rootq_prepare_many_kernel(const dlmcq_rootq_prep* __restrict__ items, int n_items) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_items) return;
+  const dlmcq_rootq_prep it = items[k];
+  const float m = static_cast<float>(it.momentum), one_minus_m = static_cast<float>(1.0 - it.momentum);
+  const float g = static_cast<float>(it.g), one_minus_g = static_cast<float>(1.0 - it.g);
+  const float q = static_cast<float>(it.hi - it.lo);
+  if (it.is_weight) {
+    float U, L;
+    if (it.training) {
+      U = it.run_a[0] * one_minus_m + m * it.param_a[0];   // base.py:137
+      L = it.run_b[0] * one_minus_m + m * it.param_b[0];   // :138
+      U = g * U + one_minus_g * U;                         // :139
+      L = g * L + one_minus_g * L;                         // :140
+      it.run_a[0] = U;                                     // :141
+      it.run_b[0] = L;                                     // :142
+    } else {
+      U = it.run_a[0];
+      L = it.run_b[0];
+    }
+    const float a0 = it.alpha[0];
+    const float r1 = relu_ref(1e-4f - a0);                 // function.py:25-26
+    const float a1 = a0 + r1;
+    const float r2 = relu_ref(a1 - 1.f);
+    it.state[RW_U] = U;
+    it.state[RW_L] = L;
+    it.state[RW_DELTA] = (U - L) / q;                      // base.py:147
+    it.state[RW_ALPHA] = a1 - r2;
+    it.state[RW_G] = g;
+    it.state[RW_M] = m;
+    it.state[RW_AMASK] = (!(r1 > 0.f) && !(r2 > 0.f)) ? 1.f : 0.f;
+    it.state[RW_Q] = q;
+  } else {
+    float rs;
+    if (it.training) {
+      rs = it.run_a[0] * one_minus_m + m * it.param_a[0];  // base.py:95
+      rs = g * rs + one_minus_g * rs;                      // :97
+      it.run_a[0] = rs;                                    // :101
+    } else {
+      rs = it.run_a[0];                                    // :105
+    }
+    it.state[RA_SCALE] = rs;
+    it.state[RA_UPPER] = rs * q;                           // :99,106
+    it.state[RA_G] = g;
+    it.state[RA_M] = m;
+    it.state[RA_Q] = q;
+  }
+}
+
+__device__ __forceinline__ int rq_find(const int64_t* __restrict__ prefix, int n_items, int64_t unit) {
+  int lo = 0, hi = n_items;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(prefix + mid) <= unit) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kRowWarps * 32)
+rootq_wt_grouped_kernel(const dlmcq_rootq_item* __restrict__ items, const int64_t* __restrict__ prefix, int n_items,
+                        int64_t total_units, float* __restrict__ partials) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  const int lane = threadIdx.x & 31;
+  const int64_t unit = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (unit >= total_units) return;
+  const int k = rq_find(prefix, n_items, unit);
+  const dlmcq_rootq_item it = items[k];
+  const int64_t beg = (unit - __ldg(prefix + k)) * DLMCQ_ROOTQ_UNIT;
+  const int64_t len = (it.numel - beg) < DLMCQ_ROOTQ_UNIT ? (it.numel - beg) : DLMCQ_ROOTQ_UNIT;
+  const RqW pw = load_rqw(it.state);
+  const T* xr = static_cast<const T*>(it.x) + beg;
+  const T* gr = BWD ? static_cast<const T*>(it.dy) + beg : nullptr;
+  T* yr = static_cast<T*>(it.y) + beg;
+  float acc[3] = {0.f, 0.f, 0.f};
+  int64_t done = 0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(yr) |
+                     reinterpret_cast<uintptr_t>(gr)) & 15u) == 0;
+  if (vec) {
+    const int64_t nvec = len / V::N;
+    const raw* xv = reinterpret_cast<const raw*>(xr);
+    const raw* gv = reinterpret_cast<const raw*>(gr);
+    raw* yv = reinterpret_cast<raw*>(yr);
+    for (int64_t j = lane; j < nvec; j += 64) {           // two 128-bit loads per tensor in flight
+      const bool two = j + 32 < nvec;
+      raw x0 = ld_stream(xv + j), x1 = x0, g0 = x0, g1 = x0;
+      if (two) x1 = ld_stream(xv + j + 32);
+      if (BWD) { g0 = ld_stream(gv + j); if (two) g1 = ld_stream(gv + j + 32); }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && !two) break;
+        float a[V::N], b[V::N], o[V::N];
+        V::unpack(h ? x1 : x0, a);
+        if (BWD) V::unpack(h ? g1 : g0, b);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e)
+          o[e] = BWD ? rq_wt_bwd(a[e], b[e], pw, acc[0], acc[1], acc[2]) : rq_wt_fwd(a[e], pw);
+        st_stream(yv + j + 32 * h, V::pack(o));
+      }
+    }
+    done = nvec * V::N;
+  }
+  for (int64_t j = done + lane; j < len; j += 32) {
+    const float a = to_f32<T>(xr[j]);
+    yr[j] = from_f32<T>(BWD ? rq_wt_bwd(a, to_f32<T>(gr[j]), pw, acc[0], acc[1], acc[2]) : rq_wt_fwd(a, pw));
+  }
+  if (BWD) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+      partials[3 * unit] = acc[0];
+      partials[3 * unit + 1] = acc[1];
+      partials[3 * unit + 2] = acc[2];
+    }
+  }
+}
+
+// one warp per tensor: fixed-order sum (double) of its units' partials, then the chain of base.py:137-139
+__global__ void __launch_bounds__(kRowWarps * 32)
+rootq_wt_grouped_finalize(const dlmcq_rootq_item* __restrict__ items, const int64_t* __restrict__ prefix, int n_items,
+                          const float* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (k >= n_items) return;
+  const dlmcq_rootq_item it = items[k];
+  const int64_t u0 = prefix[k], u1 = prefix[k + 1];
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int64_t u = u0 + lane; u < u1; u += 32) {
+    t[0] += partials[3 * u]; t[1] += partials[3 * u + 1]; t[2] += partials[3 * u + 2];
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) t[q] = warp_sum(t[q]);
+  if (lane == 0) {
+    const float g = it.state[RW_G], m = it.state[RW_M];
+    it.grads[0] = m * (g * static_cast<float>(t[0]));
+    it.grads[1] = m * (g * static_cast<float>(t[1]));
+    it.grads[2] = it.state[RW_AMASK] * static_cast<float>(t[2]);
+  }
+}
+
 // forward: one tile per CTA; backward: capped (every CTA leaves one partial sum per reduced quantity)
 static inline int rq_grid(int64_t n, int per_thread, int blocks_per_sm) {
   const int64_t tiles = (n / per_thread + kThreads * kRqUnroll - 1) / (kThreads * kRqUnroll);
@@ -443,4 +590,53 @@ extern "C" int dlmcq_rootq_act_backward(const void* x, const void* dy, void* dx,
 extern "C" int dlmcq_rootq_wt_backward(const void* w, const void* dy, void* dw, float* grads, int64_t numel, int dtype,
                                        const float* state, void* workspace, size_t workspace_bytes, void* stream) {
   return rootq_backward<true>(w, dy, dw, grads, numel, dtype, state, workspace, workspace_bytes, stream);
+}
+
+extern "C" int dlmcq_rootq_prepare_many(const dlmcq_rootq_prep* items, int n_items, void* stream) {
+  if (!items || n_items < 0) return DLMCQ_EINVAL;
+  if (n_items == 0) return DLMCQ_OK;
+  rootq_prepare_many_kernel<<<(n_items + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(items, n_items);
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_rootq_wt_forward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                              int64_t total_units, int dtype, void* stream) {
+  if (!items || !unit_prefix || n_items < 1 || total_units < 0) return DLMCQ_EINVAL;
+  if (total_units == 0) return DLMCQ_OK;
+  const int64_t blocks = (total_units + kRowWarps - 1) / kRowWarps;
+  if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLMCQ_F32)
+    rootq_wt_grouped_kernel<float, false><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, total_units, nullptr);
+  else if (dtype == DLMCQ_BF16)
+    rootq_wt_grouped_kernel<__nv_bfloat16, false><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, total_units, nullptr);
+  else
+    return DLMCQ_EINVAL;
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_rootq_wt_backward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                               int64_t total_units, int dtype, float* partials, void* stream) {
+  if (!items || !unit_prefix || !partials || n_items < 1 || total_units < 0) return DLMCQ_EINVAL;
+  if (total_units == 0) return DLMCQ_OK;
+  const int64_t blocks = (total_units + kRowWarps - 1) / kRowWarps;
+  if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DLMCQ_F32)
+    rootq_wt_grouped_kernel<float, true><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, total_units, partials);
+  else if (dtype == DLMCQ_BF16)
+    rootq_wt_grouped_kernel<__nv_bfloat16, true><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, total_units, partials);
+  else
+    return DLMCQ_EINVAL;
+  DLMCQ_LAUNCH_CHECK();
+  rootq_wt_grouped_finalize<<<(n_items + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(items, unit_prefix,
+                                                                                               n_items, partials);
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
 }

@@ -15,7 +15,7 @@ from ._lib import (BF16, F32, FORM_A1, FORM_AFFINE, FORM_SYM, FORM_ZP, ROOTQ_STA
 __all__ = ["fq_forward", "fq_backward", "dequantize", "obs_stats", "minmax_from_stats", "absmean_from_stats",
            "sweep_tensor", "sweep_channel", "kth_values", "l2norm_fixed_point", "adaround_forward", "adaround_backward",
            "adaround_init_alpha", "rootq_act_prepare", "rootq_act_forward", "rootq_act_backward", "rootq_wt_prepare",
-           "rootq_wt_forward", "rootq_wt_backward", "GroupedFakeQuant", "HostFakeQuant", "layout_of"]
+           "rootq_wt_forward", "rootq_wt_backward", "GroupedFakeQuant", "GroupedRootQ", "HostFakeQuant", "layout_of"]
 
 
 def _require_cuda(t, name="tensor"):
@@ -585,6 +585,82 @@ class GroupedFakeQuant:
                                                             _ptr(self._chan_prefix), len(entries), self._total_units,
                                                             self._total_channels, code, _ptr(self._partials),
                                                             _stream_ptr()))
+
+
+class GroupedRootQ:
+    """RootQ for a whole model with a constant number of launches: ONE launch prepares every quantizer's scalar
+    state (EMA of the running bounds, gradient mix, delta, clamped alpha - RootQ/base.py:92-101,131-147, running
+    buffers updated in place), ONE quantises all weight tensors, ONE (+ a finalisation) differentiates them.
+    Descriptor tables live on the device and are rebuilt only when pointers change."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._prep_key = self._prep_tab = self.states = None
+        self._wt = {False: [None, None, None, 0], True: [None, None, None, 0]}   # key, items, prefix, units
+        self._partials = None
+
+    def prepare(self, quantizers):
+        """quantizers: dicts with kind 'act' (in_scale, run_scale) or 'wt' (upper, lower, alpha, run_upper,
+        run_lower), plus momentum, g, lo, hi, training.  Returns the list of 8-float state views."""
+        key = tuple((q["kind"], *(q[k].data_ptr() for k in (("in_scale", "run_scale") if q["kind"] == "act" else
+                                                             ("upper", "lower", "alpha", "run_upper", "run_lower"))),
+                     q["momentum"], q["g"], q["lo"], q["hi"], bool(q["training"])) for q in quantizers)
+        if key != self._prep_key:
+            n = len(quantizers)
+            self.states = torch.zeros(n, ROOTQ_STATE_FLOATS, dtype=torch.float32, device=self.device)
+            arr = (_lib.RootqPrep * n)()
+            for i, q in enumerate(quantizers):
+                it = arr[i]
+                if q["kind"] == "act":
+                    it.param_a, it.run_a, it.is_weight = q["in_scale"].data_ptr(), q["run_scale"].data_ptr(), 0
+                else:
+                    it.param_a, it.param_b, it.alpha = q["upper"].data_ptr(), q["lower"].data_ptr(), q["alpha"].data_ptr()
+                    it.run_a, it.run_b, it.is_weight = q["run_upper"].data_ptr(), q["run_lower"].data_ptr(), 1
+                it.state = self.states[i].data_ptr()
+                it.momentum, it.g, it.lo, it.hi = float(q["momentum"]), float(q["g"]), int(q["lo"]), int(q["hi"])
+                it.training = int(bool(q["training"]))
+            self._prep_tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+            self._prep_key = key
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_rootq_prepare_many(_ptr(self._prep_tab), len(quantizers), _stream_ptr()))
+        return [self.states[i] for i in range(len(quantizers))]
+
+    def _table(self, entries, backward):
+        slot = self._wt[backward]
+        key = tuple((e["w"].data_ptr(), e["out"].data_ptr(), e["dy"].data_ptr() if backward else 0,
+                     e["state"].data_ptr(), e["grads"].data_ptr() if backward else 0, e["w"].numel()) for e in entries)
+        if key == slot[0]:
+            return slot
+        arr = (_lib.RootqItem * len(entries))()
+        units = [0]
+        for i, e in enumerate(entries):
+            it = arr[i]
+            it.x, it.y, it.state, it.numel = e["w"].data_ptr(), e["out"].data_ptr(), e["state"].data_ptr(), e["w"].numel()
+            it.dy = e["dy"].data_ptr() if backward else None
+            it.grads = e["grads"].data_ptr() if backward else None
+            units.append(units[-1] + (e["w"].numel() + _lib.ROOTQ_UNIT - 1) // _lib.ROOTQ_UNIT)
+        slot[0] = key
+        slot[1] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        slot[2] = torch.tensor(units, dtype=torch.int64).to(self.device)
+        slot[3] = units[-1]
+        if self._partials is None or self._partials.numel() < 3 * units[-1]:
+            self._partials = torch.empty(max(3 * units[-1], 1), dtype=torch.float32, device=self.device)
+        return slot
+
+    def wt_forward(self, entries, dtype=torch.float32):
+        """entries: dicts with w, out (receives w_q), state (contiguous tensors)."""
+        _, items, prefix, units = self._table(entries, False)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_rootq_wt_forward_grouped(_ptr(items), _ptr(prefix), len(entries), units,
+                                                                 F32 if dtype == torch.float32 else BF16, _stream_ptr()))
+
+    def wt_backward(self, entries, dtype=torch.float32):
+        """entries additionally carry dy and grads [3] (d wt_upper, d wt_lower, d wt_alpha); out receives dw."""
+        _, items, prefix, units = self._table(entries, True)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_rootq_wt_backward_grouped(_ptr(items), _ptr(prefix), len(entries), units,
+                                                                  F32 if dtype == torch.float32 else BF16,
+                                                                  _ptr(self._partials), _stream_ptr()))
 
 
 class HostFakeQuant:

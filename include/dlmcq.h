@@ -191,6 +191,36 @@ int dlmcq_rootq_wt_backward(const void* w, const void* dy, void* dw, float* grad
                             int64_t numel, int dtype, const float* state,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Grouped RootQ launches: the scalar prologues (RootQ/base.py:92-101,131-147) of ALL quantizers of a model
+ * in one launch, and all weight tensors quantised / differentiated in one launch each (the per-layer calls
+ * above cost 6 launches per layer per step).  Descriptor tables live in DEVICE memory.
+ *   prep: is_weight = 0: param_a = in_scale, run_a = in_run_scale (param_b, run_b, alpha unused);
+ *         is_weight = 1: param_a/b = wt_upper/wt_lower, run_a/b = wt_run_upper/wt_run_lower, alpha = wt_alpha.
+ *   item: x = w, y = w_q (forward) or dw (backward), dy = upstream gradient (backward), state = the prepared
+ *         block, grads[3] = d wt_upper, d wt_lower, d wt_alpha.
+ *   unit_prefix[k] = sum_{j<k} ceil(numel_j / DLMCQ_ROOTQ_UNIT), k = 0..n_items; partials: 3*total_units floats. */
+#define DLMCQ_ROOTQ_UNIT 2048
+typedef struct {
+  const float *param_a, *param_b, *alpha;
+  float *run_a, *run_b;
+  float* state;
+  double momentum, g;
+  int32_t lo, hi, training, is_weight;
+} dlmcq_rootq_prep;
+typedef struct {
+  const void* x;
+  void* y;
+  const void* dy;
+  const float* state;
+  float* grads;
+  int64_t numel;
+} dlmcq_rootq_item;
+int dlmcq_rootq_prepare_many(const dlmcq_rootq_prep* items, int n_items, void* stream);
+int dlmcq_rootq_wt_forward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                   int64_t total_units, int dtype, void* stream);
+int dlmcq_rootq_wt_backward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                    int64_t total_units, int dtype, float* partials, void* stream);
+
 /* ---- observers (dlmc/quantization/scalar/ops.py) --------------------------------------
  * Statistics pass: one read of the tensor -> stats[channels][4] = {min, max, max|x|, sum|x|}
  * (NaN-propagating like torch.min/max).  Multi-GPU callers all-reduce `stats` between this

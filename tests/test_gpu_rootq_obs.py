@@ -418,3 +418,51 @@ def test_percentile_observer_vs_oracle(signed, bits, pct):
     if pct == 100.0:                                                    # degenerates to the min/max observer
         ms, mo = ops.quantize_minmax_tensor(dev(t), bits, signed)
         assert torch.equal(ms, s) and torch.equal(mo.float(), o.float())
+
+
+def test_grouped_rootq_matches_per_layer_launches():
+    """One prepare launch for all quantizers and one forward / backward launch for all weight tensors give the
+    per-layer entry points' results: states, running buffers, w_q and dw bit for bit, reduced gradients to 1e-5."""
+    from dlmc_quant_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(51)
+    lo, hi, mom = 0, 15, 0.1
+    shapes = [(64, 3, 3, 3), (128, 64, 3, 3), (10, 512), (7,), (300, 33)]
+    layers = []
+    for shp in shapes:
+        w = (torch.randn(shp, generator=gen) * 0.05).cuda()
+        dy = torch.randn(shp, generator=gen).cuda()
+        up, dn = R.rootq_wt_init(w.cpu(), hi)
+        x = torch.relu(torch.randn(4, 8, 6, 6, generator=gen)).cuda()
+        in_scale = R.rootq_act_init(x.cpu(), lo, hi).cuda()
+        layers.append(dict(w=w, dy=dy, up=up.float().cuda(), dn=dn.float().cuda(), alpha=torch.tensor(0.3).cuda(),
+                           in_scale=in_scale, g_w=1 / math.sqrt(w.numel() * hi), g_i=1 / math.sqrt(x.numel() * hi)))
+    # per-layer reference path
+    ref = []
+    for L in layers:
+        rup, rdn, run = L["up"].clone() * 0.9, L["dn"].clone() * 1.1, L["in_scale"].clone() * 0.8
+        sa = Fn.rootq_act_prepare(L["in_scale"], run, mom, L["g_i"], lo, hi, True)
+        sw = Fn.rootq_wt_prepare(L["up"], L["dn"], L["alpha"], rup, rdn, mom, L["g_w"], lo, hi, True)
+        wq = Fn.rootq_wt_forward(L["w"], sw)
+        dw, gw = Fn.rootq_wt_backward(L["w"], L["dy"], sw)
+        ref.append(dict(sa=sa, sw=sw, wq=wq, dw=dw, gw=gw, rup=rup, rdn=rdn, run=run))
+    # grouped path
+    G = Fn.GroupedRootQ("cuda")
+    qs, bufs = [], []
+    for L in layers:
+        rup, rdn, run = L["up"].clone() * 0.9, L["dn"].clone() * 1.1, L["in_scale"].clone() * 0.8
+        bufs.append((rup, rdn, run))
+        qs.append(dict(kind="act", in_scale=L["in_scale"], run_scale=run, momentum=mom, g=L["g_i"], lo=lo, hi=hi, training=True))
+        qs.append(dict(kind="wt", upper=L["up"], lower=L["dn"], alpha=L["alpha"], run_upper=rup, run_lower=rdn,
+                       momentum=mom, g=L["g_w"], lo=lo, hi=hi, training=True))
+    states = G.prepare(qs)
+    ent = [dict(w=L["w"], out=torch.empty_like(L["w"]), state=states[2 * i + 1]) for i, L in enumerate(layers)]
+    G.wt_forward(ent)
+    bent = [dict(w=L["w"], dy=L["dy"], out=torch.empty_like(L["w"]), state=states[2 * i + 1],
+                 grads=torch.empty(3, device="cuda")) for i, L in enumerate(layers)]
+    G.wt_backward(bent)
+    for i, (L, r) in enumerate(zip(layers, ref)):
+        assert torch.equal(states[2 * i][:5], r["sa"][:5]) and torch.equal(states[2 * i + 1], r["sw"]), i
+        assert torch.equal(bufs[i][0], r["rup"]) and torch.equal(bufs[i][1], r["rdn"]) and torch.equal(bufs[i][2], r["run"])
+        assert bits_equal(ent[i]["out"].cpu(), r["wq"].cpu()), i
+        assert bits_equal(bent[i]["out"].cpu(), r["dw"].cpu()), i
+        assert torch.allclose(bent[i]["grads"], r["gw"], rtol=1e-5, atol=1e-6), (i, bent[i]["grads"], r["gw"])
