@@ -725,65 +725,30 @@ l2norm_rows_kernel(const T* __restrict__ x, RowGeom gm, const float* __restrict_
   if (lane == 0) { part[2 * item] = a; part[2 * item + 1] = b; }
 }
 
-// single CTA: new scale per channel, convergence measure, done flag (ops.py:79-81,207-210).
-// One warp per channel with the lanes striding over that channel's segments (per-tensor: the whole
-// CTA strides over the segments of the single channel).
+// Per-tensor (one channel): a single CTA strides over the segments, computes the new scale, the convergence
+// measure and the done flag (ops.py:79-81).
 __global__ void __launch_bounds__(kThreads)
 l2norm_finalize_kernel(const float* __restrict__ part, RowGeom gm, float* __restrict__ scale, float* __restrict__ diff,
                        int32_t* __restrict__ done, int32_t* __restrict__ iters) {
-  __shared__ double sh[4][kThreads / 32];
+  __shared__ double sh[2][kThreads / 32];
   if (*done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = kThreads / 32;
-  double num = 0.0, den = 0.0;
-  float single_new = 0.f, single_old = 0.f;
-  if (gm.channels == 1) {
-    double a = 0.0, b = 0.0;
-    for (int64_t sg = threadIdx.x; sg < gm.segs; sg += blockDim.x) {
-      a += part[2 * sg];
-      b += part[2 * sg + 1];
-    }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    if (lane == 0) { sh[2][warp] = a; sh[3][warp] = b; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double ta = 0.0, tb = 0.0;
-      for (int w = 0; w < NW; ++w) { ta += sh[2][w]; tb += sh[3][w]; }
-      single_old = scale[0];
-      single_new = static_cast<float>(ta) / static_cast<float>(tb);
-      scale[0] = single_new;
-    }
-  } else {
-    for (int64_t c = warp; c < gm.channels; c += NW) {
-      double a = 0.0, b = 0.0;
-      for (int64_t sg = lane; sg < gm.segs; sg += 32) {
-        a += part[2 * (c * gm.segs + sg)];
-        b += part[2 * (c * gm.segs + sg) + 1];
-      }
-      a = warp_sum(a);
-      b = warp_sum(b);
-      if (lane == 0) {
-        const float s_old = scale[c];
-        const float s_new = static_cast<float>(a) / static_cast<float>(b);
-        scale[c] = s_new;
-        const float d = s_new - s_old;
-        num += static_cast<double>(d * d);
-        den += static_cast<double>(s_old * s_old);
-      }
-    }
-    if (lane == 0) { sh[0][warp] = num; sh[1][warp] = den; }
-    __syncthreads();
+  double a = 0.0, b = 0.0;
+  for (int64_t sg = threadIdx.x; sg < gm.segs; sg += blockDim.x) {
+    a += part[2 * sg];
+    b += part[2 * sg + 1];
   }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    float df;
-    if (gm.channels == 1) {
-      df = fabsf(single_new - single_old) / single_old;                 // ops.py:80
-    } else {
-      double tn = 0.0, td = 0.0;
-      for (int w = 0; w < NW; ++w) { tn += sh[0][w]; td += sh[1][w]; }
-      df = sqrtf(static_cast<float>(tn)) / sqrtf(static_cast<float>(td));   // ops.py:209
-    }
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { ta += sh[0][w]; tb += sh[1][w]; }
+    const float s_old = scale[0];
+    const float s_new = static_cast<float>(ta) / static_cast<float>(tb);
+    scale[0] = s_new;
+    const float df = fabsf(s_new - s_old) / s_old;                      // ops.py:80
     diff[0] = df;
     if (iters) iters[0] += 1;
     if (!(df > 1e-5f)) done[0] = 1;                                     // `while diff > epsilon`

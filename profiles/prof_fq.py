@@ -35,3 +35,18 @@ for r in range(3):
     ev[0].record(); c.copy_(x); ev[1].record(); torch.cuda.synchronize()
     t = ev[0].elapsed_time(ev[1])
     print(f"copy_: {t*1e3:.1f} us = {8*n/t/1e6:.0f} GB/s")
+
+# the reference's eager op chain (oracle restatement of modules/base.py:96-102 + autograd) on the same GPU:
+# the "PyTorch eager on B200" comparator of SURVEY.md 8d.  Test infrastructure, not a product path.
+from oracle import restate as R  # noqa: E402
+xs, ss = x.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+for r in range(3):
+    ev[0].record()
+    ye = R.fq_affine(xs, ss, off, 0, 15, g)
+    ev[1].record()
+    ye.backward(dy)
+    ev[2].record()
+    torch.cuda.synchronize()
+    f, b = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    print(f"eager chain rep {r}: fwd {f*1e3:.1f} us = {8*n/f/1e6:.0f} GB/s | bwd {b*1e3:.1f} us = {12*n/b/1e6:.0f} GB/s (algorithmic bytes)")
+    xs.grad = ss.grad = None

@@ -1,3 +1,6 @@
+"""Scratch experiment kept for the record: back-to-back launches on ROTATING buffers (so that no input is L2-resident)
+for the flat forward / backward kernels at several sizes - the source of the "rotating buffers" figures quoted in the
+round-1 kernel history.   python profiles/tail_experiment.py"""
 import ctypes as C, math, os, sys, torch
 sys.path.insert(0, "/root/repo")
 from dlmc_quant_b200 import _lib, functional as F
