@@ -15,8 +15,9 @@ from torch import nn
 from .scalar import FSPTQuant as FSPQ
 from .scalar import RootQ as RQ
 from .scalar import modules as qnn
+from .scalar.modules.group import group_weight_quantizers  # noqa: F401  (step-level weight grouping)
 
-__all__ = ['quantize_model', 'get_layers', 'attrsetter']
+__all__ = ['quantize_model', 'get_layers', 'attrsetter', 'group_weight_quantizers']
 
 MODULE_MAPPING = {nn.Conv2d: qnn.QConv2d, nn.Linear: qnn.QLinear}
 ROOTQ_MAPPING = {nn.Conv2d: RQ.RootQConv2d, nn.Linear: RQ.RootQLinear}

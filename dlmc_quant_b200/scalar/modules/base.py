@@ -112,7 +112,10 @@ class QBase(Module):
             input = fake_quantize(input, self.in_scale, self.in_offset, self.in_min_val, self.in_max_val,
                                   FORM_AFFINE, g_i)                                      # base.py:97,102
         weight = self.weight
-        if q['weight']['enable']:
+        grouped = self.__dict__.pop('_wq', None)         # set by group_weight_quantizers' pre-hook for this step
+        if grouped is not None and q['weight']['enable']:
+            weight = grouped
+        elif q['weight']['enable']:
             if not self._ready('wt', self.wt_init_state):
                 if fnmatch(q['weight']['type'], '*output*'):
                     scale, offset = get_qparams_output(input.detach(), self.weight.detach(), self,

@@ -1,0 +1,186 @@
+"""Step-level grouping of the WEIGHT quantizers of a quantised model.
+
+`QBase.forward` fake-quantises its weight per layer (modules/base.py:131-133): for ResNet-50 that is 54 small
+forward launches and 54 x 2 backward launches per training step, all launch-latency-bound, plus ~45 us of host
+work per call.  `group_weight_quantizers(model)` installs a forward pre-hook that quantises ALL (initialised)
+weight tensors with ONE `dlmcq_fq_forward_grouped` launch before the model's forward, through ONE autograd node
+whose backward is ONE `dlmcq_fq_backward_grouped` launch; each module then finds its quantised weight ready.
+Same arithmetic as the per-layer path (same row kernels): w_q and dw bit-identical, scale gradients equal up to
+summation order.  Modules whose weight quantizer is disabled, not yet initialised (first forward: the lazy
+observer init runs per layer as usual) or not per-tensor / per-output-channel stay on the per-layer path."""
+import ctypes as C
+import math
+
+import torch
+
+from ... import _lib
+from ... import functional as F
+from ..._lib import FORM_AFFINE
+from .base import QBase
+
+__all__ = ["WeightQuantGroup", "GroupHandle", "group_weight_quantizers"]
+
+
+class _GroupedWeightFakeQuant(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, group, n, *tensors):
+        ctx.group, ctx.n = group, n
+        ctx.save_for_backward(*tensors)
+        return tuple(group._forward(tensors[:n], tensors[n:]))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        t = ctx.saved_tensors
+        dws, dss = ctx.group._backward(t[:ctx.n], t[ctx.n:], grads)
+        return (None, None, *dws, *dss)
+
+
+class WeightQuantGroup:
+    def __init__(self, model):
+        self.model = model
+        self._key = None
+        self._mods = []
+        self._candidates = None
+
+    # -- membership ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _eligible(m):
+        if not isinstance(m, QBase) or not m.qconfig['weight']['enable']:
+            return False
+        if not (getattr(m, '_host_init', None) or {}).get('wt'):
+            return False                                       # lazy observer init still pending
+        w, s = m.weight, m.wt_scale
+        if not w.is_cuda or w.dtype not in (torch.float32, torch.bfloat16) or m.wt_offset is None:
+            return False
+        per_channel = s.numel() == w.shape[0] and s.numel() > 1 and tuple(s.shape[1:]) == (1,) * (w.dim() - 1)
+        return (s.numel() == 1 or per_channel) and F.dense_as_is(w, 0)
+
+    def _refresh(self):
+        if self._candidates is None:
+            self._candidates = [m for m in self.model.modules() if isinstance(m, QBase)]
+        if len(self._mods) < len(self._candidates):             # some layers were not initialised yet: look again
+            mods = [m for m in self._candidates if self._eligible(m)]
+        else:
+            mods = self._mods
+        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(), m.weight.stride())
+                    for m in mods)
+        if key == self._key:
+            return
+        self._key, self._mods = key, mods
+        if not mods:
+            return
+        dev = mods[0].weight.device
+        self.device, self.dtype = dev, mods[0].weight.dtype
+        n = len(mods)
+        self._arr = (_lib.GroupItem * n)()
+        self._offsets = []                                      # float32 [channels] copies of the offset buffers
+        units, chans, elems = [0], [0], [0]
+        for i, m in enumerate(mods):
+            w, s = m.weight, m.wt_scale
+            c = s.numel()
+            off = m.wt_offset.detach().to(device=dev, dtype=torch.float32).reshape(-1)
+            off = (off.expand(c) if off.numel() == 1 else off).contiguous()
+            self._offsets.append(off)
+            it = self._arr[i]
+            it.x, it.scale, it.offset = w.data_ptr(), s.data_ptr(), off.data_ptr()
+            it.channels, it.inner = c, w.numel() // c
+            it.form, it.lo, it.hi = FORM_AFFINE, int(m.wt_min_val), int(m.wt_max_val)
+            it.g = 1 / math.sqrt(w.numel() * m.wt_max_val)                      # base.py:131
+            units.append(units[-1] + c * ((it.inner + F.GROUP_SEG - 1) // F.GROUP_SEG))
+            chans.append(chans[-1] + c)
+            elems.append(elems[-1] + w.numel())
+        self._units, self._chans, self._elems = units, chans, elems
+        self._unit_prefix = torch.tensor(units, dtype=torch.int64).to(dev)
+        self._chan_prefix = torch.tensor(chans, dtype=torch.int64).to(dev)
+        self._partials = torch.empty(max(units[-1], 1), dtype=torch.float32, device=dev)
+        self._es = mods[0].weight.element_size()
+        # descriptor upload without a stream synchronisation: a ring of pinned staging buffers (a blocking
+        # .to(device) from pageable memory would drain the GPU twice per step)
+        nbytes = C.sizeof(self._arr)
+        self._ring = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
+        self._ring_ev = [None] * 4
+        self._ring_i = 0
+        self._table = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def _upload(self):
+        k = self._ring_i
+        self._ring_i = (k + 1) % len(self._ring)
+        if self._ring_ev[k] is None:
+            self._ring_ev[k] = torch.cuda.Event()
+        else:
+            self._ring_ev[k].synchronize()                      # four uploads ago: long complete
+        pin = self._ring[k]
+        C.memmove(pin.data_ptr(), C.addressof(self._arr), pin.numel())
+        self._table.copy_(pin, non_blocking=True)               # stream-ordered before the launch that reads it
+        self._ring_ev[k].record()
+        return self._table
+
+    def _like(self, flat, i, w):
+        return torch.as_strided(flat, w.shape, w.stride(), storage_offset=self._elems[i])
+
+    # -- the two launches -----------------------------------------------------------------------------------
+    def _forward(self, weights, scales):
+        flat = torch.empty(self._elems[-1], dtype=self.dtype, device=self.device)
+        base = flat.data_ptr()
+        for i in range(len(weights)):
+            self._arr[i].y = base + self._elems[i] * self._es
+            self._arr[i].dy = None
+            self._arr[i].dscale = None
+        items = self._upload()
+        with F._on(self.device):
+            _lib.check(_lib.lib().dlmcq_fq_forward_grouped(items.data_ptr(), self._unit_prefix.data_ptr(), len(weights),
+                                                           self._units[-1], F._dtype_code(flat), F._stream_ptr()))
+        return [self._like(flat, i, w) for i, w in enumerate(weights)]
+
+    def _backward(self, weights, scales, grads):
+        flat = torch.empty(self._elems[-1], dtype=self.dtype, device=self.device)
+        ds = torch.empty(self._chans[-1], dtype=torch.float32, device=self.device)
+        base, dsb = flat.data_ptr(), ds.data_ptr()
+        keep = []
+        for i, w in enumerate(weights):
+            g = grads[i]
+            if g is None:
+                g = torch.zeros_like(w)
+            elif g.stride() != w.stride() or g.dtype != w.dtype:
+                g = torch.empty_like(w).copy_(g)                # same element order as the weight
+            keep.append(g)
+            it = self._arr[i]
+            it.dy, it.y, it.dscale = g.data_ptr(), base + self._elems[i] * self._es, dsb + 4 * self._chans[i]
+        items = self._upload()
+        with F._on(self.device):
+            _lib.check(_lib.lib().dlmcq_fq_backward_grouped(items.data_ptr(), self._unit_prefix.data_ptr(),
+                                                            self._chan_prefix.data_ptr(), len(weights), self._units[-1],
+                                                            self._chans[-1], F._dtype_code(flat),
+                                                            self._partials.data_ptr(), F._stream_ptr()))
+        dws = [self._like(flat, i, w) for i, w in enumerate(weights)]
+        dss = [ds[self._chans[i]:self._chans[i + 1]].reshape(s.shape).to(s.dtype) for i, s in enumerate(scales)]
+        return dws, dss
+
+    # -- hook --------------------------------------------------------------------------------------------------
+    def __call__(self, module=None, args=None):
+        self._refresh()
+        if not self._mods:
+            return None
+        n = len(self._mods)
+        outs = _GroupedWeightFakeQuant.apply(self, n, *[m.weight for m in self._mods], *[m.wt_scale for m in self._mods])
+        for m, o in zip(self._mods, outs):
+            m.__dict__['_wq'] = o                                # consumed (popped) by QBase.forward
+        return None
+
+
+class GroupHandle:
+    """Returned by group_weight_quantizers: remove() restores the per-layer behaviour."""
+
+    def __init__(self, group, hook):
+        self.group, self._hook = group, hook
+
+    def remove(self):
+        self._hook.remove()
+        for m in self.group.model.modules():
+            m.__dict__.pop('_wq', None)
+
+
+def group_weight_quantizers(model):
+    """Quantise all weight tensors of `model`'s QBase layers in one launch per direction (see module docstring)."""
+    group = WeightQuantGroup(model)
+    return GroupHandle(group, model.register_forward_pre_hook(group))

@@ -91,6 +91,9 @@ def run(arm, args, device, world):
     model.train()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
         model(x[:8])            # lazy observer init before DDP wraps the parameters (shapes may change)
+    if arm.startswith("ours") and not args.per_layer_weights:
+        from dlmc_quant_b200.quantize import group_weight_quantizers
+        group_weight_quantizers(model)      # all 54 weight tensors: one launch per direction instead of 54 x 3
     if world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True)
@@ -125,6 +128,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--arm", default="all")
+    ap.add_argument("--per-layer-weights", action="store_true", help="ours: no step-level weight grouping")
     ap.add_argument("--channels-last", action="store_true",
                     help="model and input in channels_last memory format (all arms); the fake-quant kernels index "
                          "dense channels_last tensors directly")

@@ -412,3 +412,56 @@ def test_channels_last_tensors_pass_through_without_copy():
     s1 = (x.amax(dim=(0, 2, 3)) / 15 + 1e-3).reshape(1, -1, 1, 1)
     o1 = torch.zeros_like(s1)
     assert torch.equal(F.fq_forward(x, s1, o1, 0, 15, 1, ch_axis=1), F.fq_forward(xc, s1, o1, 0, 15, 1, ch_axis=1))
+
+
+def test_grouped_weight_quantizers_match_per_layer_path():
+    """group_weight_quantizers: one launch per direction for all weight tensors; outputs, weight gradients
+    bit-identical to the per-layer modules, scale gradients equal up to summation order; channels_last too."""
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.quantize import group_weight_quantizers
+    cfg = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 4, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1 = torch.nn.Conv2d(3, 16, 3, padding=1)
+            self.c2 = torch.nn.Conv2d(16, 32, 3, padding=1, groups=2, bias=False)
+            self.fc = torch.nn.Linear(32, 10)
+
+        def forward(self, x):
+            x = torch.relu(self.c2(torch.relu(self.c1(x))))
+            return self.fc(x.mean(dim=(2, 3)))
+
+    for channels_last in (False, True):
+        torch.manual_seed(2333)
+        a = Net().cuda()
+        if channels_last:
+            a = a.to(memory_format=torch.channels_last)
+        b = copy.deepcopy(a)
+        quantize_model(a, copy.deepcopy(cfg), None)
+        quantize_model(b, copy.deepcopy(cfg), None)
+        x = torch.rand(4, 3, 12, 12, device="cuda")
+        if channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            a(x), b(x)                                   # lazy observer init, per layer in both
+        handle = group_weight_quantizers(b)
+        for step in range(2):
+            ya, yb = a(x), b(x)
+            assert torch.equal(ya, yb), (channels_last, step)
+            for m in (a, b):
+                m.zero_grad(set_to_none=True)
+            ya.square().sum().backward()
+            yb.square().sum().backward()
+            for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+                assert na == nb and pa.grad is not None and pb.grad is not None, na
+                if na.endswith("scale"):
+                    assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-6), (na, pa.grad, pb.grad)
+                else:       # cuDNN's weight-gradient algorithms are not bit-reproducible between two models
+                    assert torch.equal(pa.grad == 0, pb.grad == 0), na
+                    assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-7), na
+        assert len(handle.group._mods) == 3
+        handle.remove()
+        assert torch.equal(a(x), b(x)) and all('_wq' not in m.__dict__ for m in b.modules())
