@@ -466,3 +466,53 @@ def test_grouped_rootq_matches_per_layer_launches():
         assert bits_equal(ent[i]["out"].cpu(), r["wq"].cpu()), i
         assert bits_equal(bent[i]["out"].cpu(), r["dw"].cpu()), i
         assert torch.allclose(bent[i]["grads"], r["gw"], rtol=1e-5, atol=1e-6), (i, bent[i]["grads"], r["gw"])
+
+
+# --------------------------------------------------------------------------------------
+# full-size (2^26 elements), size-independent properties of the observers and of RootQ
+def test_full_size_observer_and_rootq_properties():
+    from dlmc_quant_b200 import functional as Fn
+    n = 1 << 26
+    torch.manual_seed(2333)
+    x = torch.relu(torch.randn(n, device="cuda")) * 2
+    half = n // 2
+    # statistics of a concatenation = merge of the parts' statistics
+    st, s0, s1 = Fn.obs_stats(x), Fn.obs_stats(x[:half]), Fn.obs_stats(x[half:])
+    assert st[0, 0] == torch.minimum(s0[0, 0], s1[0, 0]) and st[0, 1] == torch.maximum(s0[0, 1], s1[0, 1])
+    assert abs(float(st[0, 3]) - float(s0[0, 3]) - float(s1[0, 3])) <= 1e-5 * float(st[0, 3])
+    # the 80 sweep sums are additive over a split of the tensor (same candidates: the whole tensor's statistics)
+    sse = Fn.sweep_tensor_sse(x, st, 8).double()
+    parts = Fn.sweep_tensor_sse(x[:half], st, 8).double() + Fn.sweep_tensor_sse(x[half:], st, 8).double()
+    assert torch.allclose(sse, parts, rtol=2e-5)
+    # ... and equal to the eager evaluation of one candidate on the GPU (ops.py:53-61), candidate 17
+    r = torch.tensor(1.0 - 0.01 * 17, dtype=torch.float32, device="cuda")
+    c_hi, c_lo = r * st[0, 1], r * st[0, 0]
+    sc = (c_hi - c_lo) / 255
+    zp = torch.round(-c_lo / sc)
+    xq = ((torch.round(x / sc) + zp).clamp(0, 255) - zp) * sc
+    want = float(((xq - x) ** 2).double().sum())
+    assert abs(float(sse[17]) - want) <= 2e-5 * want
+    # exact order statistics against a full sort
+    ranks = [n // 1000, n - n // 1000]
+    srt = torch.sort(x).values
+    assert torch.equal(Fn.kth_values(x, ranks), torch.stack([srt[k - 1] for k in ranks]))
+    del srt, xq
+    # RootQ: the quantised weights lie on the 16-level grid {L + j*delta} - plus the 15 interval midpoints, which
+    # the reference produces for inputs exactly on a midpoint (sgn(0) = 0, RootQ/function.py:58-67; a handful of
+    # the 6.7e7 samples) - and re-quantising changes nothing
+    w = torch.randn(n, device="cuda") * 0.05
+    up, lo_b = torch.tensor(0.12, device="cuda"), torch.tensor(-0.11, device="cuda")
+    state = Fn.rootq_wt_prepare(up, lo_b, torch.tensor(0.3, device="cuda"), up.clone(), lo_b.clone(), 0.1,
+                                1 / math.sqrt(n * 15), 0, 15, False)
+    wq = Fn.rootq_wt_forward(w, state)
+    assert torch.unique(wq).numel() <= 31
+    assert torch.equal(Fn.rootq_wt_forward(wq, state), wq)
+    # RootQ activations: idempotent, bounded by [0, run_scale * 15], backward linear in dy
+    sa = Fn.rootq_act_prepare(torch.tensor(0.5, device="cuda"), torch.tensor(0.5, device="cuda"), 0.1,
+                              1 / math.sqrt(n * 15), 0, 15, False)
+    y = Fn.rootq_act_forward(x, sa)
+    assert torch.equal(Fn.rootq_act_forward(y, sa), y) and float(y.min()) >= 0 and float(y.max()) <= 7.5 + 1e-6
+    dy = torch.randn(n, device="cuda")
+    dx1, g1 = Fn.rootq_act_backward(x, dy, sa)
+    dx2, g2 = Fn.rootq_act_backward(x, dy * 2, sa)
+    assert torch.equal(dx2, dx1 * 2) and abs(float(g2) - 2 * float(g1)) <= 1e-5 * abs(float(g2)) + 1e-7
