@@ -104,7 +104,9 @@ def rows_sharded(rows2d, fn, group=None, min_rows_per_rank=2048):
         pad = torch.zeros(per, dtype=mine[k].dtype, device=rows2d.device)
         pad[:stop - start] = mine[k].reshape(-1)
         gathered = torch.empty(per * w, dtype=pad.dtype, device=rows2d.device)
-        dist.all_gather_into_tensor(gathered, pad, group=group) if rows2d.is_cuda else \
+        if rows2d.is_cuda:
+            dist.all_gather_into_tensor(gathered, pad, group=group)
+        else:                               # gloo (CPU tests) has no all_gather_into_tensor
             dist.all_gather(list(gathered.split(per)), pad, group=group)
         out.append(gathered[:channels])
     return tuple(out)
