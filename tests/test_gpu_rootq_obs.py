@@ -516,3 +516,58 @@ def test_full_size_observer_and_rootq_properties():
     dx1, g1 = Fn.rootq_act_backward(x, dy, sa)
     dx2, g2 = Fn.rootq_act_backward(x, dy * 2, sa)
     assert torch.equal(dx2, dx1 * 2) and abs(float(g2) - 2 * float(g1)) <= 1e-5 * abs(float(g2)) + 1e-7
+
+
+# --------------------------------------------------------------------------------------
+# bf16 tensors (API extension, SURVEY.md A.8 vi): reference(x.float()) rounded once to bf16; reductions in fp32
+def test_bf16_rootq_and_observers():
+    from dlmc_quant_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(61)
+    bf = torch.bfloat16
+    x = (torch.relu(torch.randn(8, 32, 16, 16, generator=gen)) * 1.3).to(bf)
+    w = (torch.randn(64, 96, 3, 3, generator=gen) * 0.03).to(bf)
+    dyx, dyw = torch.randn(x.shape, generator=gen).to(bf), torch.randn(w.shape, generator=gen).to(bf)
+    lo, hi, mom = 0, 15, 0.1
+    in_scale = R.rootq_act_init(x.float(), lo, hi) * 0.9
+    run_scale = in_scale * 1.05
+    up, dn = R.rootq_wt_init(w.float(), hi)
+    up, dn = (up * 0.8).float(), (dn * 1.1).float()
+    a = torch.tensor(0.4)
+    # activations
+    y_ref, _, dx_ref, ds_ref = R.rootq_act_fwd_bwd(x.float(), in_scale, run_scale, mom, lo, hi, dyx.float())
+    g_i = 1 / math.sqrt(x.numel() * hi)
+    st = Fn.rootq_act_prepare(_scalar(in_scale), _scalar(run_scale), mom, g_i, lo, hi, True)
+    y = Fn.rootq_act_forward(dev(x), st)
+    assert y.dtype == bf and bits_equal(y.float().cpu(), y_ref.to(bf).float())
+    dx, ds = Fn.rootq_act_backward(dev(x), dev(dyx), st)
+    assert dx.dtype == bf and bits_equal(dx.float().cpu(), dx_ref.to(bf).float())
+    red_close(ds, ds_ref, abs_sum=(dyx.float().abs().sum() * hi * mom * g_i).reshape(1))
+    # weights
+    yw_ref, _, _, dw_ref, du, dl, da = R.rootq_wt_fwd_bwd(w.float(), up, dn, a, up * 1.02, dn * 0.97, mom, lo, hi, dyw.float())
+    g_w = 1 / math.sqrt(w.numel() * hi)
+    sw = Fn.rootq_wt_prepare(_scalar(up), _scalar(dn), _scalar(a), _scalar(up * 1.02), _scalar(dn * 0.97), mom, g_w,
+                             lo, hi, True)
+    yw = Fn.rootq_wt_forward(dev(w), sw)
+    assert yw.dtype == bf and bits_equal(yw.float().cpu(), yw_ref.to(bf).float())
+    dw, gr = Fn.rootq_wt_backward(dev(w), dev(dyw), sw)
+    assert torch.allclose(dw.float().cpu(), dw_ref, rtol=2 ** -7, atol=1e-6)      # one bf16 rounding of the result
+    floor = (dyw.float().abs().sum() * hi * mom * g_w).reshape(1)
+    red_close(gr[0], du, abs_sum=floor)
+    red_close(gr[1], dl, abs_sum=floor)
+    # observers on bf16 data == observers on the up-converted data
+    t = (torch.relu(torch.randn(6, 24, 14, 14, generator=gen)) * 2).to(bf)
+    for ch_axis in (None, 1):
+        sb = Fn.obs_stats(dev(t), ch_axis=ch_axis).cpu()
+        sf = Fn.obs_stats(dev(t.float()), ch_axis=ch_axis).cpu()
+        assert torch.equal(sb[:, :3], sf[:, :3]) and torch.allclose(sb[:, 3], sf[:, 3], rtol=1e-6)
+    s, o, picked = Fn.sweep_tensor(dev(t), 8)
+    rs, ro, rp = R.obs_l2loss_tensor(t.float(), 8, False, return_index=True)
+    assert abs(int(picked) - rp) <= 1
+    if int(picked) == rp:
+        exact(s, rs.reshape(1), "scale")
+    rows = t.reshape(6, -1)
+    st4 = Fn.obs_stats(dev(rows), ch_axis=0)
+    s0, o0 = Fn.minmax_from_stats(st4, 4, False)
+    sb, itb, doneb = Fn.l2norm_fixed_point(dev(rows), s0, o0, 0, 15, max_iters=200)
+    sf, itf, donef = Fn.l2norm_fixed_point(dev(rows.float()), s0, o0, 0, 15, max_iters=200)
+    assert doneb == donef and torch.allclose(sb, sf, rtol=1e-5)
