@@ -205,10 +205,15 @@ constexpr int kCmajUnroll = 8;
 constexpr int64_t kCmajMaxInner = 256;
 
 // short rows, more than one batch index, and 32-bit element offsets inside one work item
+int64_t cmaj_max_inner();   // kCmajMaxInner unless overridden by DLMCQ_CMAJ_MAX_INNER (tuning aid)
 inline bool cmaj_ok(int64_t outer, int64_t channels, int64_t inner) {
-  return outer > 1 && inner >= 1 && inner < kCmajMaxInner && channels * 8192 < (int64_t(1) << 31);
+  return outer > 1 && inner >= 1 && inner < cmaj_max_inner() && channels * 8192 < (int64_t(1) << 31);
 }
-inline CmajGeom make_cmaj(int64_t outer, int64_t channels, int64_t inner) {
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// vec: elements per access unit (1, or the 128-bit vector width when rows are whole vectors): the kernels index
+// units, so `magic` divides by inner / vec
+inline CmajGeom make_cmaj(int64_t outer, int64_t channels, int64_t inner, int vec = 1) {
   CmajGeom g;
   g.outer = outer; g.channels = channels; g.inner = inner;
   int64_t bc = 8192 / (inner > 0 ? inner : 1);
@@ -216,8 +221,14 @@ inline CmajGeom make_cmaj(int64_t outer, int64_t channels, int64_t inner) {
   if (bc > outer) bc = outer;
   g.bc = static_cast<int32_t>(bc);
   g.chunks = static_cast<int32_t>((outer + bc - 1) / bc);
-  g.magic = static_cast<uint32_t>((1u << 24) / static_cast<uint32_t>(inner > 0 ? inner : 1)) + 1u;
+  const uint32_t units = static_cast<uint32_t>(inner > 0 ? inner / vec : 1);
+  g.magic = static_cast<uint32_t>((1u << 24) / (units > 0 ? units : 1)) + 1u;
   return g;
+}
+// rows are whole 128-bit vectors and every row start is 16-byte aligned
+template <typename T>
+inline bool cmaj_vec_ok(int64_t inner, const void* a, const void* b, const void* c, const void* d) {
+  return inner % Vec<T>::N == 0 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d);
 }
 
 // Programmatic dependent launch: consecutive kernels of one stream (the per-layer quantizer launches of a
@@ -243,7 +254,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Persistent grid for a streaming kernel over `work_items` block-tiles.
 inline int stream_grid(int64_t tiles, int blocks_per_sm) {

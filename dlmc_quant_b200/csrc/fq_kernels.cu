@@ -202,7 +202,7 @@ fq_bwd_flat(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
 // row kernels (per-channel qparams): one warp per row segment
 // ---------------------------------------------------------------------------------------
 template <int FORM, typename T>
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, 3)
 fq_fwd_rows(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, RowGeom gm,
             const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
   const int lane = threadIdx.x & 31;
@@ -213,7 +213,7 @@ fq_fwd_rows(const T* __restrict__ x, T* __restrict__ y, T* __restrict__ codes, R
   const int64_t beg = seg * gm.seg;
   const int64_t len = (gm.inner - beg) < gm.seg ? (gm.inner - beg) : gm.seg;
   const int64_t base = row * gm.inner + beg;
-  fwd_row_segment<FORM, T>(x + base, y ? y + base : nullptr, codes ? codes + base : nullptr, len, p, lo, hi, lane);
+  fwd_row_segment<FORM, T, 8>(x + base, y ? y + base : nullptr, codes ? codes + base : nullptr, len, p, lo, hi, lane);
 }
 
 // Backward rows: writes dx; per-(row,segment) partials go to `part` (2 floats each) unless the
@@ -252,11 +252,17 @@ fq_bwd_rows(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ d
 // warp-per-row kernel idle and pay the per-row setup 1.4 M times), and the per-channel scale gradient
 // stays in registers across the whole chunk.
 // ---------------------------------------------------------------------------------------
-template <int FORM, typename T, bool BWD>
+// VEC = 1: scalar accesses (rows of any length / alignment).  VEC = Vec<T>::N: rows are whole, aligned 128-bit
+// vectors (14x14, 8x8, 12x12 ... planes): the flattened index runs over vectors, so the index arithmetic is paid
+// once per 4 (fp32) / 8 (bf16) elements and the accesses are 128-bit.
+template <int FORM, typename T, bool BWD, int VEC>
 __global__ void __launch_bounds__(kRowWarps * 32, 4)
 fq_cmaj_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, T* __restrict__ codes,
                CmajGeom gm, const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo,
                float hi, float* __restrict__ dscale, float* __restrict__ part, int direct) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  constexpr int U = VEC == 1 ? kCmajUnroll : 4;
   const int lane = threadIdx.x & 31;
   const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (item >= gm.channels * gm.chunks) return;
@@ -265,43 +271,75 @@ fq_cmaj_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict_
   const int64_t j = item / gm.channels, c = item - j * gm.channels;
   const int64_t b0 = j * gm.bc;
   const int64_t nb = (gm.outer - b0) < gm.bc ? (gm.outer - b0) : gm.bc;
-  const uint32_t total = static_cast<uint32_t>(nb * gm.inner);
-  const uint32_t inner = static_cast<uint32_t>(gm.inner);
+  const uint32_t inner = static_cast<uint32_t>(gm.inner) / VEC;          // units per row
+  const uint32_t total = static_cast<uint32_t>(nb) * inner;
   const ChanParams p = make_params<FORM>(scale, offset, c, g, lo, hi);
-  const uint32_t plane = static_cast<uint32_t>(gm.channels * gm.inner);   // bc * plane < 2^31 (make_cmaj)
+  const uint32_t plane = static_cast<uint32_t>(gm.channels * gm.inner) / VEC;   // bc * plane < 2^31 (cmaj_ok)
   const int64_t base = (b0 * gm.channels + c) * gm.inner;
   const T* xb = x + base;
   const T* gb = BWD ? dy + base : nullptr;
   T* ob = out ? out + base : nullptr;
   T* cb = codes ? codes + base : nullptr;
   float as = 0.f, ao = 0.f;
-  for (uint32_t t0 = 0; t0 < total; t0 += 32 * kCmajUnroll) {
-    float v[kCmajUnroll], gq[kCmajUnroll];
-    uint32_t off[kCmajUnroll];
-    bool ok[kCmajUnroll];
+  for (uint32_t t0 = 0; t0 < total; t0 += 32 * U) {
+    uint32_t off[U];
+    bool ok[U];
 #pragma unroll
-    for (int u = 0; u < kCmajUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const uint32_t t = t0 + u * 32 + lane;
       ok[u] = t < total;
       const uint32_t bl = static_cast<uint32_t>((static_cast<uint64_t>(t) * gm.magic) >> 24);
       off[u] = bl * plane + (t - bl * inner);
-      v[u] = ok[u] ? to_f32<T>(xb[off[u]]) : 0.f;
-      if (BWD) gq[u] = ok[u] ? to_f32<T>(gb[off[u]]) : 0.f;
     }
-    if (BWD) {
-      float d[kCmajUnroll];
-      fq_vec_bwd<FORM, false, kCmajUnroll>(v, gq, p, lo, hi, d, as, ao);
+    if constexpr (VEC == 1) {
+      float v[U], gq[U];
 #pragma unroll
-      for (int u = 0; u < kCmajUnroll; ++u)
-        if (ok[u]) ob[off[u]] = from_f32<T>(d[u]);
+      for (int u = 0; u < U; ++u) {
+        v[u] = ok[u] ? to_f32<T>(xb[off[u]]) : 0.f;
+        if (BWD) gq[u] = ok[u] ? to_f32<T>(gb[off[u]]) : 0.f;
+      }
+      if (BWD) {
+        float d[U];
+        fq_vec_bwd<FORM, false, U>(v, gq, p, lo, hi, d, as, ao);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (ok[u]) ob[off[u]] = from_f32<T>(d[u]);
+      } else {
+        float cd[U], y[U];
+        fq_vec<FORM, U>(v, p, lo, hi, cd, y);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ok[u]) {
+            if (ob) ob[off[u]] = from_f32<T>(y[u]);
+            if (cb) cb[off[u]] = from_f32<T>(cd[u]);
+          }
+        }
+      }
     } else {
-      float cd[kCmajUnroll], y[kCmajUnroll];
-      fq_vec<FORM, kCmajUnroll>(v, p, lo, hi, cd, y);
+      const raw* xv = reinterpret_cast<const raw*>(xb);
+      const raw* gv = reinterpret_cast<const raw*>(gb);
+      raw rx[U], rg[U];
 #pragma unroll
-      for (int u = 0; u < kCmajUnroll; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (ok[u]) {
-          if (ob) ob[off[u]] = from_f32<T>(y[u]);
-          if (cb) cb[off[u]] = from_f32<T>(cd[u]);
+          rx[u] = ld_stream(xv + off[u]);
+          if (BWD) rg[u] = ld_stream(gv + off[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float f[V::N], o1[V::N], o2[V::N];
+        V::unpack(rx[u], f);
+        if (BWD) {
+          float fg[V::N];
+          V::unpack(rg[u], fg);
+          fq_vec_bwd<FORM, false, V::N>(f, fg, p, lo, hi, o1, as, ao);
+          st_stream(reinterpret_cast<raw*>(ob) + off[u], V::pack(o1));
+        } else {
+          fq_vec<FORM, V::N>(f, p, lo, hi, o2, o1);
+          if (ob) st_stream(reinterpret_cast<raw*>(ob) + off[u], V::pack(o1));
+          if (cb) st_stream(reinterpret_cast<raw*>(cb) + off[u], V::pack(o2));
         }
       }
     }
@@ -395,10 +433,12 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
           static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale, qp->offset, qp->g, lo, hi);
     }
   } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
-    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner);
+    const bool vec = cmaj_vec_ok<T>(l->inner, x, y, codes, nullptr);
+    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);
     const int64_t blocks = (cg.channels * cg.chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
-    fq_cmaj_kernel<FORM, T, false><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+    auto kern = vec ? fq_cmaj_kernel<FORM, T, false, Vec<T>::N> : fq_cmaj_kernel<FORM, T, false, 1>;
+    kern<<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
         static_cast<const T*>(x), nullptr, static_cast<T*>(y), static_cast<T*>(codes), cg, qp->scale, qp->offset,
         qp->g, lo, hi, nullptr, nullptr, 0);
   } else {
@@ -436,11 +476,13 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
                                dscale, doffset, ws);
     if (e != cudaSuccess) return set_cuda_error(e);
   } else if (cmaj_ok(l->outer, l->channels, l->inner) && doffset == nullptr && n > 0) {
-    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner);
+    const bool vec = cmaj_vec_ok<T>(l->inner, x, dy, dx, nullptr);
+    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);
     const int64_t blocks = (cg.channels * cg.chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
     const int direct = cg.chunks == 1 ? 1 : 0;
-    fq_cmaj_kernel<FORM, T, true><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+    auto kern = vec ? fq_cmaj_kernel<FORM, T, true, Vec<T>::N> : fq_cmaj_kernel<FORM, T, true, 1>;
+    kern<<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
         static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), nullptr, cg, qp->scale, qp->offset,
         qp->g, lo, hi, dscale, ws_partials(ws), direct);
     if (!direct) {

@@ -184,35 +184,55 @@ stats_rows_kernel(const T* __restrict__ x, RowGeom gm, float* __restrict__ stats
 
 // channel-major statistics for per-channel activations with short rows (see fq_cmaj_kernel): one warp per
 // (channel, batch chunk) walks the flattened (b, e) index space; partial [channel][chunk].
-template <typename T, bool ABS>
+template <typename T, bool ABS, int VEC>
 __global__ void __launch_bounds__(kRowWarps * 32)
 stats_cmaj_kernel(const T* __restrict__ x, CmajGeom gm, Stat4* __restrict__ part) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
   const int lane = threadIdx.x & 31;
   const int64_t item = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (item >= gm.channels * gm.chunks) return;
   const int64_t jc = item / gm.channels, c = item - jc * gm.channels;   // adjacent warps: adjacent channels
   const int64_t b0 = jc * gm.bc;
   const int64_t nb = (gm.outer - b0) < gm.bc ? (gm.outer - b0) : gm.bc;
-  const uint32_t total = static_cast<uint32_t>(nb * gm.inner);
-  const uint32_t inner = static_cast<uint32_t>(gm.inner);
-  const uint32_t plane = static_cast<uint32_t>(gm.channels * gm.inner);
+  const uint32_t inner = static_cast<uint32_t>(gm.inner) / VEC;          // access units per row
+  const uint32_t total = static_cast<uint32_t>(nb) * inner;
+  const uint32_t plane = static_cast<uint32_t>(gm.channels * gm.inner) / VEC;
   const T* xb = x + (b0 * gm.channels + c) * gm.inner;
   Stat4 s;
   stat_init(s);
-  constexpr int U = 8;
+  constexpr int U = VEC == 1 ? 8 : 4;
   for (uint32_t t0 = 0; t0 < total; t0 += 32 * U) {
-    float v[U];
+    uint32_t off[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t t = t0 + u * 32 + lane;
       ok[u] = t < total;
       const uint32_t bl = static_cast<uint32_t>((static_cast<uint64_t>(t) * gm.magic) >> 24);
-      v[u] = ok[u] ? to_f32<T>(xb[bl * plane + (t - bl * inner)]) : 0.f;
+      off[u] = bl * plane + (t - bl * inner);
     }
+    if constexpr (VEC == 1) {
+      float v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (ok[u]) stat_add<ABS>(s, v[u]);
+      for (int u = 0; u < U; ++u) v[u] = ok[u] ? to_f32<T>(xb[off[u]]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) stat_add<ABS>(s, v[u]);
+    } else {
+      raw r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) r[u] = ld_stream(reinterpret_cast<const raw*>(xb) + off[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        float f[V::N];
+        V::unpack(r[u], f);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) stat_add<ABS>(s, f[e]);
+      }
+    }
   }
   s = stat_warp(s);
   if (lane == 0) part[c * gm.chunks + jc] = s;
@@ -810,11 +830,13 @@ static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* w
     const int64_t tiles = (n / Vec<T>::N + kThreads * 4 - 1) / (kThreads * 4);
     stats_flat_kernel<T, ABS><<<stream_grid(tiles, 8), kThreads, 0, st>>>(x, n, stats, ws);
   } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
-    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner);
+    const bool vec = cmaj_vec_ok<T>(l->inner, x, nullptr, nullptr, nullptr);
+    const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);
     const int64_t blocks = (cg.channels * cg.chunks + kRowWarps - 1) / kRowWarps;
     if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
     Stat4* part = reinterpret_cast<Stat4*>(ws_partials(ws));
-    stats_cmaj_kernel<T, ABS><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(x, cg, part);
+    auto kern = vec ? stats_cmaj_kernel<T, ABS, Vec<T>::N> : stats_cmaj_kernel<T, ABS, 1>;
+    kern<<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(x, cg, part);
     DLMCQ_LAUNCH_CHECK();
     stats_finalize_kernel<<<static_cast<unsigned>(cg.channels), 128, 0, st>>>(part, cg.chunks, cg.chunks, 0, stats);
   } else {

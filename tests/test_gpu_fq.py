@@ -201,7 +201,9 @@ SHAPES = [
     ((32, 9), 0),                # depthwise rows
     ((16, 4608), 0),             # longest ResNet row
     ((3, 5000), 0),              # row longer than one segment
-    ((4, 8, 7, 7), 1),           # activations, channel axis 1, 49-element planes
+    ((4, 8, 7, 7), 1),           # activations, channel axis 1, 49-element planes (scalar channel-major kernel)
+    ((5, 6, 8, 8), 1),           # 64-element planes: whole 128-bit vectors (vectorised channel-major kernel)
+    ((3, 4, 14, 14), 1),         # 196-element planes: vectorised for fp32, scalar for bf16 (196 % 8 != 0)
     ((2, 6, 56, 56), 1),
 ]
 

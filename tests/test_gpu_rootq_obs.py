@@ -327,20 +327,23 @@ def test_sweep_channel_unstaged_rows_bf16_and_block_geometry():
         assert torch.equal(s_b, s_all[lo_r:hi_r]) and torch.equal(o_b, o_all[lo_r:hi_r])
 
 
-def test_channel_major_kernels_with_several_batch_chunks():
-    """[B, C, 7, 7] activations with B*49 > 8192: every channel is covered by several (channel, batch chunk)
-    work items whose partial statistics / scale gradients are combined by the CTA-per-channel finalisers."""
+@pytest.mark.parametrize("shape", [(400, 6, 7, 7), (150, 6, 14, 14), (260, 5, 8, 8)])
+def test_channel_major_kernels_with_several_batch_chunks(shape):
+    """[B, C, h, w] activations with small planes and B*h*w > 8192: every channel is covered by several (channel,
+    batch chunk) work items whose partial statistics / scale gradients are combined by the CTA-per-channel
+    finalisers.  7x7: scalar accesses; 14x14 and 8x8: rows are whole 128-bit vectors (vectorised variant)."""
     gen = torch.Generator().manual_seed(22)
-    x = torch.relu(torch.randn(400, 6, 7, 7, generator=gen)) * 1.5
+    x = torch.relu(torch.randn(shape, generator=gen)) * 1.5
     dy = torch.randn(x.shape, generator=gen)
     st = F().obs_stats(dev(x), ch_axis=1).cpu()
-    rows = x.transpose(0, 1).reshape(6, -1)
+    rows = x.transpose(0, 1).reshape(shape[1], -1)
     assert torch.equal(st[:, 0], rows.min(1)[0]) and torch.equal(st[:, 1], rows.max(1)[0])
     assert torch.equal(st[:, 2], rows.abs().max(1)[0]) and torch.allclose(st[:, 3], rows.abs().sum(1), rtol=1e-5)
     xn = x.clone()
-    xn[399, 4, 6, 6] = float("nan")
+    xn[shape[0] - 1, 4, shape[2] - 1, shape[3] - 1] = float("nan")
     stn = F().obs_stats(dev(xn), ch_axis=1).cpu()
-    assert torch.isnan(stn[4]).all() and not torch.isnan(stn[[0, 1, 2, 3, 5]]).any()
+    others = [c for c in range(shape[1]) if c != 4]
+    assert torch.isnan(stn[4]).all() and not torch.isnan(stn[others]).any()
     scale, off = R.obs_minmax_channel(x, 4, False, ch_axis=1)
     g = R.lsq_g(x.numel(), 15)
     xs, ss = x.clone().requires_grad_(True), scale.clone().requires_grad_(True)
