@@ -574,3 +574,40 @@ def test_bf16_rootq_and_observers():
     sb, itb, doneb = Fn.l2norm_fixed_point(dev(rows), s0, o0, 0, 15, max_iters=200)
     sf, itf, donef = Fn.l2norm_fixed_point(dev(rows.float()), s0, o0, 0, 15, max_iters=200)
     assert doneb == donef and torch.allclose(sb, sf, rtol=1e-5)
+
+
+def test_reductions_are_deterministic_run_to_run():
+    """Every reduction on the path is fixed-order (no floating-point atomics): repeated launches on the same input
+    return the same bits - also a race detector for the multi-warp channel sweep (shared-memory exchange + named
+    barriers) under every warps-per-row setting."""
+    import os
+    from dlmc_quant_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(71)
+    w = dev(torch.randn(96, 2304, generator=gen) * 0.02)
+    x = dev(torch.relu(torch.randn(1 << 22, generator=gen)) * 2)
+    dy = dev(torch.randn(1 << 22, generator=gen))
+    xa = dev(torch.relu(torch.randn(64, 48, 14, 14, generator=gen)))
+    dya = dev(torch.randn(64, 48, 14, 14, generator=gen))
+    try:
+        for wpr in ("1", "2", "4", "8", None):
+            if wpr is None:
+                os.environ.pop("DLMCQ_SWEEP_WPR", None)
+            else:
+                os.environ["DLMCQ_SWEEP_WPR"] = wpr
+            first = Fn.sweep_channel(w, 4, True)
+            for _ in range(10):
+                again = Fn.sweep_channel(w, 4, True)
+                assert torch.equal(first[0], again[0]) and torch.equal(first[1], again[1]), wpr
+    finally:
+        os.environ.pop("DLMCQ_SWEEP_WPR", None)
+    st = Fn.obs_stats(x)
+    scale, off = Fn.minmax_from_stats(st, 4, False)
+    ref = (Fn.fq_backward(x, dy, scale, off, 0, 15, 1, g=1e-3)[1], Fn.sweep_tensor_sse(x, st, 8), Fn.obs_stats(x),
+           Fn.kth_values(x, [1000, 4000000]))
+    sa, oa = Fn.minmax_from_stats(Fn.obs_stats(xa, ch_axis=1), 4, False)
+    ref_a = Fn.fq_backward(xa, dya, sa, oa, 0, 15, 1, g=1e-3, ch_axis=1)[1]
+    for _ in range(10):
+        got = (Fn.fq_backward(x, dy, scale, off, 0, 15, 1, g=1e-3)[1], Fn.sweep_tensor_sse(x, st, 8), Fn.obs_stats(x),
+               Fn.kth_values(x, [1000, 4000000]))
+        assert all(torch.equal(a, b) for a, b in zip(ref, got))
+        assert torch.equal(ref_a, Fn.fq_backward(xa, dya, sa, oa, 0, 15, 1, g=1e-3, ch_axis=1)[1])
