@@ -36,11 +36,11 @@ class _GroupedWeightFakeQuant(torch.autograd.Function):
 
 
 class WeightQuantGroup:
-    def __init__(self, model):
+    def __init__(self, model, modules=None):
         self.model = model
         self._key = None
         self._mods = []
-        self._candidates = None
+        self._candidates = list(modules) if modules is not None else None
 
     # -- membership ---------------------------------------------------------------------------------------
     @staticmethod
@@ -171,16 +171,43 @@ class WeightQuantGroup:
 class GroupHandle:
     """Returned by group_weight_quantizers: remove() restores the per-layer behaviour."""
 
-    def __init__(self, group, hook):
-        self.group, self._hook = group, hook
+    def __init__(self, model, groups, hook):
+        self.model, self.groups, self._hook = model, groups, hook
+        self.group = groups[0]
 
     def remove(self):
         self._hook.remove()
-        for m in self.group.model.modules():
+        for m in self.model.modules():
             m.__dict__.pop('_wq', None)
 
 
-def group_weight_quantizers(model):
-    """Quantise all weight tensors of `model`'s QBase layers in one launch per direction (see module docstring)."""
-    group = WeightQuantGroup(model)
-    return GroupHandle(group, model.register_forward_pre_hook(group))
+def group_weight_quantizers(model, n_groups=None):
+    """Quantise all weight tensors of `model`'s QBase layers in one launch per direction (see module docstring).
+
+    n_groups > 1 splits the layers, in forward order, into that many groups of about equal parameter bytes, each with
+    its own autograd node: a group's backward runs as soon as ITS layers' weight gradients exist, so a data-parallel
+    wrapper can overlap the all-reduce of the later layers' gradients with the rest of the backward pass (one node
+    for the whole model delivers every weight gradient at the very end).  Default: 1, or 4 when torch.distributed
+    is initialised with more than one rank."""
+    if n_groups is None:
+        import torch.distributed as dist
+        n_groups = 4 if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else 1
+    mods = [m for m in model.modules() if isinstance(m, QBase)]
+    n_groups = max(1, min(int(n_groups), len(mods) or 1))
+    total = sum(m.weight.numel() for m in mods) or 1
+    chunks, cur, acc = [], [], 0
+    for m in mods:
+        cur.append(m)
+        acc += m.weight.numel()
+        if acc >= total * (len(chunks) + 1) / n_groups and len(chunks) < n_groups - 1:
+            chunks.append(cur)
+            cur = []
+    if cur:
+        chunks.append(cur)
+    groups = [WeightQuantGroup(model, c) for c in chunks]
+
+    def hook(module, args):
+        for g in groups:
+            g(module, args)
+        return None
+    return GroupHandle(model, groups, model.register_forward_pre_hook(hook))
