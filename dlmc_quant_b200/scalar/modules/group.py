@@ -62,8 +62,9 @@ class WeightQuantGroup:
             mods = [m for m in self._candidates if self._eligible(m)]
         else:
             mods = self._mods
-        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(), m.weight.stride())
-                    for m in mods)
+        # wt_offset._version: an in-place update of the buffer (load_state_dict) must refresh our fp32 copy of it
+        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(), m.wt_offset._version,
+                     m.weight.stride()) for m in mods)
         if key == self._key:
             return
         self._key, self._mods = key, mods
@@ -78,8 +79,8 @@ class WeightQuantGroup:
         for i, m in enumerate(mods):
             w, s = m.weight, m.wt_scale
             c = s.numel()
-            off = m.wt_offset.detach().to(device=dev, dtype=torch.float32).reshape(-1)
-            off = (off.expand(c) if off.numel() == 1 else off).contiguous()
+            off = m.wt_offset.detach().to(device=dev, dtype=torch.float32).reshape(-1)   # a view when already fp32
+            off = (off.expand(c) if off.numel() == 1 and c > 1 else off).contiguous()
             self._offsets.append(off)
             it = self._arr[i]
             it.x, it.scale, it.offset = w.data_ptr(), s.data_ptr(), off.data_ptr()
