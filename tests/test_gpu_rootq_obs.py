@@ -611,3 +611,36 @@ def test_reductions_are_deterministic_run_to_run():
                Fn.kth_values(x, [1000, 4000000]))
         assert all(torch.equal(a, b) for a, b in zip(ref, got))
         assert torch.equal(ref_a, Fn.fq_backward(xa, dya, sa, oa, 0, 15, 1, g=1e-3, ch_axis=1)[1])
+
+
+def test_sweep_channel_edge_rows_under_every_geometry():
+    """NaN rows, constant rows (zero scale: literal chain), all-zero rows, single-element rows and rows shorter than
+    the number of lanes, with 1..8 warps per row (warps without elements must still take part in the exchange)."""
+    import os
+    from dlmc_quant_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(81)
+    cases = []
+    t = torch.rand(6, 700, generator=gen) * 3 + 0.5
+    t[1, 13] = float("nan")
+    t[2] = 1.75
+    t[3] = 0.0
+    t[4, ::2] = 0.0
+    cases.append(t)
+    cases.append(torch.rand(5, 1, generator=gen) + 0.1)
+    cases.append(torch.rand(3, 5, generator=gen) * 2)
+    cases.append((torch.randn(4, 33, generator=gen) * 0.02))
+    try:
+        for wpr in ("1", "2", "4", "8"):
+            os.environ["DLMCQ_SWEEP_WPR"] = wpr
+            for t in cases:
+                for signed in (False, True):
+                    s, o = Fn.sweep_channel(dev(t), 4, signed)
+                    rs, ro = R.obs_l2loss_channel(t.clone(), 4, signed)
+                    rs, ro = rs.reshape(-1), ro.reshape(-1).float()
+                    s, o = s.cpu(), o.cpu()
+                    nan_rows = torch.isnan(rs)
+                    assert torch.equal(torch.isnan(s), nan_rows) and torch.equal(torch.isnan(o), torch.isnan(ro)), (wpr, t.shape)
+                    ok = ~nan_rows
+                    _sweep_rows_equivalent(t[ok], s[ok], o[ok], rs[ok], ro[ok], 4)
+    finally:
+        os.environ.pop("DLMCQ_SWEEP_WPR", None)
