@@ -397,6 +397,148 @@ dequant_kernel(const T* __restrict__ codes, T* __restrict__ y, int64_t n, int64_
 }
 
 // ---------------------------------------------------------------------------------------
+// tiled per-channel kernels: per-channel ACTIVATIONS [B, C, HW] with planes that are whole, aligned 128-bit vectors
+// and at least 64 vectors long.  The tensor is streamed exactly like the flat kernels - one contiguous 16 KB tile
+// per CTA, four 128-bit loads in flight per thread, packed arithmetic - and only the qparams lookup differs: the
+// <= kTileRows rows a tile touches have their ChanParams resolved once per CTA into shared memory.  Backward: every
+// thread adds its vectors' scale-gradient terms into a private shared-memory slot per row, a warp folds each row's
+// 256 slots, the per-(tile, row) partials go to the workspace and one CTA per channel combines them in a fixed
+// order (deterministic).  Replaces the warp-per-row kernels on this geometry (5.4-6.0 -> 6.3+ TB/s).
+// ---------------------------------------------------------------------------------------
+constexpr int kTileVecs = kThreads * kUnroll;     // 1024 vectors per tile
+constexpr int kTileMinVpr = 64;                   // vectors per row at least
+constexpr int kTileRows = kTileVecs / kTileMinVpr + 2;
+
+struct TileGeom {
+  int64_t nvec;        // vectors in the tensor
+  uint32_t vpr;        // vectors per row (inner / Vec::N)
+  uint32_t channels;
+  uint32_t step_rows;  // kThreads / vpr
+  uint32_t step_rem;   // kThreads % vpr
+};
+
+template <typename T>
+static inline bool tiled_ok(const dlmcq_layout* l, const void* a, const void* b, const void* c) {
+  const int64_t vn = Vec<T>::N;
+  return l->outer > 1 && l->channels > 1 && l->inner % vn == 0 && l->inner / vn >= kTileMinVpr &&
+         l->inner / vn < (int64_t(1) << 31) && l->channels < (int64_t(1) << 31) && aligned16(a) && aligned16(b) &&
+         aligned16(c);
+}
+template <typename T>
+static inline TileGeom make_tile_geom(const dlmcq_layout* l) {
+  TileGeom g;
+  g.vpr = static_cast<uint32_t>(l->inner / Vec<T>::N);
+  g.nvec = l->outer * l->channels * static_cast<int64_t>(g.vpr);
+  g.channels = static_cast<uint32_t>(l->channels);
+  g.step_rows = kThreads / g.vpr;
+  g.step_rem = kThreads % g.vpr;
+  return g;
+}
+
+template <int FORM, typename T, bool BWD>
+__global__ void __launch_bounds__(kThreads, 4)
+fq_tiled_chan_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, T* __restrict__ codes,
+                     TileGeom gm, const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo,
+                     float hi, float* __restrict__ part /* [tiles][kTileRows] */) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  __shared__ ChanParams sp[kTileRows];
+  __shared__ float acc_sm[BWD ? kTileRows * kThreads : 1];
+  __shared__ int64_t s_row_first;
+  __shared__ uint32_t s_nrows, s_rem_first;
+  const int64_t tile = blockIdx.x;
+  const int64_t v_first = tile * kTileVecs;
+  if (threadIdx.x == 0) {                        // the 64-bit divisions once per CTA, not once per thread
+    const int64_t rf = v_first / gm.vpr;
+    const int64_t v_last = (v_first + kTileVecs < gm.nvec ? v_first + kTileVecs : gm.nvec) - 1;
+    s_row_first = rf;
+    s_rem_first = static_cast<uint32_t>(v_first - rf * gm.vpr);
+    s_nrows = static_cast<uint32_t>(v_last / gm.vpr - rf) + 1u;             // <= kTileRows
+  }
+  __syncthreads();
+  const int nrows = static_cast<int>(s_nrows);
+  if (threadIdx.x < nrows)
+    sp[threadIdx.x] = make_params<FORM>(scale, offset, (s_row_first + threadIdx.x) % gm.channels, g, lo, hi);
+  if (BWD) {
+    for (int r = 0; r < nrows; ++r) acc_sm[r * kThreads + threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  // local row / remainder of this thread's first vector, then +kThreads vectors per step
+  const int64_t v0 = v_first + threadIdx.x;
+  const uint32_t t0 = s_rem_first + threadIdx.x;                            // < vpr + kThreads
+  uint32_t lr = t0 / gm.vpr;
+  uint32_t rem = t0 - lr * gm.vpr;
+  const raw* xv = reinterpret_cast<const raw*>(x);
+  const raw* gv = reinterpret_cast<const raw*>(dy);
+  raw rx[kUnroll], rg[kUnroll];
+  uint32_t rows[kUnroll];
+  bool ok[kUnroll];
+#pragma unroll
+  for (int k = 0; k < kUnroll; ++k) {
+    const int64_t v = v0 + static_cast<int64_t>(k) * kThreads;
+    ok[k] = v < gm.nvec;
+    rows[k] = lr;
+    if (ok[k]) {
+      rx[k] = ld_stream(xv + v);
+      if (BWD) rg[k] = ld_stream(gv + v);
+    }
+    lr += gm.step_rows;
+    rem += gm.step_rem;
+    if (rem >= gm.vpr) { rem -= gm.vpr; ++lr; }
+  }
+#pragma unroll
+  for (int k = 0; k < kUnroll; ++k) {
+    if (!ok[k]) continue;
+    const int64_t v = v0 + static_cast<int64_t>(k) * kThreads;
+    const ChanParams p = sp[rows[k]];
+    float f[V::N], o1[V::N], o2[V::N];
+    V::unpack(rx[k], f);
+    if (BWD) {
+      float fg[V::N], as = 0.f, ao = 0.f;
+      V::unpack(rg[k], fg);
+      fq_vec_bwd<FORM, false, V::N>(f, fg, p, lo, hi, o1, as, ao);
+      st_stream(reinterpret_cast<raw*>(out) + v, V::pack(o1));
+      acc_sm[rows[k] * kThreads + threadIdx.x] += as;
+    } else {
+      fq_vec<FORM, V::N>(f, p, lo, hi, o2, o1);
+      if (out) st_stream(reinterpret_cast<raw*>(out) + v, V::pack(o1));
+      if (codes) st_stream(reinterpret_cast<raw*>(codes) + v, V::pack(o2));
+    }
+  }
+  if (BWD) {
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < nrows; r += kThreads / 32) {
+      float a = 0.f;
+#pragma unroll
+      for (int q = 0; q < kThreads / 32; ++q) a += acc_sm[r * kThreads + q * 32 + lane];
+      a = warp_sum(a);
+      if (lane == 0) part[tile * kTileRows + r] = a;
+    }
+  }
+}
+
+// one CTA per channel: the rows (b, ch) of that channel, each covered by 1..k consecutive tiles
+__global__ void __launch_bounds__(128)
+tiled_chan_finalize(const float* __restrict__ part, TileGeom gm, int64_t outer, float gmul, float* __restrict__ dscale) {
+  __shared__ double sh[4];
+  const int64_t ch = blockIdx.x;
+  double s = 0.0;
+  for (int64_t b = threadIdx.x; b < outer; b += blockDim.x) {
+    const int64_t row = b * gm.channels + ch;
+    const int64_t t0 = (row * gm.vpr) / kTileVecs, t1 = ((row + 1) * gm.vpr - 1) / kTileVecs;
+    for (int64_t t = t0; t <= t1; ++t) {
+      const int64_t row_first = (t * kTileVecs) / gm.vpr;
+      s += static_cast<double>(part[t * kTileRows + (row - row_first)]);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) dscale[ch] = static_cast<float>((sh[0] + sh[1]) + (sh[2] + sh[3])) * gmul;
+}
+
+// ---------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------
 static inline int check_layout(const dlmcq_layout* l) {
@@ -432,6 +574,13 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
       fq_fwd_flat_unaligned<FORM, T><<<stream_grid(tiles, 8), kThreads, 0, st>>>(
           static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), n, qp->scale, qp->offset, qp->g, lo, hi);
     }
+  } else if (tiled_ok<T>(l, x, y, codes)) {
+    const TileGeom tg = make_tile_geom<T>(l);
+    const int64_t tiles = (tg.nvec + kTileVecs - 1) / kTileVecs;
+    if (tiles > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+    fq_tiled_chan_kernel<FORM, T, false><<<static_cast<unsigned>(tiles), kThreads, 0, st>>>(
+        static_cast<const T*>(x), nullptr, static_cast<T*>(y), static_cast<T*>(codes), tg, qp->scale, qp->offset,
+        qp->g, lo, hi, nullptr);
   } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
     const bool vec = cmaj_vec_ok<T>(l->inner, x, y, codes, nullptr);
     const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);
@@ -475,6 +624,16 @@ static int launch_bwd(const void* x, const void* dy, void* dx, float* dscale, fl
                                static_cast<const T*>(dy), static_cast<T*>(dx), n, qp->scale, qp->offset, qp->g, lo, hi,
                                dscale, doffset, ws);
     if (e != cudaSuccess) return set_cuda_error(e);
+  } else if (doffset == nullptr && n > 0 && tiled_ok<T>(l, x, dy, dx)) {
+    const TileGeom tg = make_tile_geom<T>(l);
+    const int64_t tiles = (tg.nvec + kTileVecs - 1) / kTileVecs;
+    if (tiles > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
+    fq_tiled_chan_kernel<FORM, T, true><<<static_cast<unsigned>(tiles), kThreads, 0, st>>>(
+        static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<T*>(dx), nullptr, tg, qp->scale, qp->offset,
+        qp->g, lo, hi, ws_partials(ws));
+    DLMCQ_LAUNCH_CHECK();
+    const float gmul = (FORM == DLMCQ_FORM_AFFINE || FORM == DLMCQ_FORM_A1) ? qp->g : 1.f;
+    tiled_chan_finalize<<<static_cast<unsigned>(l->channels), 128, 0, st>>>(ws_partials(ws), tg, l->outer, gmul, dscale);
   } else if (cmaj_ok(l->outer, l->channels, l->inner) && doffset == nullptr && n > 0) {
     const bool vec = cmaj_vec_ok<T>(l->inner, x, dy, dx, nullptr);
     const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);
@@ -572,6 +731,10 @@ extern "C" size_t dlmcq_workspace_bytes(const dlmcq_layout* l) {
     const RowGeom gm = make_geom(l->outer, l->channels, l->inner);
     const size_t rows_bytes = static_cast<size_t>(gm.rows * gm.segs) * 4 * sizeof(float);
     if (kWsHeaderBytes + rows_bytes > bytes) bytes = kWsHeaderBytes + rows_bytes;
+    // tiled per-channel backward: one float per (16 KB tile, row of the tile); bound with the bf16 vector width
+    const size_t tiles = static_cast<size_t>(l->outer * l->channels * l->inner) / (kTileVecs * 4) + 1;
+    const size_t tiled_bytes = tiles * kTileRows * sizeof(float);
+    if (kWsHeaderBytes + tiled_bytes > bytes) bytes = kWsHeaderBytes + tiled_bytes;
   }
   return bytes;
 }

@@ -204,7 +204,9 @@ SHAPES = [
     ((4, 8, 7, 7), 1),           # activations, channel axis 1, 49-element planes (scalar channel-major kernel)
     ((5, 6, 8, 8), 1),           # 64-element planes: whole 128-bit vectors (vectorised channel-major kernel)
     ((3, 4, 14, 14), 1),         # 196-element planes: vectorised for fp32, scalar for bf16 (196 % 8 != 0)
-    ((2, 6, 56, 56), 1),
+    ((2, 6, 56, 56), 1),         # long planes: tiled per-channel kernels (rows span several 16 KB tiles)
+    ((3, 5, 16, 16), 1),         # 64-vector planes: 16-17 rows per tile (fp32 tiled; bf16 warp-per-row)
+    ((3, 7, 20, 20), 1),         # 100-vector planes, ragged last tile
 ]
 
 
