@@ -328,6 +328,26 @@ def test_workspace_is_left_reusable():
     assert all(torch.equal(r[0][0], k[0]) for k in r[1:])
 
 
+@pytest.mark.parametrize("shape", [(3, 6, 32, 32), (4, 8, 8, 8), (3, 5, 7, 7), (2, 4, 16, 16)])
+def test_backward_bf16_per_channel_layouts(shape):
+    """bf16 per-channel activations through every kernel family (tiled: 32x32 planes = 128 vectors; vectorised
+    channel-major: 8x8; scalar channel-major: 7x7; warp-per-row: 16x16 = 32 vectors): fp32 math on the up-converted
+    values, one rounding of dx, fp32 scale gradients."""
+    gen = torch.Generator().manual_seed(17)
+    x = (torch.relu(torch.randn(shape, generator=gen)) * 1.5).bfloat16()
+    dy = torch.randn(shape, generator=gen).bfloat16()
+    scale, off = R.obs_minmax_channel(x.float(), 4, False, ch_axis=1)
+    g = R.lsq_g(x.numel(), 15)
+    dx_ref, ds_ref = oracle_bwd(AFFINE, x.float(), scale, off, 0, 15, g, dy.float())
+    _, y_ref = oracle_fwd(AFFINE, x.float(), scale, off, 0, 15, g)
+    y = F().fq_forward(dev(x), dev(scale), dev(off), 0, 15, AFFINE, g=g, ch_axis=1)
+    exact(y.float(), y_ref.bfloat16().float(), "y bf16")
+    dx, ds = F().fq_backward(dev(x), dev(dy), dev(scale), dev(off), 0, 15, AFFINE, g=g, ch_axis=1)
+    assert dx.dtype == torch.bfloat16
+    exact(dx.float(), dx_ref.bfloat16().float(), "dx bf16")
+    red_close(ds, ds_ref.reshape(-1), abs_sum=dy.float().abs().sum(dim=(0, 2, 3)) * 15 * g)
+
+
 # --------------------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE sizes; oracle too slow on CPU here)
 @pytest.mark.parametrize("n", [1 << 26])
