@@ -1,14 +1,6 @@
-"""dlmc/quantization/scalar/FSPTQuant/linear.py: FSPTQLinear."""
-import torch.nn.functional as F
-from torch.nn import Linear
-
+"""FSPTQLinear (reference: dlmc/quantization/scalar/FSPTQuant/linear.py); the class body lives in scalar/_layers.py."""
+from .._layers import make_layer
 from .base import FSPTQBase
 
-
-class FSPTQLinear(FSPTQBase, Linear):
-    def __init__(self, *args, qconfig=None, **kwargs):
-        Linear.__init__(self, *args, **kwargs)
-        self.initialize(qconfig)
-
-    def _forward_func(self, input, weight):
-        return F.linear(input, weight, self.bias)
+__all__ = ["FSPTQLinear"]
+FSPTQLinear = make_layer("FSPTQLinear", FSPTQBase, "linear", __name__)

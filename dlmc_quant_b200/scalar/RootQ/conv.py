@@ -1,18 +1,6 @@
-"""dlmc/quantization/scalar/RootQ/conv.py: RootQConv2d."""
-import torch.nn.functional as F
-from torch.nn import Conv2d
-from torch.nn.modules.utils import _pair
-
+"""RootQConv2d (reference: dlmc/quantization/scalar/RootQ/conv.py); the class body lives in scalar/_layers.py."""
+from .._layers import make_layer
 from .base import RootQBase
 
-
-class RootQConv2d(RootQBase, Conv2d):
-    def __init__(self, *args, qconfig=None, **kwargs):
-        Conv2d.__init__(self, *args, **kwargs)
-        self.initialize(qconfig)
-
-    def _forward_func(self, input, weight):
-        if self.padding_mode != 'zeros':
-            return F.conv2d(F.pad(input, self._reversed_padding_repeated_twice, mode=self.padding_mode),
-                            weight, self.bias, self.stride, _pair(0), self.dilation, self.groups)
-        return F.conv2d(input, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+__all__ = ["RootQConv2d"]
+RootQConv2d = make_layer("RootQConv2d", RootQBase, "conv", __name__)

@@ -1,14 +1,6 @@
-"""dlmc/quantization/scalar/RootQ/linear.py: RootQLinear."""
-import torch.nn.functional as F
-from torch.nn import Linear
-
+"""RootQLinear (reference: dlmc/quantization/scalar/RootQ/linear.py); the class body lives in scalar/_layers.py."""
+from .._layers import make_layer
 from .base import RootQBase
 
-
-class RootQLinear(RootQBase, Linear):
-    def __init__(self, *args, qconfig=None, **kwargs):
-        Linear.__init__(self, *args, **kwargs)
-        self.initialize(qconfig)
-
-    def _forward_func(self, input, weight):
-        return F.linear(input, weight, self.bias)
+__all__ = ["RootQLinear"]
+RootQLinear = make_layer("RootQLinear", RootQBase, "linear", __name__)

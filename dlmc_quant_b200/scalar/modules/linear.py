@@ -1,14 +1,6 @@
-"""dlmc/quantization/scalar/modules/linear.py: QLinear."""
-import torch.nn.functional as F
-from torch.nn import Linear
-
+"""QLinear (reference: dlmc/quantization/scalar/modules/linear.py); the class body lives in scalar/_layers.py."""
+from .._layers import make_layer
 from .base import QBase
 
-
-class QLinear(QBase, Linear):
-    def __init__(self, *args, qconfig=None, **kwargs):
-        Linear.__init__(self, *args, **kwargs)
-        self.initialize(qconfig)
-
-    def _forward_func(self, input, weight):
-        return F.linear(input, weight, self.bias)
+__all__ = ["QLinear"]
+QLinear = make_layer("QLinear", QBase, "linear", __name__)
