@@ -7,7 +7,7 @@ BitMixer / MetaQ mappings are not offered: those packages are absent from the re
 (quantize.py:10,12 import modules that do not exist)."""
 import copy
 import re
-from operator import attrgetter, itemgetter
+from operator import attrgetter
 from typing import Dict, Iterable, List
 
 from torch import nn
@@ -19,93 +19,88 @@ from .scalar.modules.group import group_weight_quantizers  # noqa: F401  (step-l
 
 __all__ = ['quantize_model', 'get_layers', 'attrsetter', 'group_weight_quantizers']
 
-MODULE_MAPPING = {nn.Conv2d: qnn.QConv2d, nn.Linear: qnn.QLinear}
-ROOTQ_MAPPING = {nn.Conv2d: RQ.RootQConv2d, nn.Linear: RQ.RootQLinear}
-FSPTQUANT_MAPPING = {nn.Conv2d: FSPQ.FSPTQConv2d, nn.Linear: FSPQ.FSPTQLinear}
+# quantization_type -> {torch layer class: quantised class}   (quantize.py:19-42; None = the QAT / PTQ / LSQ modules)
+FAMILIES = {
+    None: {nn.Conv2d: qnn.QConv2d, nn.Linear: qnn.QLinear},
+    "RootQ": {nn.Conv2d: RQ.RootQConv2d, nn.Linear: RQ.RootQLinear},
+    "FSPTQ": {nn.Conv2d: FSPQ.FSPTQConv2d, nn.Linear: FSPQ.FSPTQLinear},
+}
+MODULE_MAPPING, ROOTQ_MAPPING, FSPTQUANT_MAPPING = FAMILIES[None], FAMILIES["RootQ"], FAMILIES["FSPTQ"]
 
 
-def attrsetter(*items):
-    """dlmc/utils/access.py:12-27."""
-    def resolve_attr(obj, attr):
-        attrs = attr.split(".")
-        for name in attrs[:-1]:
-            obj = getattr(obj, name)
-        return obj, attrs[-1]
-
-    def g(obj, val):
-        for attr in items:
-            resolved_obj, resolved_attr = resolve_attr(obj, attr)
-            setattr(resolved_obj, resolved_attr, val)
-    return g
+def attrsetter(*paths):
+    """dlmc/utils/access.py:12-27: setter for dotted attribute paths (`attrsetter("layer1.0.conv1")(model, m)`)."""
+    def setter(root, value):
+        for path in paths:
+            *parents, leaf = path.split(".")
+            owner = root
+            for name in parents:
+                owner = getattr(owner, name)
+            setattr(owner, leaf, value)
+    return setter
 
 
 def get_layers(model: nn.Module, filter_regexp: str = "(.*?)", filter_types: Iterable = None) -> List[str]:
-    """dlmc/utils/access.py:30-61: layer names from parameter names, filtered by regex and type."""
-    names = map(itemgetter(0), model.named_parameters())
-    names = filter(lambda x: "bias" not in x, names)
-    names = map(lambda x: x.replace(".weight_orig", ""), names)
-    names = map(lambda x: x.replace(".weight", ""), names)
-    r = re.compile("(module\\.)?" + "(" + filter_regexp + ")")
-    names = list(filter(r.match, names))
+    """dlmc/utils/access.py:30-61: the names of the modules that own a weight (derived from the parameter names,
+    `.weight` / spectral-norm `.weight_orig` stripped, biases skipped), kept when they match the regular expression
+    (an optional DataParallel `module.` prefix is tolerated) and, if given, the module types."""
+    pattern = re.compile(r"(module\.)?(" + filter_regexp + ")")
+    names = []
+    for pname, _ in model.named_parameters():
+        if "bias" in pname:
+            continue
+        name = pname.replace(".weight_orig", "").replace(".weight", "")
+        if pattern.match(name):
+            names.append(name)
     if filter_types is not None:
         names = [n for n in names if isinstance(attrgetter(n)(model), filter_types)]
     return names
 
 
-def _override_options(dst_config: Dict, src_config: Dict = None) -> Dict:
-    """quantize.py:44-58."""
-    if src_config is None:
-        return dst_config
-    dst_config = copy.deepcopy(dst_config)
-    if 'type' in src_config:
-        dst_config['type'] = src_config['type']
-    if 'enable' in src_config:
-        dst_config['enable'] = src_config['enable']
-    if 'args' in src_config:
-        dst_config['args'].update(src_config['args'])
-    return dst_config
+def _merged(base: Dict, override: Dict = None) -> Dict:
+    """quantize.py:44-58: `type`, `enable` replace, `args` update; the default block is never modified."""
+    merged = copy.deepcopy(base)
+    for key in ("type", "enable"):
+        if override and key in override:
+            merged[key] = override[key]
+    if override and "args" in override:
+        merged["args"].update(override["args"])
+    return merged
+
+
+def _swap_class(model, name, quantised_cls, layer_config):
+    """quantize.py:130-136: same object state under the quantised class - __init__ is never called."""
+    original = attrgetter(name)(model)
+    swapped = quantised_cls.__new__(quantised_cls)
+    swapped.__dict__.update(original.__dict__)
+    swapped.initialize(layer_config)
+    attrsetter(name)(model, swapped)
+    return swapped
 
 
 def quantize_model(model: nn.Module, config: Dict, logger=None, quantization_type: str = None, **kwargs) -> None:
-    """quantize.py:61-142."""
-    default_weight_config = config['weight']
-    default_input_config = config['input']
-    default_momentum_config = 0.1
-    if quantization_type == "RootQ":
-        mapping = ROOTQ_MAPPING
-        default_momentum_config = config['momentum']
-    elif quantization_type == "FSPTQ":
-        mapping = FSPTQUANT_MAPPING
-    elif quantization_type in ("BitMixer", "MetaQ"):
+    """quantize.py:61-142: every Conv2d / Linear that is not excluded becomes the quantised class of the chosen
+    family, configured from the `weight` / `input` blocks plus the first matching `override_options` entry."""
+    if quantization_type in ("BitMixer", "MetaQ"):
         raise NotImplementedError(f"{quantization_type}: its package is not part of the reference tree either")
-    else:
-        mapping = MODULE_MAPPING
+    family = FAMILIES.get(quantization_type, FAMILIES[None])
+    momentum = config['momentum'] if quantization_type == "RootQ" else 0.1
 
-    all_layers = get_layers(model, filter_types=tuple(mapping.keys()))
-    exclude_layers = []
-    for regexp in config.get('exclude_layers', []):
-        exclude_layers.extend(get_layers(model, filter_regexp=regexp))
-    quantized_layers = [l for l in all_layers if l not in exclude_layers]
+    excluded = {n for rx in config.get('exclude_layers', []) for n in get_layers(model, filter_regexp=rx)}
+    overrides = {}
+    for entry in config.get('override_options', []):
+        for rx in entry['layers']:
+            for n in get_layers(model, filter_regexp=rx):
+                assert n not in overrides, f"layer {n} matched by two override_options entries"
+                overrides[n] = entry['options']
 
-    override_options = {}
-    for opt in config.get('override_options', []):
-        for regexp in opt['layers']:
-            for l in get_layers(model, filter_regexp=regexp):
-                assert l not in override_options
-                override_options[l] = opt['options']
-    for layer in quantized_layers:
-        module = attrgetter(layer)(model)
-        weight_config, input_config = default_weight_config, default_input_config
-        if layer in override_options:
-            weight_config = _override_options(weight_config, override_options[layer].get("weight", None))
-            input_config = _override_options(input_config, override_options[layer].get("input", None))
-        layer_config = {"input": copy.deepcopy(input_config), "weight": copy.deepcopy(weight_config),
-                        "momentum": default_momentum_config}
-        new_type = mapping[type(module)]
-        module_q = new_type.__new__(new_type)
-        module_q.__dict__.update(module.__dict__)
-        module_q.initialize(layer_config)
-        attrsetter(layer)(model, module_q)
+    for name in get_layers(model, filter_types=tuple(family)):
+        if name in excluded:
+            continue
+        opts = overrides.get(name, {})
+        layer_config = {"input": _merged(config['input'], opts.get("input")),
+                        "weight": _merged(config['weight'], opts.get("weight")), "momentum": momentum}
+        _swap_class(model, name, family[type(attrgetter(name)(model))], layer_config)
         if logger is not None:
             logger.info("Quantize module {} with method <input: {}> <weight: {}>".format(
-                layer, layer_config['input'], layer_config['weight']))
+                name, layer_config['input'], layer_config['weight']))
