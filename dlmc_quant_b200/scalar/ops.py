@@ -8,7 +8,8 @@ Differences that are deliberate and documented in DESIGN.md:
     same qparams (the reference initialises each DDP rank from its local batch, SURVEY.md 2.4);
   * l2norm loops are bounded (`max_iters`): the reference's `while diff > eps` never terminates on
     some inputs (the unsigned per-channel form oscillates forever on data with negative values);
-  * `quantize_l2norm_pixel` is not provided: its best-scale bookkeeping is dead code in the reference
+  * `quantize_l2norm_pixel` is not provided: in the reference it raises NameError on every input (ops.py:237
+    calls `emulate_quantize`, which ops.py never imports), its best-scale bookkeeping is dead code
     (ops.py:242-244 assigns best_mse to itself) and nothing in the repo selects it.
 """
 import math
