@@ -1,6 +1,7 @@
 """CPU tests of the host-side mirror of the reference interface: class swap, state names and shapes
 (checkpoint / fnmatch compatibility), config handling, and that compute fails loudly without CUDA."""
 import copy
+import os
 from fnmatch import fnmatch
 
 import pytest
@@ -140,3 +141,23 @@ def test_forward_without_cuda_raises():
     quantize_model(net, copy.deepcopy(CFG), None)
     with pytest.raises(DlmcqError):
         net(torch.randn(2, 3, 8, 8))
+
+
+def test_compat_aliases_resolve_reference_import_paths():
+    """`import dlmc.quantization.scalar...` (the reference's paths, as used by its trainers) -> this package."""
+    import subprocess
+    import sys
+    code = (
+        "import dlmc_quant_b200.compat as c; c.install();"
+        "from dlmc.utils.quantize import quantize_model;"
+        "from dlmc.quantization.scalar import modules as qnn, RootQ as RQ, FSPTQuant as FSPQ;"
+        "from dlmc.quantization.scalar.ops import get_qparams_tensor;"
+        "from dlmc.quantization.scalar.utils import get_qrange;"
+        "from dlmc.utils.merge_bn import merge_bn;"
+        "import dlmc_quant_b200.scalar.modules as ours;"
+        "assert qnn.QConv2d is ours.QConv2d and RQ.RootQConv2d.__module__.startswith('dlmc_quant_b200');"
+        "assert get_qrange(True, 4) == (-7, 7) and quantize_model.__module__ == 'dlmc_quant_b200.quantize';"
+        "print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
