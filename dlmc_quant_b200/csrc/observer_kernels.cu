@@ -143,7 +143,7 @@ stats_rows_kernel(const T* __restrict__ x, RowGeom gm, float* __restrict__ stats
   if ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) {
     const int64_t nvec = len / V::N;
     const raw* xv = reinterpret_cast<const raw*>(xr);
-    constexpr int U = 4;                                     // 128-bit loads in flight per lane
+    constexpr int U = 8;                                     // 128-bit loads in flight per lane
     int64_t j = lane;
     for (; j + 32 * (U - 1) < nvec; j += 32 * U) {
       raw r[U];
