@@ -461,7 +461,7 @@ def test_grouped_weight_quantizers_match_per_layer_path():
                     assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-6), (na, pa.grad, pb.grad)
                 else:       # cuDNN's weight-gradient algorithms are not bit-reproducible between two models
                     assert torch.equal(pa.grad == 0, pb.grad == 0), na
-                    assert torch.allclose(pa.grad, pb.grad, rtol=1e-4, atol=1e-7), na
+                    assert torch.allclose(pa.grad, pb.grad, rtol=1e-3, atol=1e-5), na
         assert sum(len(g._mods) for g in handle.groups) == 3 and len(handle.groups) == (2 if channels_last else 1)
         handle.remove()
         assert torch.equal(a(x), b(x)) and all('_wq' not in m.__dict__ for m in b.modules())
