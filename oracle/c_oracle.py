@@ -138,3 +138,10 @@ def repvgg_fuse(k3, bn3, k1, bn1, bn_id, eps):
     lib().orc_repvgg_fuse(_p(k3), *[_p(t) for t in a3], C.c_float(eps), _p(k1), *[_p(t) for t in a1], C.c_float(eps),
                           *[_p(t) for t in ai], C.c_float(eps), C.c_int64(c), C.c_int64(cin_g), _p(wo), _p(bo))
     return wo, bo
+
+
+def kth_value(x, k, abs_input=False):
+    x = _f(x).reshape(-1)
+    fn = lib().orc_kth_value
+    fn.restype = C.c_float
+    return fn(_p(x), C.c_int64(x.size), C.c_int64(int(k)), C.c_int(int(abs_input)))

@@ -300,3 +300,20 @@ void orc_repvgg_fuse(const float* k3, const float* g3, const float* b3, const fl
     bias_out[c] = (bias3 + bias1) + biasid;
   }
 }
+
+/* ---- percentile observer (extension, no reference counterpart): the k-th smallest value (1-based) of x or |x|,
+ * NaN sorts last like torch.sort / torch.kthvalue, -0 == +0.  O(n log n) by sorting a copy. */
+static int cmp_float_nan_last(const void* a, const void* b) {
+  const float x = *(const float*)a, y = *(const float*)b;
+  const int nx = x != x, ny = y != y;
+  if (nx || ny) return nx - ny;
+  return (x > y) - (x < y);
+}
+float orc_kth_value(const float* x, int64_t n, int64_t k, int abs_input) {
+  float* t = (float*)malloc((size_t)n * sizeof(float));
+  for (int64_t i = 0; i < n; ++i) t[i] = abs_input ? fabsf(x[i]) : x[i];
+  qsort(t, (size_t)n, sizeof(float), cmp_float_nan_last);
+  const float v = t[k - 1];
+  free(t);
+  return v;
+}

@@ -77,3 +77,25 @@ def test_closed_form_gradients_agree_with_autograd(seed):
     dx, ds = CO.fq_backward(x.numpy(), dy.numpy(), scale.numpy(), None, 3, lo, hi, 0.0, channels, inner)
     assert np.array_equal(dx.reshape(-1) == 0, dx_t.reshape(-1).numpy() == 0)
     assert np.all(np.abs(ds - ds_t.double().numpy()) <= 2e-5 * np.abs(ds_t.double().numpy()) + floor.numpy() + 1e-12), seed
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_percentile_oracles_agree(seed):
+    """The extension observer's two CPU statements: torch.kthvalue (oracle/restate.py) and a plain-C sort."""
+    gen = torch.Generator().manual_seed(100 + seed)
+    n = int(torch.randint(1, 5000, (1,), generator=gen))
+    x = torch.randn(n, generator=gen) * 3
+    if seed % 2:
+        x = torch.relu(x)
+    for k in sorted({1, n, (n + 1) // 2, max(1, n - n // 100)}):
+        assert CO.kth_value(x.numpy(), k) == float(x.kthvalue(k)[0])
+        assert CO.kth_value(x.numpy(), k, abs_input=True) == float(x.abs().kthvalue(k)[0])
+    signed = bool(seed % 2 == 0)
+    s, o = R.obs_percentile_tensor(x if signed else x.abs(), 8, signed, 99.0)
+    k_hi = min(n, max(1, math.ceil(0.99 * n)))
+    v = x if signed else x.abs()
+    if signed:
+        assert float(s) == np.float32(CO.kth_value(v.numpy(), k_hi, abs_input=True)) / np.float32(127)
+    else:
+        lo_v, hi_v = CO.kth_value(v.numpy(), n + 1 - k_hi), CO.kth_value(v.numpy(), k_hi)
+        assert float(s) == (np.float32(hi_v) - np.float32(lo_v)) / np.float32(255) and float(o) == lo_v
