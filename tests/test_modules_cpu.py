@@ -161,3 +161,19 @@ def test_compat_aliases_resolve_reference_import_paths():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_weight_group_partition_is_contiguous_and_balanced():
+    """group_weight_quantizers(model, n_groups): forward-ordered, contiguous chunks of about equal parameter bytes
+    (so that data-parallel gradient buckets fill while the backward pass is still running)."""
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.quantize import group_weight_quantizers
+    net = torch.nn.Sequential(*[torch.nn.Conv2d(8, 8, 3) for _ in range(6)], torch.nn.Conv2d(8, 64, 3))
+    quantize_model(net, copy.deepcopy(CFG), None)
+    handle = group_weight_quantizers(net, n_groups=3)
+    chunks = [g._candidates for g in handle.groups]
+    assert [m for c in chunks for m in c] == list(net) and all(chunks)      # forward order, nothing lost
+    sizes = [sum(m.weight.numel() for m in c) for c in chunks]
+    assert 2 <= len(chunks) <= 3 and max(sizes) <= 0.7 * sum(sizes)         # bytes spread over the groups
+    assert len(group_weight_quantizers(net).groups) == 1        # single process: one group
+    handle.remove()
