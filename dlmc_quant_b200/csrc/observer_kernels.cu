@@ -454,6 +454,9 @@ sweep_tensor_kernel(const T* __restrict__ x, int64_t n, const float* __restrict_
     a = warp_sum(a);
     if (lane == 0) part[static_cast<int64_t>(blockIdx.x) * kNC + c] = a;
   }
+  // the partials above are stored by lane 0 of ALL warps: every warp must have stored before thread 0 fences and
+  // draws the ticket (the barrier + thread 0's cumulative fence order all of this CTA's partials before the ticket)
+  __syncthreads();
   if (take_last_ticket(ws_counter(ws), gridDim.x)) {
     if (threadIdx.x < kNC) {
       double a = 0.0;

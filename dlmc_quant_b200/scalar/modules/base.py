@@ -25,6 +25,18 @@ from .function import *  # noqa: F401,F403  (the reference re-exports the Functi
 from .function import fake_quantize
 from ... import dist as qdist
 
+# bumped whenever any layer's quantizer state is invalidated (reset_qparams, load_state_dict): step-level caches
+# (modules/group.py) re-evaluate their membership when it changes
+QPARAMS_EPOCH = [0]
+
+
+def _channel_scale_shape(weight, qtype, axis_of_weight, lead=0):
+    """Shape of a per-channel scale known at initialize() time (so that the Parameter object an optimizer / DDP
+    reducer captured before the first forward is the one the observer fills), or None for per-tensor types."""
+    if 'channel' not in str(qtype) or not isinstance(weight, torch.Tensor):
+        return None
+    return [1] * lead + [weight.shape[axis_of_weight]] + [1] * (weight.dim() - 1 - lead)
+
 
 class QBase(Module):
     __metaclass__ = ABCMeta
@@ -50,11 +62,20 @@ class QBase(Module):
                                                       qconfig['weight']['args']['n_bits'])
         self.in_min_val, self.in_max_val = get_qrange(qconfig['input']['args']['signed'],
                                                       qconfig['input']['args']['n_bits'])
-        dev = self.weight.device if isinstance(getattr(self, 'weight', None), torch.Tensor) else None
-        self.register_parameter('in_scale', torch.nn.Parameter(torch.ones(1, device=dev)))
+        w = getattr(self, 'weight', None)
+        dev = w.device if isinstance(w, torch.Tensor) else None
+        # per-channel types: the scale Parameters are sized here ([1,C,1,1] inputs of an ungrouped layer / [C,1,1,1]
+        # weights with ch_axis 0), so they are never replaced after an optimizer or DDP captured them; the reference
+        # registers [1] and then crashes in copy_ (base.py:116,128)
+        in_shape = wt_shape = None
+        if getattr(self, 'groups', 1) == 1:
+            in_shape = _channel_scale_shape(w, qconfig['input']['type'], 1, lead=1)
+        if qconfig['weight']['args'].get('ch_axis', 0) == 0 and 'output' not in str(qconfig['weight']['type']):
+            wt_shape = _channel_scale_shape(w, qconfig['weight']['type'], 0)
+        self.register_parameter('in_scale', torch.nn.Parameter(torch.ones(in_shape or 1, device=dev)))
         self.register_buffer('in_offset', None)
         self.register_buffer('in_init_state', torch.zeros(1, device=dev))
-        self.register_parameter('wt_scale', torch.nn.Parameter(torch.ones(1, device=dev)))
+        self.register_parameter('wt_scale', torch.nn.Parameter(torch.ones(wt_shape or 1, device=dev)))
         self.register_buffer('wt_offset', None)
         self.register_buffer('wt_init_state', torch.zeros(1, device=dev))
         self._host_init = {'in': None, 'wt': None}      # host mirror of *_init_state (None = unknown)
@@ -65,10 +86,24 @@ class QBase(Module):
         self.in_init_state.fill_(0)
         self.wt_init_state.fill_(0)
         self._host_init = {'in': False, 'wt': False}
+        QPARAMS_EPOCH[0] += 1
 
-    def _load_from_state_dict(self, *args, **kwargs):
-        super()._load_from_state_dict(*args, **kwargs)
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # a checkpoint written after calibration may hold per-channel scales / offsets where this (fresh) module
+        # still has the [1] placeholders: take the checkpoint's shapes instead of failing the strict size check
+        for name in ('in_scale', 'wt_scale'):
+            v = state_dict.get(prefix + name)
+            p = getattr(self, name, None)
+            if isinstance(v, torch.Tensor) and p is not None and v.shape != p.shape:
+                setattr(self, name, torch.nn.Parameter(torch.empty(v.shape, dtype=p.dtype, device=p.device)))
+        for name in ('in_offset', 'wt_offset'):
+            v = state_dict.get(prefix + name)
+            b = getattr(self, name, None)
+            if isinstance(v, torch.Tensor) and (b is None or b.shape != v.shape):
+                setattr(self, name, torch.empty(v.shape, dtype=v.dtype, device=self.in_init_state.device))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
         self._host_init = {'in': None, 'wt': None}       # re-read the flags after a checkpoint load
+        QPARAMS_EPOCH[0] += 1
 
     def _ready(self, which, flag):
         h = getattr(self, '_host_init', None)
@@ -83,8 +118,12 @@ class QBase(Module):
         value = value.detach().to(p.device, torch.float32)
         if value.numel() == p.numel():
             p.data.copy_(value.reshape(p.shape))
-        else:                                            # per-channel observer: allocate to fit
+        else:
+            # observer result of a shape initialize() could not foresee (pixel / grouped-input types): allocate
+            # to fit.  An optimizer / DDP wrapper built BEFORE this first forward still holds the old Parameter -
+            # calibrate (one forward) before building them for such types.
             setattr(self, name, torch.nn.Parameter(value.clone()))
+            QPARAMS_EPOCH[0] += 1
 
     @abstractmethod
     def _forward_func(self, input, weight):

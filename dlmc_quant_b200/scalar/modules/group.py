@@ -16,73 +16,45 @@ import torch
 from ... import _lib
 from ... import functional as F
 from ..._lib import FORM_AFFINE
-from .base import QBase
+from .base import QPARAMS_EPOCH, QBase
 
 __all__ = ["WeightQuantGroup", "GroupHandle", "group_weight_quantizers"]
 
 
 class _GroupedWeightFakeQuant(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, group, n, *tensors):
-        ctx.group, ctx.n = group, n
+    def forward(ctx, plan, n, *tensors):
+        ctx.plan, ctx.n = plan, n             # the plan (membership + tables) this forward ran with
         ctx.save_for_backward(*tensors)
-        return tuple(group._forward(tensors[:n], tensors[n:]))
+        return tuple(plan.forward(tensors[:n]))
 
     @staticmethod
     def backward(ctx, *grads):
         t = ctx.saved_tensors
-        dws, dss = ctx.group._backward(t[:ctx.n], t[ctx.n:], grads)
+        dws, dss = ctx.plan.backward(t[:ctx.n], t[ctx.n:], grads)
         return (None, None, *dws, *dss)
 
 
-class WeightQuantGroup:
-    def __init__(self, model, modules=None):
-        self.model = model
-        self._key = None
-        self._mods = []
-        self._candidates = list(modules) if modules is not None else None
+class _Plan:
+    """Descriptor tables for one fixed membership (same device, same dtype).  Forward stores the plan in its
+    autograd context, so backward uses the tables of the membership it was computed with even if the group
+    re-plans in between (reset_qparams, a new layer becoming ready)."""
 
-    # -- membership ---------------------------------------------------------------------------------------
-    @staticmethod
-    def _eligible(m):
-        if not isinstance(m, QBase) or not m.qconfig['weight']['enable']:
-            return False
-        if not (getattr(m, '_host_init', None) or {}).get('wt'):
-            return False                                       # lazy observer init still pending
-        w, s = m.weight, m.wt_scale
-        if not w.is_cuda or w.dtype not in (torch.float32, torch.bfloat16) or m.wt_offset is None:
-            return False
-        per_channel = s.numel() == w.shape[0] and s.numel() > 1 and tuple(s.shape[1:]) == (1,) * (w.dim() - 1)
-        return (s.numel() == 1 or per_channel) and F.dense_as_is(w, 0)
-
-    def _refresh(self):
-        if self._candidates is None:
-            self._candidates = [m for m in self.model.modules() if isinstance(m, QBase)]
-        if len(self._mods) < len(self._candidates):             # some layers were not initialised yet: look again
-            mods = [m for m in self._candidates if self._eligible(m)]
-        else:
-            mods = self._mods
-        # wt_offset._version: an in-place update of the buffer (load_state_dict) must refresh our fp32 copy of it
-        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(), m.wt_offset._version,
-                     m.weight.stride()) for m in mods)
-        if key == self._key:
-            return
-        self._key, self._mods = key, mods
-        if not mods:
-            return
+    def __init__(self, mods):
+        self.mods = mods
         dev = mods[0].weight.device
         self.device, self.dtype = dev, mods[0].weight.dtype
         n = len(mods)
-        self._arr = (_lib.GroupItem * n)()
-        self._offsets = []                                      # float32 [channels] copies of the offset buffers
+        self.arr = (_lib.GroupItem * n)()
+        self.offsets = []                                       # float32 [channels] copies of the offset buffers
         units, chans, elems = [0], [0], [0]
         for i, m in enumerate(mods):
             w, s = m.weight, m.wt_scale
             c = s.numel()
             off = m.wt_offset.detach().to(device=dev, dtype=torch.float32).reshape(-1)   # a view when already fp32
             off = (off.expand(c) if off.numel() == 1 and c > 1 else off).contiguous()
-            self._offsets.append(off)
-            it = self._arr[i]
+            self.offsets.append(off)
+            it = self.arr[i]
             it.x, it.scale, it.offset = w.data_ptr(), s.data_ptr(), off.data_ptr()
             it.channels, it.inner = c, w.numel() // c
             it.form, it.lo, it.hi = FORM_AFFINE, int(m.wt_min_val), int(m.wt_max_val)
@@ -90,14 +62,14 @@ class WeightQuantGroup:
             units.append(units[-1] + c * ((it.inner + F.GROUP_SEG - 1) // F.GROUP_SEG))
             chans.append(chans[-1] + c)
             elems.append(elems[-1] + w.numel())
-        self._units, self._chans, self._elems = units, chans, elems
-        self._unit_prefix = torch.tensor(units, dtype=torch.int64).to(dev)
-        self._chan_prefix = torch.tensor(chans, dtype=torch.int64).to(dev)
-        self._partials = torch.empty(max(units[-1], 1), dtype=torch.float32, device=dev)
-        self._es = mods[0].weight.element_size()
+        self.units, self.chans, self.elems = units, chans, elems
+        self.unit_prefix = torch.tensor(units, dtype=torch.int64).to(dev)
+        self.chan_prefix = torch.tensor(chans, dtype=torch.int64).to(dev)
+        self.partials = torch.empty(max(units[-1], 1), dtype=torch.float32, device=dev)
+        self.es = mods[0].weight.element_size()
         # descriptor upload without a stream synchronisation: a ring of pinned staging buffers (a blocking
         # .to(device) from pageable memory would drain the GPU twice per step)
-        nbytes = C.sizeof(self._arr)
+        nbytes = C.sizeof(self.arr)
         self._ring = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
         self._ring_ev = [None] * 4
         self._ring_i = 0
@@ -111,31 +83,31 @@ class WeightQuantGroup:
         else:
             self._ring_ev[k].synchronize()                      # four uploads ago: long complete
         pin = self._ring[k]
-        C.memmove(pin.data_ptr(), C.addressof(self._arr), pin.numel())
+        C.memmove(pin.data_ptr(), C.addressof(self.arr), pin.numel())
         self._table.copy_(pin, non_blocking=True)               # stream-ordered before the launch that reads it
         self._ring_ev[k].record()
         return self._table
 
     def _like(self, flat, i, w):
-        return torch.as_strided(flat, w.shape, w.stride(), storage_offset=self._elems[i])
+        return torch.as_strided(flat, w.shape, w.stride(), storage_offset=self.elems[i])
 
     # -- the two launches -----------------------------------------------------------------------------------
-    def _forward(self, weights, scales):
-        flat = torch.empty(self._elems[-1], dtype=self.dtype, device=self.device)
+    def forward(self, weights):
+        flat = torch.empty(self.elems[-1], dtype=self.dtype, device=self.device)
         base = flat.data_ptr()
         for i in range(len(weights)):
-            self._arr[i].y = base + self._elems[i] * self._es
-            self._arr[i].dy = None
-            self._arr[i].dscale = None
+            self.arr[i].y = base + self.elems[i] * self.es
+            self.arr[i].dy = None
+            self.arr[i].dscale = None
         items = self._upload()
         with F._on(self.device):
-            _lib.check(_lib.lib().dlmcq_fq_forward_grouped(items.data_ptr(), self._unit_prefix.data_ptr(), len(weights),
-                                                           self._units[-1], F._dtype_code(flat), F._stream_ptr()))
+            _lib.check(_lib.lib().dlmcq_fq_forward_grouped(items.data_ptr(), self.unit_prefix.data_ptr(), len(weights),
+                                                           self.units[-1], F._dtype_code(flat), F._stream_ptr()))
         return [self._like(flat, i, w) for i, w in enumerate(weights)]
 
-    def _backward(self, weights, scales, grads):
-        flat = torch.empty(self._elems[-1], dtype=self.dtype, device=self.device)
-        ds = torch.empty(self._chans[-1], dtype=torch.float32, device=self.device)
+    def backward(self, weights, scales, grads):
+        flat = torch.empty(self.elems[-1], dtype=self.dtype, device=self.device)
+        ds = torch.empty(self.chans[-1], dtype=torch.float32, device=self.device)
         base, dsb = flat.data_ptr(), ds.data_ptr()
         keep = []
         for i, w in enumerate(weights):
@@ -145,17 +117,63 @@ class WeightQuantGroup:
             elif g.stride() != w.stride() or g.dtype != w.dtype:
                 g = torch.empty_like(w).copy_(g)                # same element order as the weight
             keep.append(g)
-            it = self._arr[i]
-            it.dy, it.y, it.dscale = g.data_ptr(), base + self._elems[i] * self._es, dsb + 4 * self._chans[i]
+            it = self.arr[i]
+            it.dy, it.y, it.dscale = g.data_ptr(), base + self.elems[i] * self.es, dsb + 4 * self.chans[i]
         items = self._upload()
         with F._on(self.device):
-            _lib.check(_lib.lib().dlmcq_fq_backward_grouped(items.data_ptr(), self._unit_prefix.data_ptr(),
-                                                            self._chan_prefix.data_ptr(), len(weights), self._units[-1],
-                                                            self._chans[-1], F._dtype_code(flat),
-                                                            self._partials.data_ptr(), F._stream_ptr()))
+            _lib.check(_lib.lib().dlmcq_fq_backward_grouped(items.data_ptr(), self.unit_prefix.data_ptr(),
+                                                            self.chan_prefix.data_ptr(), len(weights), self.units[-1],
+                                                            self.chans[-1], F._dtype_code(flat),
+                                                            self.partials.data_ptr(), F._stream_ptr()))
         dws = [self._like(flat, i, w) for i, w in enumerate(weights)]
-        dss = [ds[self._chans[i]:self._chans[i + 1]].reshape(s.shape).to(s.dtype) for i, s in enumerate(scales)]
+        dss = [ds[self.chans[i]:self.chans[i + 1]].reshape(s.shape).to(s.dtype) for i, s in enumerate(scales)]
         return dws, dss
+
+
+class WeightQuantGroup:
+    def __init__(self, model, modules=None):
+        self.model = model
+        self._key = None
+        self._plan = None
+        self._epoch = -1
+        self._mods = []
+        self._candidates = list(modules) if modules is not None else None
+
+    # -- membership ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _eligible(m):
+        if not isinstance(m, QBase) or not m.qconfig['weight']['enable']:
+            return False
+        if not (getattr(m, '_host_init', None) or {}).get('wt'):
+            return False                                       # observer init pending (first forward / reset_qparams)
+        w, s = m.weight, m.wt_scale
+        if not w.is_cuda or w.dtype not in (torch.float32, torch.bfloat16) or m.wt_offset is None:
+            return False
+        per_channel = s.numel() == w.shape[0] and s.numel() > 1 and tuple(s.shape[1:]) == (1,) * (w.dim() - 1)
+        return (s.numel() == 1 or per_channel) and F.dense_as_is(w, 0)
+
+    def _refresh(self):
+        if self._candidates is None:
+            self._candidates = [m for m in self.model.modules() if isinstance(m, QBase)]
+        # membership is re-evaluated while layers are still missing and whenever ANY layer's quantizer state was
+        # invalidated since the last look (reset_qparams - the reference's QATTrainer calls it every
+        # update_qparams_period steps, qat_trainer.py:44-48 - or a checkpoint load): such a layer leaves the
+        # group, re-observes its weight on the per-layer path in this forward, and rejoins on the next one
+        if len(self._mods) < len(self._candidates) or self._epoch != QPARAMS_EPOCH[0]:
+            self._epoch = QPARAMS_EPOCH[0]
+            mods = [m for m in self._candidates if self._eligible(m)]
+            if mods:        # one launch = one device and one element type; the rest stays on the per-layer path
+                dev, dt = mods[0].weight.device, mods[0].weight.dtype
+                mods = [m for m in mods if m.weight.device == dev and m.weight.dtype == dt]
+        else:
+            mods = self._mods
+        # wt_offset._version: an in-place update of the buffer (load_state_dict) must refresh our fp32 copy of it
+        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(), m.wt_offset._version,
+                     m.weight.stride(), m.weight.dtype) for m in mods)
+        if key == self._key:
+            return
+        self._key, self._mods = key, mods
+        self._plan = _Plan(mods) if mods else None
 
     # -- hook --------------------------------------------------------------------------------------------------
     def __call__(self, module=None, args=None):
@@ -163,7 +181,8 @@ class WeightQuantGroup:
         if not self._mods:
             return None
         n = len(self._mods)
-        outs = _GroupedWeightFakeQuant.apply(self, n, *[m.weight for m in self._mods], *[m.wt_scale for m in self._mods])
+        outs = _GroupedWeightFakeQuant.apply(self._plan, n, *[m.weight for m in self._mods],
+                                             *[m.wt_scale for m in self._mods])
         for m, o in zip(self._mods, outs):
             m.__dict__['_wq'] = o                                # consumed (popped) by QBase.forward
         return None

@@ -85,12 +85,12 @@ def test_golden_qbase_quantizers(name):
                              ilo, ihi, AFFINE, g=g_i)
     assert torch.allclose(dx.cpu(), c.out["dx"], rtol=1e-6, atol=0)
     assert torch.equal(dx.cpu() == 0, c.out["dx"] == 0)
-    red_close(ds, c.out["grad_in_scale"], abs_sum=floor_of(c.out["d_qx"], ihi, g_i), rtol=2e-5)
+    red_close(ds, c.out["grad_in_scale"], abs_sum=floor_of(c.out["d_qx"], ihi, g_i), rtol=1e-5)
     dw, dsw = F().fq_backward(dev(w), dev(c.out["d_qw"]), dev(c.out["param_wt_scale"]), dev(c.out["buf_wt_offset"]),
                               wlo, whi, AFFINE, g=g_w, ch_axis=wax)
     assert torch.allclose(dw.cpu(), c.out["grad_weight"], rtol=1e-6, atol=0)
     red_close(dsw, c.out["grad_wt_scale"], abs_sum=floor_of(c.out["d_qw"], whi, g_w, rows=w.shape[0] if wax == 0 else None),
-              rtol=2e-5)
+              rtol=1e-5)
 
 
 FUNLSQ = load("funlsq")
@@ -104,7 +104,7 @@ def test_golden_funlsq(name):
     exact(y, c.out["y"], "y")
     dw, ds = F().fq_backward(dev(c.inp["w"]), dev(c.inp["dy"]), dev(c.inp["scale"]), dev(c.inp["offset"]), lo, hi, A1, g=g)
     exact(dw, c.out["dw"], "dw")
-    red_close(ds, c.out["dscale"], abs_sum=floor_of(c.inp["dy"], max(abs(lo), hi), g), rtol=2e-5)
+    red_close(ds, c.out["dscale"], abs_sum=floor_of(c.inp["dy"], max(abs(lo), hi), g), rtol=1e-5)
 
 
 FSPTQ = load("fsptq")
@@ -122,10 +122,10 @@ def test_golden_fsptq_quantizers(name):
     exact(F().fq_forward(dev(w), dev(s_w), None, wlo, whi, SYM, ch_axis=0), c.out["qw"], "qw")
     dx, ds = F().fq_backward(dev(x), dev(c.out["d_qx"]), dev(s_in), dev(o_in), ilo, ihi, ZP)
     assert torch.allclose(dx.cpu(), c.out["dx"], rtol=1e-6, atol=0)
-    red_close(ds, c.out["grad_in_scale"], abs_sum=floor_of(c.out["d_qx"], ihi), rtol=2e-5)
+    red_close(ds, c.out["grad_in_scale"], abs_sum=floor_of(c.out["d_qx"], ihi), rtol=1e-5)
     dw, dsw = F().fq_backward(dev(w), dev(c.out["d_qw"]), dev(s_w), None, wlo, whi, SYM, ch_axis=0)
     assert torch.allclose(dw.cpu(), c.out["grad_weight"], rtol=1e-6, atol=0)
-    red_close(dsw, c.out["grad_wt_scale"], abs_sum=floor_of(c.out["d_qw"], whi, rows=w.shape[0]), rtol=2e-5)
+    red_close(dsw, c.out["grad_wt_scale"], abs_sum=floor_of(c.out["d_qw"], whi, rows=w.shape[0]), rtol=1e-5)
 
 
 @pytest.mark.parametrize("name", sorted(n for n in FSPTQ if "ada" in n))
@@ -144,7 +144,7 @@ def test_golden_adaround(name):
     if "qw_eval" in c.out:
         exact(F().adaround_forward(dev(w), a, dev(s_w), wlo, whi, soft=False), c.out["qw_eval"], "hard rounding")
     dalpha, ds = F().adaround_backward(dev(w), a, dev(c.out["d_qw"]), dev(s_w), wlo, whi)
-    red_close(ds, c.out["grad_wt_scale"], abs_sum=floor_of(c.out["d_qw"], whi, rows=w.shape[0]), rtol=2e-5)
+    red_close(ds, c.out["grad_wt_scale"], abs_sum=floor_of(c.out["d_qw"], whi, rows=w.shape[0]), rtol=1e-5)
     if "grad_alpha" in c.out:
         assert torch.allclose(dalpha.cpu(), c.out["grad_alpha"], rtol=1e-5, atol=1e-9)
 

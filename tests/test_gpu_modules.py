@@ -465,3 +465,45 @@ def test_grouped_weight_quantizers_match_per_layer_path():
         assert sum(len(g._mods) for g in handle.groups) == 3 and len(handle.groups) == (2 if channels_last else 1)
         handle.remove()
         assert torch.equal(a(x), b(x)) and all('_wq' not in m.__dict__ for m in b.modules())
+
+
+def test_grouped_weights_follow_reset_qparams_and_checkpoints():
+    """reset_qparams (QATTrainer calls it every update_qparams_period steps, qat_trainer.py:44-48) must re-run the
+    WEIGHT observers too when the step-level weight group is installed: the layer leaves the group, re-observes on
+    the per-layer path, rejoins; per-channel scale Parameters keep their identity throughout (an optimizer built
+    before the first forward keeps updating them) and a calibrated state_dict loads into a fresh model."""
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.quantize import group_weight_quantizers
+    cfg = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 4, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+    torch.manual_seed(2333)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 8, 3, padding=1)).cuda()
+    quantize_model(net, copy.deepcopy(cfg), None)
+    assert tuple(net[0].wt_scale.shape) == (8, 1, 1, 1) and tuple(net[0].in_scale.shape) == (1,)
+    params_before = {n: p for n, p in net.named_parameters()}
+    handle = group_weight_quantizers(net)
+    x = torch.rand(2, 3, 8, 8, device="cuda")
+    net(x); net(x)
+    assert len(handle.group._mods) == 2
+    assert all(p is params_before[n] for n, p in net.named_parameters()), "scale Parameters were replaced"
+    s_old = net[0].wt_scale.detach().clone()
+    with torch.no_grad():
+        net[0].weight.mul_(3.0)
+    for m in (net[0], net[2]):
+        m.reset_qparams()
+    y = net(x)                                           # re-observes inputs AND weights
+    assert float(net[0].wt_init_state) == 1 and net[0]._host_init['wt'] is True
+    assert torch.allclose(net[0].wt_scale, 3.0 * s_old, rtol=1e-6), "weight observer did not re-run under the group"
+    ref = copy.deepcopy(net)
+    for m in ref.modules():
+        m._forward_pre_hooks.clear()
+        m.__dict__.pop('_wq', None)
+    assert torch.equal(net(x), ref(x)) and len(handle.group._mods) == 2     # rejoined, same result as per layer
+    assert torch.equal(y, ref(x))
+    # a calibrated checkpoint into a fresh (uncalibrated) model
+    fresh = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 8, 3, padding=1)).cuda()
+    quantize_model(fresh, copy.deepcopy(cfg), None)
+    fresh.load_state_dict(ref.state_dict(), strict=True)
+    assert torch.equal(fresh(x), ref(x))
+    handle.remove()

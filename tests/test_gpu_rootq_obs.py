@@ -44,7 +44,7 @@ def test_golden_rootq(name):
     dx, ds = F().rootq_act_backward(dev(x), dev(c.out["d_qx"]), st)
     assert torch.equal(dx.cpu() == 0, c.out["dx"] == 0)
     assert torch.allclose(dx.cpu(), c.out["dx"], rtol=1e-6, atol=0)
-    red_close(ds, c.out["grad_in_scale"], abs_sum=(c.out["d_qx"].abs().sum() * ihi * m * g_i).reshape(1), rtol=2e-5)
+    red_close(ds, c.out["grad_in_scale"], abs_sum=(c.out["d_qx"].abs().sum() * ihi * m * g_i).reshape(1), rtol=1e-5)
 
     ru, rl = _scalar(c.inp["pre_wt_run_upper"]), _scalar(c.inp["pre_wt_run_lower"])
     sw = F().rootq_wt_prepare(_scalar(c.inp["pre_wt_upper"]), _scalar(c.inp["pre_wt_lower"]),
@@ -55,9 +55,9 @@ def test_golden_rootq(name):
     dw, gr = F().rootq_wt_backward(dev(w), dev(c.out["d_qw"]), sw)
     assert torch.allclose(dw.cpu(), c.out["grad_weight"], rtol=1e-5, atol=1e-8)      # north_star: 1e-5 relative
     floor = c.out["d_qw"].abs().sum() * whi * m * g_w
-    red_close(gr[0], c.out["grad_wt_upper"], abs_sum=floor.reshape(1), rtol=2e-5)
-    red_close(gr[1], c.out["grad_wt_lower"], abs_sum=floor.reshape(1), rtol=2e-5)
-    red_close(gr[2], c.out["grad_wt_alpha"], abs_sum=(c.out["d_qw"].abs().sum() * 1e-3).reshape(1), rtol=2e-5)
+    red_close(gr[0], c.out["grad_wt_upper"], abs_sum=floor.reshape(1), rtol=1e-5)
+    red_close(gr[1], c.out["grad_wt_lower"], abs_sum=floor.reshape(1), rtol=1e-5)
+    red_close(gr[2], c.out["grad_wt_alpha"], abs_sum=(c.out["d_qw"].abs().sum() * 1e-3).reshape(1), rtol=1e-5)
 
 
 @pytest.mark.parametrize("wbits,abits,mom,alpha", [(4, 4, 0.1, 0.25), (2, 3, 0.3, 0.6), (8, 8, 0.05, 1.7), (3, 4, 0.1, -0.2)])
@@ -486,7 +486,7 @@ def test_full_size_observer_and_rootq_properties():
     # the 80 sweep sums are additive over a split of the tensor (same candidates: the whole tensor's statistics)
     sse = Fn.sweep_tensor_sse(x, st, 8).double()
     parts = Fn.sweep_tensor_sse(x[:half], st, 8).double() + Fn.sweep_tensor_sse(x[half:], st, 8).double()
-    assert torch.allclose(sse, parts, rtol=2e-5)
+    assert torch.allclose(sse, parts, rtol=1e-5)
     # ... and equal to the eager evaluation of one candidate on the GPU (ops.py:53-61), candidate 17
     r = torch.tensor(1.0 - 0.01 * 17, dtype=torch.float32, device="cuda")
     c_hi, c_lo = r * st[0, 1], r * st[0, 0]

@@ -124,6 +124,30 @@ def test_state_dict_round_trip_resets_host_flags():
     assert m._host_init == {"in": None, "wt": None} and float(m.in_init_state) == 1.0
 
 
+def test_per_channel_scales_are_sized_at_initialize_and_load_from_checkpoints():
+    """Per-channel types: the scale Parameters get their final shape in initialize() (the reference registers [1] and
+    crashes in copy_, base.py:116,128), so an optimizer built before the first forward holds the right objects; a
+    calibrated checkpoint (per-channel scales, offset buffers present) loads strictly into a fresh model."""
+    cfg = copy.deepcopy(CFG)
+    cfg["weight"] = {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}}
+    cfg["input"] = {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": False}}
+    net = Net()
+    quantize_model(net, copy.deepcopy(cfg), None)
+    assert tuple(net.conv1.wt_scale.shape) == (8, 1, 1, 1) and tuple(net.conv1.in_scale.shape) == (1, 3, 1, 1)
+    assert tuple(net.fc.wt_scale.shape) == (10, 1) and tuple(net.fc.in_scale.shape) == (1, 4)
+    # a calibrated state dict from a model whose placeholders were [1]
+    net2 = Net()
+    quantize_model(net2, copy.deepcopy(CFG), None)
+    sd = net.state_dict()
+    for name, mod in net.named_modules():
+        if isinstance(mod, modules.QBase):
+            sd[name + ".in_offset"] = torch.zeros_like(mod.in_scale)
+            sd[name + ".wt_offset"] = torch.zeros_like(mod.wt_scale)
+    net2.load_state_dict(sd, strict=True)
+    assert tuple(net2.conv1.wt_scale.shape) == (8, 1, 1, 1) and tuple(net2.conv1.wt_offset.shape) == (8, 1, 1, 1)
+    assert tuple(net2.fc.in_offset.shape) == (1, 4)
+
+
 def test_channel_axis_inference():
     w = torch.zeros(8, 4, 3, 3)
     assert infer_ch_axis(w, torch.ones(1)) is None and infer_ch_axis(w, torch.tensor(1.0)) is None
