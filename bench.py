@@ -281,18 +281,24 @@ def run_ours(args, rank, world, device):
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
 
     e2e = run_e2e(args, wl, rank, world, device)
+    launches_total = wl.launches_per_step * args.steps
+    cfg_elems, cfg_act_elems, cfg_ds = wl.elems, wl.act_elems, wl.dscale.numel()
+    del wl
+    torch.cuda.empty_cache()
+    qat = run_qat(args, rank, world, device)
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "resnet50_w4a4_qat_quantizers (54 layers: A4 per-tensor act + W4 per-channel weight, "
                                   "QBase form, fwd+bwd)", "per_gpu_batch": args.batch, "image": "3x224x224",
-                      "elements_per_step_per_gpu": wl.elems, "l2": "working set %.1f GB per GPU, far larger than the "
-                      "126 MB L2; no flush needed" % (wl.act_elems * 16 / 1e9), "cuda_graphs": True,
-                      "collective": "all_reduce(SUM) of %d scale-grad floats per step" % wl.dscale.numel() if world > 1
+                      "elements_per_step_per_gpu": cfg_elems, "l2": "working set %.1f GB per GPU, far larger than the "
+                      "126 MB L2; no flush needed" % (cfg_act_elems * 16 / 1e9), "cuda_graphs": True,
+                      "collective": "all_reduce(SUM) of %d scale-grad floats per step" % cfg_ds if world > 1
                       else "none (1 GPU)"},
            "elements_per_s": round(total_elems / (ms * 1e-3), 1),
            "images_per_s_quantizer_path": round(args.batch * world * args.steps / (ms * 1e-3), 1),
-           "gpu_launches": wl.launches_per_step * args.steps, "roofline": roofline, "clocks": clocks, "e2e": e2e}
+           "gpu_launches": launches_total, "roofline": roofline, "clocks": clocks, "e2e": e2e,
+           "qat_images_per_s": qat}
     if rank == 0:
         out["cpu_baseline"] = cpu_reference(sample_batch=1, passes=3) if world == 1 else None
         print(json.dumps(out), flush=True)
@@ -356,6 +362,171 @@ def run_e2e(args, wl, rank, world, device):
             "ms_per_step": round(dt / steps * 1e3, 2), "host_buffers": "pinned, one set sized to the largest layer, reused by all layers",
             "api": "dlmcq_host_fq_forward_backward_async per layer + one dlmcq_host_synchronize (activations); H2D/grouped launch/D2H (weights)"}
 
+
+
+# ------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: end-to-end ResNet-50 W4A4 QAT images/s
+# ------------------------------------------------------------------------------------------
+QAT_CFG = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": W_BITS, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": A_BITS, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+
+
+def _eager_reference_modules(model):
+    """The `eager` arm: every Conv2d / Linear wrapped so that its input and weight go through the reference's own
+    eager op chain on the SAME GPU - a restatement, for timing only, of dlmc/quantization/scalar/modules/base.py:
+    82-102,106-133 with utils.py:24-32 (grad_scale, round_pass) and the min/max observers of ops.py:20-34,121-140,
+    including the reference's per-forward `if self.in_init_state == 0` device-to-host checks (base.py:82,107).
+    Per-channel wt_scale is pre-shaped [C,1,1,1] (the only way the reference runs per-channel)."""
+    import torch.nn as nn
+    import torch.nn.functional as TF
+
+    def grad_scale(x, scale):                  # utils.py:24-27
+        y_grad = x * scale
+        return (x - y_grad).detach() + y_grad
+
+    def round_pass(x):                         # utils.py:29-32
+        return (x.round() - x).detach() + x
+
+    class EagerQ(nn.Module):
+        def __init__(self, base):
+            super().__init__()
+            self.base = base
+            dev = base.weight.device
+            self.in_scale = nn.Parameter(torch.ones(1, device=dev))
+            self.wt_scale = nn.Parameter(torch.ones([base.weight.shape[0]] + [1] * (base.weight.dim() - 1), device=dev))
+            self.register_buffer("in_init_state", torch.zeros(1, device=dev))
+            self.register_buffer("wt_init_state", torch.zeros(1, device=dev))
+            self.in_max, self.wt_max = 2 ** A_BITS - 1, 2 ** (W_BITS - 1) - 1
+
+        def forward(self, x):
+            w = self.base.weight
+            if self.in_init_state == 0:                                             # base.py:82 (D2H sync)
+                mn, mx = x.detach().min(), x.detach().max()                         # ops.py:26-33
+                self.in_scale.data.copy_((mx - mn) / self.in_max)
+                self.in_offset = mn
+                self.in_init_state.fill_(1)
+            g_i = 1 / math.sqrt(x.numel() * self.in_max)                            # base.py:96
+            s = grad_scale(self.in_scale, g_i)
+            x = round_pass(((x - self.in_offset) / s).clamp(0, self.in_max)) * s + self.in_offset   # base.py:102
+            if self.wt_init_state == 0:                                             # base.py:107 (D2H sync)
+                absmax = w.detach().reshape(w.shape[0], -1).abs().max(dim=1)[0]     # ops.py:121-127
+                self.wt_scale.data.copy_((absmax / self.wt_max).reshape(self.wt_scale.shape))
+                self.wt_offset = torch.zeros_like(self.wt_scale)
+                self.wt_init_state.fill_(1)
+            g_w = 1 / math.sqrt(w.numel() * self.wt_max)                            # base.py:131
+            ws = grad_scale(self.wt_scale, g_w)
+            wq = round_pass(((w - self.wt_offset) / ws).clamp(-self.wt_max, self.wt_max)) * ws + self.wt_offset
+            b = self.base
+            if isinstance(b, nn.Conv2d):
+                return TF.conv2d(x, wq, b.bias, b.stride, b.padding, b.dilation, b.groups)
+            return TF.linear(x, wq, b.bias)
+
+    for _, m in list(model.named_modules()):
+        for cname, c in list(m.named_children()):
+            if isinstance(c, (nn.Conv2d, nn.Linear)):
+                setattr(m, cname, EagerQ(c))
+    return model
+
+
+def _qat_arm(arm, channels_last, batch, steps, rank, world, device):
+    """One arm of the QAT benchmark, with the reference harness's methodology (example/benchmark/benchmark.py:168-197:
+    SGD nesterov lr 0.01 wd 5e-4 momentum 0.9, cross-entropy, 2 warm-up steps, wall clock over the remaining steps,
+    images = batch * n_gpu per step; benchmark.yaml:14 cudnn.benchmark on; DDP for N > 1)."""
+    import copy
+    import torch.distributed as dist
+    import torch.nn as nn
+    import torchvision
+    torch.manual_seed(2333)
+    model = torchvision.models.resnet50().to(device)
+    if arm in ("ours", "ours_fused"):
+        from dlmc_quant_b200 import quantize_model
+        quantize_model(model, copy.deepcopy(QAT_CFG), None)
+    elif arm == "eager":
+        _eager_reference_modules(model)
+    x = torch.randn(batch, 3, 224, 224, device=device)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    t = torch.randint(0, 1000, (batch,), device=device)
+    model.train()
+    with torch.no_grad():
+        model(x[:8])                    # lazy observer init (all arms: same warm state) before DDP / the optimizer
+    fused_sites = None
+    if arm in ("ours", "ours_fused"):
+        from dlmc_quant_b200.quantize import group_weight_quantizers
+        group_weight_quantizers(model)  # all 54 weight tensors: one launch per direction
+    if arm == "ours_fused":
+        from dlmc_quant_b200.fuse import fuse_bn_act_quant
+        h = fuse_bn_act_quant(model)
+        fused_sites = {"blocks": h.blocks, "sequentials": h.sequentials, "batchnorms": h.batchnorms}
+    if world > 1:
+        model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=5e-4)
+    crit = nn.CrossEntropyLoss()
+
+    def step():
+        opt.zero_grad()
+        loss = crit(model(x), t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = step()
+    lv = float(loss)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    clocks = sampler.stop()
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt)
+    out = {"images_per_s": round(batch * world * steps / dt, 1), "ms_per_step": round(dt / steps * 1e3, 2),
+           "loss_finite": math.isfinite(lv), "sm_mhz": clocks["sm_mhz"], "reasons": clocks["reasons"]}
+    if fused_sites:
+        out["fused_sites"] = fused_sites
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_qat(args, rank, world, device):
+    """ResNet-50 W4A4 QAT images/s for four arms on the same GPU(s): un-quantised, the reference's eager quantizer
+    chain, this package (fused quantizer kernels), this package with the quantizers fused into their producers."""
+    if args.no_qat:
+        return None
+    torch.backends.cudnn.benchmark = True
+    res = {"model": "torchvision resnet50, W4 per-channel (minmax_channel) / A4 per-tensor (minmax_tensor) QBase QAT, "
+                    "fp32 tensors (cuDNN TF32 convolutions: torch default)",
+           "methodology": "example/benchmark/benchmark.py:168-197 (SGD nesterov, 2 warm-up steps, wall clock, "
+                          "images = batch * n_gpu * steps / s), synthetic 3x224x224",
+           "per_gpu_batch": args.qat_batch, "n_gpus": world, "steps": args.qat_steps,
+           "parallelism": "DistributedDataParallel (bucketed ncclAllReduce of 25.6 M weight gradients + scale "
+                          "gradients per step)" if world > 1 else "single GPU",
+           "arms": {"fp32": "un-quantised model", "eager": "reference eager op chain + autograd on this GPU",
+                    "ours": "dlmc_quant_b200.quantize_model + group_weight_quantizers",
+                    "ours_fused": "ours + fuse_bn_act_quant (BatchNorm+ReLU+next layer's input fake-quant in one "
+                                  "kernel per direction; channels_last only)"}}
+    for fmt, cl, arms in (("nchw", False, ("fp32", "eager", "ours")),
+                          ("channels_last", True, ("fp32", "eager", "ours", "ours_fused"))):
+        res[fmt] = {}
+        for arm in arms:
+            try:
+                res[fmt][arm] = _qat_arm(arm, cl, args.qat_batch, args.qat_steps, rank, world, device)
+            except Exception as e:                      # an arm that fails must not take the headline metric down
+                res[fmt][arm] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+    return res
 
 # ------------------------------------------------------------------------------------------
 def cpu_reference(sample_batch=1, passes=3):
@@ -454,6 +625,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=1)
+    ap.add_argument("--no-qat", action="store_true", help="skip the ResNet-50 QAT images/s arms")
+    ap.add_argument("--qat-steps", type=int, default=10)
+    ap.add_argument("--qat-batch", type=int, default=128, help="per-GPU batch of the QAT arms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

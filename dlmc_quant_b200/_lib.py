@@ -59,6 +59,14 @@ class FinalizeItem(C.Structure):
     _fields_ = [("partials", C.c_void_p), ("dscale", C.c_void_p)]
 
 
+class BnqDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("channels", C.c_int64), ("dtype", C.c_int32), ("flags", C.c_int32),
+                ("eps", C.c_float), ("momentum", C.c_float)]
+
+
+BNQ_TRAINING, BNQ_RELU, BNQ_RESIDUAL = 1, 2, 4
+
+
 class DlmcqError(RuntimeError):
     pass
 
@@ -113,6 +121,10 @@ SIGNATURES = {
     "dlmcq_fq_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
     "dlmcq_fq_backward_grouped": (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),
     "dlmcq_fold_grouped": (_I, [_P, _P, _I, _L, _P]),
+    "dlmcq_bnq_workspace_bytes": (_Z, [C.POINTER(BnqDesc)]),
+    "dlmcq_bnq_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(BnqDesc), _QP, _P, _Z, _P]),
+    "dlmcq_bnq_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(BnqDesc), _QP, _P, _Z,
+                                _P]),
     "dlmcq_host_staging_bytes": (_Z, [_L, _I]),
     "dlmcq_host_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
     "dlmcq_host_fq_forward_backward_async": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),

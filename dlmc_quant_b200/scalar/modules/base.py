@@ -135,41 +135,58 @@ class QBase(Module):
         count = t.numel() * qdist.world_size()
         return F.absmean_from_stats(stats, count, 2.0, math.sqrt(qmax), 0), torch.zeros(1, device=t.device)
 
-    def forward(self, input):
+    def _quant_input(self, input):
+        """base.py:82-102: lazy observer init, then the fused input fake-quant."""
         q = self.qconfig
-        if q['input']['enable']:
-            if not self._ready('in', self.in_init_state):
-                if fnmatch(q['input']['type'], 'LSQ'):
-                    scale, self.in_offset = self._lsq_init(input, self.in_max_val)
-                else:
-                    scale, offset = get_qparams_tensor(input.detach(), qtype=q['input']['type'], **q['input']['args'])
-                    self.in_offset = offset.detach().float()
-                self._set_scale('in_scale', scale)
-                self.in_init_state.fill_(1)
-                self._host_init['in'] = True
-            g_i = 1 / math.sqrt(input.numel() * self.in_max_val)                       # base.py:96
-            input = fake_quantize(input, self.in_scale, self.in_offset, self.in_min_val, self.in_max_val,
-                                  FORM_AFFINE, g_i)                                      # base.py:97,102
-        weight = self.weight
+        if not self._ready('in', self.in_init_state):
+            if fnmatch(q['input']['type'], 'LSQ'):
+                scale, self.in_offset = self._lsq_init(input, self.in_max_val)
+            else:
+                scale, offset = get_qparams_tensor(input.detach(), qtype=q['input']['type'], **q['input']['args'])
+                self.in_offset = offset.detach().float()
+            self._set_scale('in_scale', scale)
+            self.in_init_state.fill_(1)
+            self._host_init['in'] = True
+        g_i = 1 / math.sqrt(input.numel() * self.in_max_val)                       # base.py:96
+        return fake_quantize(input, self.in_scale, self.in_offset, self.in_min_val, self.in_max_val,
+                             FORM_AFFINE, g_i)                                      # base.py:97,102
+
+    def _quant_weight(self, input):
+        """base.py:106-133 (`input` is only used by the output-aware observers)."""
+        q = self.qconfig
         grouped = self.__dict__.pop('_wq', None)         # set by group_weight_quantizers' pre-hook for this step
-        if grouped is not None and q['weight']['enable']:
-            weight = grouped
-        elif q['weight']['enable']:
-            if not self._ready('wt', self.wt_init_state):
-                if fnmatch(q['weight']['type'], '*output*'):
-                    scale, offset = get_qparams_output(input.detach(), self.weight.detach(), self,
-                                                       qtype=q['weight']['type'], **q['weight']['args'])
-                    self.wt_offset = offset.detach().float()
-                elif fnmatch(q['weight']['type'], 'LSQ'):
-                    scale, self.wt_offset = self._lsq_init(self.weight, self.wt_max_val)
-                else:
-                    scale, offset = get_qparams_tensor(self.weight.detach(), qtype=q['weight']['type'],
-                                                       **q['weight']['args'])
-                    self.wt_offset = offset.detach().float()
-                self._set_scale('wt_scale', scale)
-                self.wt_init_state.fill_(1)
-                self._host_init['wt'] = True
-            g_w = 1 / math.sqrt(self.weight.numel() * self.wt_max_val)                  # base.py:131
-            weight = fake_quantize(self.weight, self.wt_scale, self.wt_offset, self.wt_min_val, self.wt_max_val,
-                                   FORM_AFFINE, g_w)                                     # base.py:132-133
-        return self._forward_func(input, weight)
+        if not q['weight']['enable']:
+            return self.weight
+        if grouped is not None:
+            return grouped
+        if not self._ready('wt', self.wt_init_state):
+            if fnmatch(q['weight']['type'], '*output*'):
+                scale, offset = get_qparams_output(input.detach(), self.weight.detach(), self,
+                                                   qtype=q['weight']['type'], **q['weight']['args'])
+                self.wt_offset = offset.detach().float()
+            elif fnmatch(q['weight']['type'], 'LSQ'):
+                scale, self.wt_offset = self._lsq_init(self.weight, self.wt_max_val)
+            else:
+                scale, offset = get_qparams_tensor(self.weight.detach(), qtype=q['weight']['type'],
+                                                   **q['weight']['args'])
+                self.wt_offset = offset.detach().float()
+            self._set_scale('wt_scale', scale)
+            self.wt_init_state.fill_(1)
+            self._host_init['wt'] = True
+        g_w = 1 / math.sqrt(self.weight.numel() * self.wt_max_val)                  # base.py:131
+        return fake_quantize(self.weight, self.wt_scale, self.wt_offset, self.wt_min_val, self.wt_max_val,
+                             FORM_AFFINE, g_w)                                      # base.py:132-133
+
+    def forward_prequantized(self, input_q):
+        """The layer on an input that its producer already fake-quantised with THIS layer's in_scale / in_offset
+        (dlmc_quant_b200.fuse: BatchNorm + ReLU + this quantizer run as one kernel)."""
+        return self._forward_func(input_q, self._quant_weight(input_q))
+
+    def forward(self, input):
+        if self.qconfig['input']['enable']:
+            pre = getattr(input, '_dlmcq_q', None)       # (consumer, a_q) attached by a fused producer (fuse.py)
+            if pre is not None and pre[0] is self:
+                input = pre[1]
+            else:
+                input = self._quant_input(input)
+        return self._forward_func(input, self._quant_weight(input))

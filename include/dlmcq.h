@@ -346,6 +346,49 @@ typedef struct {
 int dlmcq_fold_grouped(const dlmcq_fold_item* items, const int64_t* chan_prefix, int n_items,
                        int64_t total_channels, void* stream);
 
+/* ---- activation fake-quant fused into its producer ----------------
+ * BatchNorm (+ residual add) (+ ReLU) -> QBase input fake-quant, for CHANNELS-LAST tensors: a dense [rows, channels]
+ * matrix, channels innermost (a channels_last NCHW activation with rows = N*H*W, or a [N, C] matrix).  Replaces the
+ * chain nn.BatchNorm2d -> (out += identity) -> nn.ReLU -> QBase.forward's input branch
+ * (dlmc/quantization/scalar/modules/base.py:96-102, reached from modules/conv.py:13-19) and its autograd:
+ *     z = (x - mean) * (gamma * invstd) + beta [+ identity];   a = relu(z) or z;
+ *     a_q = FORM_AFFINE fake-quant of a with the CONSUMER layer's in_scale / in_offset (per-tensor)
+ * forward : training -> batch statistics (biased variance for normalising, unbiased for the running buffer, momentum
+ *           update in place, exactly nn.BatchNorm2d); eval -> the running buffers.  save_mean / save_invstd
+ *           [channels] are written either way and are what the backward call needs.  a_out and q_out may each be
+ *           NULL (both NULL: statistics only).  qp is required when q_out is given: form must be FORM_AFFINE,
+ *           scale / offset point to ONE float each.
+ * backward: d_a = gradient w.r.t. a_out (NULL if none), d_q = gradient w.r.t. q_out (NULL if none) ->
+ *           dx, dgamma[channels], dbeta[channels] (either may be NULL), dscale[1] (with d_q; includes the factor g).
+ *           With DLMCQ_BNQ_RESIDUAL the saved plain output a_saved is read instead of recomputing a (z contains
+ *           the identity), and dz_out - the gradient of z, which IS the gradient of the identity input - is written.
+ * Given a, a_q is bit-identical to dlmcq_fq_forward(a); BatchNorm itself is floating-point reduction work and agrees
+ * with a library batch-norm within reduction-order tolerance.  Deterministic (fixed-order reductions, no atomics).
+ * channels must be a multiple of 4 (fp32) / 8 (bf16) and all tensor pointers 16-byte aligned, otherwise
+ * DLMCQ_EUNSUPPORTED / DLMCQ_EALIGN (callers then run the unfused chain).  Workspace: dlmcq_bnq_workspace_bytes(),
+ * no initialisation needed. */
+#define DLMCQ_BNQ_TRAINING 1
+#define DLMCQ_BNQ_RELU 2
+#define DLMCQ_BNQ_RESIDUAL 4
+typedef struct {
+  int64_t rows;     /* N*H*W */
+  int64_t channels; /* C (innermost) */
+  int32_t dtype;    /* dlmcq_dtype of x / identity / a / a_q / gradients */
+  int32_t flags;    /* DLMCQ_BNQ_* */
+  float eps;        /* nn.BatchNorm2d.eps */
+  float momentum;   /* nn.BatchNorm2d.momentum (training) */
+} dlmcq_bnq_desc;
+size_t dlmcq_bnq_workspace_bytes(const dlmcq_bnq_desc* desc);
+int dlmcq_bnq_forward(const void* x, const void* identity, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                      void* a_out, void* q_out, const dlmcq_bnq_desc* desc, const dlmcq_qparams* qp,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int dlmcq_bnq_backward(const void* x, const void* a_saved, const void* d_a, const void* d_q,
+                       const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                       void* dx, void* dz_out, float* dgamma, float* dbeta, float* dscale,
+                       const dlmcq_bnq_desc* desc, const dlmcq_qparams* qp, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------
  * Same arithmetic as dlmcq_fq_forward + dlmcq_fq_backward on a per-tensor-scale tensor that
  * lives in (pinned) HOST memory: x, dy in; y, dx and dscale out.  Chunks are pipelined

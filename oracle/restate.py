@@ -105,6 +105,21 @@ def fq_affine_fwd_bwd(x, scale, offset, lo, hi, g, dy):
     return y.detach(), dx, ds
 
 
+def bn_act_fq_chain(x, gamma, beta, running_mean, running_var, training, momentum, eps, identity, relu,
+                    scale, offset, lo, hi, g):
+    """The producer chain the fused kernels replace, as the reference runs it: the model's
+    nn.BatchNorm2d -> `out += identity` -> nn.ReLU (e.g. model/classification/cifarresnet_large.py:24-46,
+    torchvision Bottleneck.forward) followed by QBase.forward's input branch, modules/base.py:96-102.
+    Returns (a, a_q); a_q is None when scale is None.  running_* are updated in place like nn.BatchNorm2d."""
+    z = F.batch_norm(x, running_mean, running_var, gamma, beta, training, momentum, eps)
+    if identity is not None:
+        z = z + identity
+    a = F.relu(z) if relu else z
+    if scale is None:
+        return a, None
+    return a, fq_affine(a, scale, offset, lo, hi, g)
+
+
 def lsq_init_scale(x, qmax):
     """modules/base.py:84,119 - LSQ initial scale 2*mean|x|/sqrt(qmax)."""
     return 2 * x.detach().abs().mean() / math.sqrt(qmax)
