@@ -482,7 +482,7 @@ def _qat_arm(arm, channels_last, batch, steps, rank, world, device):
     t0 = time.perf_counter()
     for _ in range(steps):
         loss = step()
-    lv = float(loss)
+    lv = float(loss.detach())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -517,10 +517,15 @@ def run_qat(args, rank, world, device):
                     "ours": "dlmc_quant_b200.quantize_model + group_weight_quantizers",
                     "ours_fused": "ours + fuse_bn_act_quant (BatchNorm+ReLU+next layer's input fake-quant in one "
                                   "kernel per direction; channels_last only)"}}
+    only = set(args.qat_arms.split(",")) if args.qat_arms else None
     for fmt, cl, arms in (("nchw", False, ("fp32", "eager", "ours")),
                           ("channels_last", True, ("fp32", "eager", "ours", "ours_fused"))):
+        if only and fmt not in only and not (only & set(arms)):
+            continue
         res[fmt] = {}
         for arm in arms:
+            if only and arm not in only and fmt not in only:
+                continue
             try:
                 res[fmt][arm] = _qat_arm(arm, cl, args.qat_batch, args.qat_steps, rank, world, device)
             except Exception as e:                      # an arm that fails must not take the headline metric down
@@ -627,6 +632,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1)
     ap.add_argument("--no-qat", action="store_true", help="skip the ResNet-50 QAT images/s arms")
     ap.add_argument("--qat-steps", type=int, default=10)
+    ap.add_argument("--qat-arms", default="", help="comma list restricting the QAT arms / formats (diagnostic), e.g. "
+                                                   "'channels_last' or 'fp32,ours_fused'")
+    ap.add_argument("--qat-only", action="store_true", help="skip the kernel metric; print only the QAT arms (diagnostic)")
     ap.add_argument("--qat-batch", type=int, default=128, help="per-GPU batch of the QAT arms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -645,7 +653,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     try:
-        run_ours(args, rank, world, device)
+        if args.qat_only:
+            q = run_qat(args, rank, world, device)
+            if rank == 0:
+                print(json.dumps({"qat_images_per_s": q}), flush=True)
+        else:
+            run_ours(args, rank, world, device)
     finally:
         if world > 1:
             import torch.distributed as dist

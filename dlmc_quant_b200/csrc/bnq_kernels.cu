@@ -24,6 +24,8 @@
 // same `fq_vec<FORM_AFFINE>` code as the stand-alone kernels: given the BatchNorm output `a` (which the kernel
 // can also write), a_q is BIT-IDENTICAL to dlmcq_fq_forward(a) - that is how parity with the reference's
 // quantizer chain is carried over (tests: fused a_q == fq_forward(fused a)).
+#include <stdlib.h>
+
 #include "fq_math.cuh"
 
 namespace dlmcq {
@@ -54,7 +56,7 @@ static inline BnqGeom make_bnq_geom(int64_t rows, int64_t C) {
   g.gy = (g.cv + g.txw - 1) / g.txw;
   const int64_t rpp = static_cast<int64_t>(g.ty) * kBnqU;
   const int64_t passes = (rows + rpp - 1) / rpp;
-  int64_t target = static_cast<int64_t>(num_sms()) * 8 / g.gy;   // ~8 resident CTAs per SM
+  int64_t target = static_cast<int64_t>(num_sms()) * 4 / g.gy;   // 4 resident CTAs per SM (64 registers per thread)
   if (target < 1) target = 1;
   int64_t cap = rows / 16;   // every CTA leaves 2*C partial floats behind: keep them well below the tensor itself
   if (cap < 1) cap = 1;
@@ -159,6 +161,8 @@ bnq_stats_kernel(const T* __restrict__ x, BnqGeom gm, float* __restrict__ part) 
   constexpr int VN = V::N;
   extern __shared__ __align__(16) float sm[];
   BNQ_THREAD_COORDS();
+  pdl_wait();          // x is the output of the previous operation on the stream
+  pdl_trigger();
   const raw* xv = reinterpret_cast<const raw*>(x);
   float s1[VN], s2[VN], k[VN];
 #pragma unroll
@@ -192,28 +196,29 @@ bnq_stats_kernel(const T* __restrict__ x, BnqGeom gm, float* __restrict__ part) 
   bnq_store_partials<VN>(s1, s2, sm, gm, tx, ty, col, active, part);
 }
 
-// one CTA per 32 channels: 8 thread rows stride over the nbx partials (coalesced over channels), fixed-order fold
+// one WARP per channel: the lanes stride over the nbx per-CTA partials (independent loads, all in flight at once),
+// accumulate in double and fold with a fixed shuffle tree - a few microseconds whatever the partial count (a thread
+// per channel walking the partials serially took 25-50 us, more than the statistics pass itself)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bnq_stats_finalize_kernel(const T* __restrict__ x, const float* __restrict__ part, BnqGeom gm, float eps, float momentum,
                           float* __restrict__ running_mean, float* __restrict__ running_var,
                           float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  __shared__ double sh[2][8][32];
-  const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  double a1 = 0.0, a2 = 0.0;
-  if (c < gm.C) {
-    for (int b = by; b < gm.nbx; b += 8) {
-      a1 += static_cast<double>(part[static_cast<size_t>(b) * 2 * gm.C + c]);
-      a2 += static_cast<double>(part[static_cast<size_t>(b) * 2 * gm.C + gm.C + c]);
-    }
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  pdl_wait();          // the partials come from the statistics kernel launched just before
+  pdl_trigger();
+  if (c >= gm.C) return;
+  double t1 = 0.0, t2 = 0.0;
+  const size_t stride = 2 * static_cast<size_t>(gm.C);
+#pragma unroll 4
+  for (int b = lane; b < gm.nbx; b += 32) {
+    t1 += static_cast<double>(__ldcg(part + b * stride + c));
+    t2 += static_cast<double>(__ldcg(part + b * stride + gm.C + c));
   }
-  sh[0][by][cx] = a1;
-  sh[1][by][cx] = a2;
-  __syncthreads();
-  if (by == 0 && c < gm.C) {
-    double t1 = 0.0, t2 = 0.0;
-    for (int r = 0; r < 8; ++r) { t1 += sh[0][r][cx]; t2 += sh[1][r][cx]; }
+  t1 = warp_sum(t1);
+  t2 = warp_sum(t2);
+  if (lane == 0) {
     const double n = static_cast<double>(gm.rows);
     const double k = static_cast<double>(to_f32<T>(x[c]));
     const double m1 = t1 / n;
@@ -242,8 +247,149 @@ __global__ void bnq_eval_prepare_kernel(const float* __restrict__ running_mean, 
 }
 
 // ---------------------------------------------------------------------------------------
+// packed fast path shared by the apply / reduce / dx kernels.
+//
+// All arithmetic is issued as f32x2 instructions (FADD2 / FMUL2 / FFMA2: two IEEE-RN results per issue slot): with
+// scalar code these kernels are issue-bound, not HBM-bound (measured: 30 - 57 thread-instructions per element, 0.50 -
+// 0.81 of the HBM roofline; ncu summary in profiles/).  The quantizer stage is, operation for operation, the packed
+// branch of fq_vec / fq_vec_bwd<FORM_AFFINE> (fq_math.cuh), so a_q stays bit-identical to the stand-alone kernel's.
+// Domain: that branch needs |a - offset| <= 2^60.  The test here is on the RAW inputs and per thread iteration (one
+// FMNMX per element, one branch per 16-32 elements): all |x|, |identity| <= 2^20 together with per-channel constants
+// of magnitude <= 2^20 bound |a - offset| by 2^43.  Anything else (huge activations, NaN-free or not) takes the
+// generic per-vector code, which carries the same guards as the stand-alone kernels.
+// ---------------------------------------------------------------------------------------
+constexpr float kBnqSafe = 0x1p20f;
+
+template <int VN>
+struct BnCh2 {
+  float2 nmean[VN / 2], a[VN / 2], b[VN / 2], istd[VN / 2];
+  bool safe;
+};
+template <int VN>
+__device__ __forceinline__ void load_bnch2(BnCh2<VN>& c2, const BnCh<VN>& c) {
+  float m = 0.f;
+#pragma unroll
+  for (int e = 0; e < VN; e += 2) {
+    c2.nmean[e / 2] = make_float2(-c.mean[e], -c.mean[e + 1]);
+    c2.a[e / 2] = make_float2(c.a[e], c.a[e + 1]);
+    c2.b[e / 2] = make_float2(c.b[e], c.b[e + 1]);
+    c2.istd[e / 2] = make_float2(c.istd[e], c.istd[e + 1]);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(c.mean[e]), fabsf(c.mean[e + 1])), fmaxf(fabsf(c.a[e]), fabsf(c.a[e + 1]))));
+    m = fmaxf(m, fmaxf(fabsf(c.b[e]), fabsf(c.b[e + 1])));
+  }
+  // NaN constants are ignored by fmaxf and simply flow through the fast path (as NaN data does)
+  c2.safe = m <= kBnqSafe;
+}
+
+struct QuantK {
+  ChanParams p;
+  float2 r2, ns2, off2, noff2;
+  float lo, hi;
+  bool fast;
+};
+__device__ __forceinline__ QuantK make_quantk(const float* scale, const float* offset, float g, float lo, float hi) {
+  QuantK k;
+  k.p = make_params<DLMCQ_FORM_AFFINE>(scale, offset, 0, g, lo, hi);
+  k.r2 = make_float2(k.p.fd.r, k.p.fd.r);
+  k.ns2 = make_float2(-k.p.fd.s, -k.p.fd.s);
+  k.off2 = make_float2(k.p.off, k.p.off);
+  k.noff2 = make_float2(-k.p.off, -k.p.off);
+  k.lo = lo;
+  k.hi = hi;
+  k.fast = k.p.fd.ok && fabsf(k.p.off) <= kBnqSafe;
+  return k;
+}
+
+// relu as max.NaN against `floor` (0, or -inf for "no ReLU"): one instruction, NaN propagates like torch.relu
+__device__ __forceinline__ float2 act_pair(float2 z, float floor) {
+  return make_float2(max_nan(z.x, floor), max_nan(z.y, floor));
+}
+template <typename T>
+__device__ __forceinline__ float2 round_to_storage(float2 v) {
+  if (sizeof(T) == 2) return make_float2(to_f32<T>(from_f32<T>(v.x)), to_f32<T>(from_f32<T>(v.y)));
+  return v;
+}
+// q = RN((act - off) / s'), c = clamp(q), cd = rint(c)   (the packed AFFINE branch of fq_vec)
+__device__ __forceinline__ void quant_pair(float2 act, const QuantK& k, float2& q, float2& c, float2& cd) {
+  const float2 num = __fadd2_rn(act, k.noff2);
+  const float2 q0 = __fmul2_rn(num, k.r2);
+  const float2 er = __ffma2_rn(k.ns2, q0, num);
+  q = __ffma2_rn(er, k.r2, q0);
+  c = make_float2(clamp_fast(q.x, k.lo, k.hi), clamp_fast(q.y, k.lo, k.hi));
+  cd = __fadd2_rn(__fadd2_rn(c, make_float2(kRoundMagic, kRoundMagic)), make_float2(-kRoundMagic, -kRoundMagic));
+}
+__device__ __forceinline__ float2 dequant_pair(float2 cd, const QuantK& k) {
+  // scalar mul.rn: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (see fq_math.cuh)
+  const float2 t = make_float2(__fmul_rn(cd.x, k.p.mul), __fmul_rn(cd.y, k.p.mul));
+  return __fadd2_rn(t, k.off2);
+}
+template <int VN>
+__device__ __forceinline__ float absmax_vec(const float (&f)[VN], float m) {
+#pragma unroll
+  for (int e = 0; e < VN; ++e) m = fmaxf(m, fabsf(f[e]));
+  return m;
+}
+
+// The streaming kernels below share one loop shape.  A CTA owns the row tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// (a tile = ty * U rows); FULL tiles run without a single predicate or 64-bit multiply in the loop (one offset,
+// bumped by a constant), the ragged last tile is handled once, by one CTA, on the generic path.  The grid is sized
+// so that a CTA sees several tiles: the per-thread set-up (16 per-channel constants, the quantizer's reciprocal) costs
+// ~150 instructions, which at one 16-element tile per thread was a third of all instructions issued.
+template <int VN>
+__device__ __forceinline__ BnCh<VN> unpack_bnch(const BnCh2<VN>& c2) {
+  BnCh<VN> c;
+#pragma unroll
+  for (int e = 0; e < VN; e += 2) {
+    c.mean[e] = -c2.nmean[e / 2].x; c.mean[e + 1] = -c2.nmean[e / 2].y;
+    c.a[e] = c2.a[e / 2].x; c.a[e + 1] = c2.a[e / 2].y;
+    c.b[e] = c2.b[e / 2].x; c.b[e + 1] = c2.b[e / 2].y;
+    c.istd[e] = c2.istd[e / 2].x; c.istd[e + 1] = c2.istd[e / 2].y;
+  }
+  return c;
+}
+template <int VN>
+__device__ __forceinline__ void load_bnch2(BnCh2<VN>& c2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           const float* __restrict__ mean, const float* __restrict__ invstd, int ch0) {
+  BnCh<VN> c;
+  load_bnch<VN>(c, gamma, beta, mean, invstd, ch0);
+  load_bnch2<VN>(c2, c);
+}
+
+struct TileLoop {
+  int64_t nfull;      // number of full tiles
+  int64_t off;        // this thread's first vector of the CTA's first tile
+  int64_t stride;     // vectors between consecutive tiles of this CTA
+  int64_t du;         // vectors between the U rows a thread loads per tile
+  int64_t tail_r0;    // first row of the ragged tile, or -1
+};
+__device__ __forceinline__ TileLoop make_tile_loop(const BnqGeom& gm, int U, int ty, int col) {
+  TileLoop t;
+  const int64_t tile_rows = static_cast<int64_t>(gm.ty) * U;
+  t.nfull = gm.rows / tile_rows;
+  t.du = static_cast<int64_t>(gm.ty) * gm.cv;
+  t.off = (static_cast<int64_t>(blockIdx.x) * tile_rows + ty) * gm.cv + col;
+  t.stride = static_cast<int64_t>(gridDim.x) * tile_rows * gm.cv;
+  const bool mine = (t.nfull * tile_rows < gm.rows) && (static_cast<int64_t>(blockIdx.x) == t.nfull % gridDim.x);
+  t.tail_r0 = mine ? t.nfull * tile_rows : -1;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
 // forward, pass 2: normalise (+ identity) (+ ReLU) -> a (optional) and fake-quant(a) (optional)
 // ---------------------------------------------------------------------------------------
+template <typename T, int VN, bool QUANT>
+__device__ __forceinline__ void apply_generic_vec(const float (&fx)[VN], const float* fi, const BnCh<VN>& c, bool relu,
+                                                  const ChanParams& p, float lo, float hi, float (&act)[VN],
+                                                  float (&y)[VN]) {
+  bn_act_vec<VN>(fx, c, fi, relu, act);
+  if (QUANT) {
+    float src[VN], code[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) src[e] = sizeof(T) == 2 ? to_f32<T>(from_f32<T>(act[e])) : act[e];
+    fq_vec<DLMCQ_FORM_AFFINE, VN>(src, p, lo, hi, code, y);
+  }
+}
+
 template <typename T, bool HAS_ID, bool QUANT>
 __global__ void __launch_bounds__(kBnqThreads, 3)
 bnq_apply_kernel(const T* __restrict__ x, const T* __restrict__ idn, const float* __restrict__ gamma,
@@ -253,53 +399,90 @@ bnq_apply_kernel(const T* __restrict__ x, const T* __restrict__ idn, const float
   using V = Vec<T>;
   using raw = typename V::raw;
   constexpr int VN = V::N;
-  BNQ_THREAD_COORDS();
-  if (!active) return;
-  BnCh<VN> c;
-  load_bnch<VN>(c, gamma, beta, mean, invstd, col * VN);
-  ChanParams p;
-  if (QUANT) p = make_params<DLMCQ_FORM_AFFINE>(scale, offset, 0, g, lo, hi);
+  constexpr int U = kBnqU;
+  const int tx = static_cast<int>(threadIdx.x) % gm.txw;
+  const int ty = static_cast<int>(threadIdx.x) / gm.txw;
+  const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
+  pdl_wait();          // mean / invstd come from the finalisation kernel launched just before
+  pdl_trigger();
+  if (col >= gm.cv || ty >= gm.ty) return;
+  BnCh2<VN> c2;
+  load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
+  QuantK k;
+  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
+  const bool fast_ok = c2.safe && (!QUANT || k.fast);
+  const float floor = relu ? 0.f : -INFINITY;
   const raw* xv = reinterpret_cast<const raw*>(x);
   const raw* iv = reinterpret_cast<const raw*>(idn);
   raw* av = reinterpret_cast<raw*>(a_out);
   raw* qv = reinterpret_cast<raw*>(q_out);
-  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rpp; r0 < gm.rows; r0 += static_cast<int64_t>(gridDim.x) * rpp) {
-    raw rx[kBnqU], ri[kBnqU];
-    bool ok[kBnqU];
+  const TileLoop tl = make_tile_loop(gm, U, ty, col);
+  int64_t off = tl.off;
+  for (int64_t t = blockIdx.x; t < tl.nfull; t += gridDim.x, off += tl.stride) {
+    raw rx[U], ri[U];
 #pragma unroll
-    for (int u = 0; u < kBnqU; ++u) {
-      const int64_t row = r0 + ty + static_cast<int64_t>(u) * gm.ty;
-      ok[u] = row < gm.rows;
-      if (ok[u]) {
-        rx[u] = ld_stream(xv + row * gm.cv + col);
-        if (HAS_ID) ri[u] = ld_stream(iv + row * gm.cv + col);
+    for (int u = 0; u < U; ++u) {
+      rx[u] = ld_stream(xv + off + u * tl.du);
+      if (HAS_ID) ri[u] = ld_stream(iv + off + u * tl.du);
+    }
+    float fx[U][VN], fi[U][VN];
+    float m = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      V::unpack(rx[u], fx[u]);
+      m = absmax_vec<VN>(fx[u], m);
+      if (HAS_ID) {
+        V::unpack(ri[u], fi[u]);
+        m = absmax_vec<VN>(fi[u], m);
       }
     }
+    if (fast_ok && m <= kBnqSafe) {
 #pragma unroll
-    for (int u = 0; u < kBnqU; ++u) {
-      if (!ok[u]) continue;
-      const int64_t idx = (r0 + ty + static_cast<int64_t>(u) * gm.ty) * gm.cv + col;
-      float f[VN], fi[VN], act[VN];
-      V::unpack(rx[u], f);
-      if (HAS_ID) V::unpack(ri[u], fi);
-      bn_act_vec<VN>(f, c, HAS_ID ? fi : nullptr, relu != 0, act);
-      if (av) {
-        // `a` is re-read by the backward pass and by the next block's residual add: default L2 policy
-        av[idx] = V::pack(act);
-      }
-      if (QUANT) {
-        float src[VN], code[VN], y[VN];
-        if (sizeof(T) == 2) {
-          // bf16: the unfused chain quantises the bf16-ROUNDED activation
+      for (int u = 0; u < U; ++u) {
+        float act[VN], y[VN];
 #pragma unroll
-          for (int e = 0; e < VN; ++e) src[e] = to_f32<T>(from_f32<T>(act[e]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < VN; ++e) src[e] = act[e];
+        for (int e = 0; e < VN; e += 2) {
+          const float2 tt = __fadd2_rn(make_float2(fx[u][e], fx[u][e + 1]), c2.nmean[e / 2]);
+          float2 z = __ffma2_rn(tt, c2.a[e / 2], c2.b[e / 2]);
+          if (HAS_ID) z = __fadd2_rn(z, make_float2(fi[u][e], fi[u][e + 1]));
+          const float2 a2 = act_pair(z, floor);
+          act[e] = a2.x;
+          act[e + 1] = a2.y;
+          if (QUANT) {
+            float2 q, cc, cd;
+            quant_pair(round_to_storage<T>(a2), k, q, cc, cd);
+            const float2 yy = dequant_pair(cd, k);
+            y[e] = yy.x;
+            y[e + 1] = yy.y;
+          }
         }
-        fq_vec<DLMCQ_FORM_AFFINE, VN>(src, p, lo, hi, code, y);
-        st_stream(qv + idx, V::pack(y));
+        if (av) av[off + u * tl.du] = V::pack(act);   // re-read by the backward pass / the next block: default L2 policy
+        if (QUANT) st_stream(qv + off + u * tl.du, V::pack(y));
       }
+    } else {
+      const BnCh<VN> c = unpack_bnch<VN>(c2);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float act[VN], y[VN];
+        apply_generic_vec<T, VN, QUANT>(fx[u], HAS_ID ? fi[u] : nullptr, c, relu != 0, k.p, lo, hi, act, y);
+        if (av) av[off + u * tl.du] = V::pack(act);
+        if (QUANT) st_stream(qv + off + u * tl.du, V::pack(y));
+      }
+    }
+  }
+  if (tl.tail_r0 >= 0) {
+    const BnCh<VN> c = unpack_bnch<VN>(c2);
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = tl.tail_r0 + ty + static_cast<int64_t>(u) * gm.ty;
+      if (row >= gm.rows) break;
+      const int64_t idx = row * gm.cv + col;
+      float fx[VN], fi[VN], act[VN], y[VN];
+      V::unpack(ld_stream(xv + idx), fx);
+      if (HAS_ID) V::unpack(ld_stream(iv + idx), fi);
+      apply_generic_vec<T, VN, QUANT>(fx, HAS_ID ? fi : nullptr, c, relu != 0, k.p, lo, hi, act, y);
+      if (av) av[idx] = V::pack(act);
+      if (QUANT) st_stream(qv + idx, V::pack(y));
     }
   }
 }
@@ -313,6 +496,7 @@ bnq_apply_kernel(const T* __restrict__ x, const T* __restrict__ idn, const float
 //                  gradient of the identity branch - is written once and re-read by the dx pass.
 // pass 1 (reduce): per-channel sum(dz), sum(dz * xhat), and the per-tensor scale-gradient sum.
 // ---------------------------------------------------------------------------------------
+// generic (guarded) per-vector code
 template <typename T, int VN, bool RESID, bool QUANT>
 __device__ __forceinline__ void bnq_dz_vec(const float (&fx)[VN], const float (&fa)[VN], const float* fda,
                                            const float (&fdq)[VN], const BnCh<VN>& c, bool relu, const ChanParams& p,
@@ -344,8 +528,27 @@ __device__ __forceinline__ void bnq_dz_vec(const float (&fx)[VN], const float (&
   for (int e = 0; e < VN; ++e) dz[e] = relu ? ((act[e] > 0.f) ? da[e] : 0.f) : da[e];
 }
 
-template <typename T, bool RESID, bool QUANT>
-__global__ void __launch_bounds__(kBnqThreads, 3)
+// packed: dz for one pair.  `act` is the (storage-rounded) activation.
+template <bool QUANT>
+__device__ __forceinline__ float2 dz_pair(float2 act, float2 dq, float2 da_in, bool has_da, float floor, const QuantK& k,
+                                          float2& acc2) {
+  float2 da = make_float2(0.f, 0.f);
+  if (QUANT) {
+    float2 q, c, cd;
+    quant_pair(act, k, q, c, cd);
+    const float2 df = __fadd2_rn(cd, make_float2(-q.x, -q.y));
+    const bool in0 = (c.x == q.x), in1 = (c.y == q.y);        // in range <=> the clamp was the identity (NaN: false)
+    acc2 = __ffma2_rn(dq, make_float2(in0 ? df.x : cd.x, in1 ? df.y : cd.y), acc2);
+    da = make_float2(in0 ? dq.x : 0.f, in1 ? dq.y : 0.f);
+  }
+  if (has_da) da = __fadd2_rn(da, da_in);
+  return make_float2(act.x > floor ? da.x : 0.f, act.y > floor ? da.y : 0.f);
+}
+
+// U / MINB: rows in flight per thread and resident CTAs per SM.  The recomputing quantizer variants carry ~100 live
+// registers with four rows in flight: <4, 2> keeps them all, <2, 3> trades rows in flight for a third resident CTA.
+template <typename T, bool RESID, bool QUANT, int U, int MINB>
+__global__ void __launch_bounds__(kBnqThreads, MINB)
 bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, const T* __restrict__ d_a,
                       const T* __restrict__ d_q, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ mean, const float* __restrict__ invstd, T* __restrict__ dz_out,
@@ -356,103 +559,167 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
   constexpr int VN = V::N;
   extern __shared__ __align__(16) float sm[];
   __shared__ float red[64];
-  BNQ_THREAD_COORDS();
-  BnCh<VN> c;
-  if (active) load_bnch<VN>(c, gamma, beta, mean, invstd, col * VN);
-  ChanParams p;
-  if (QUANT) p = make_params<DLMCQ_FORM_AFFINE>(scale, offset, 0, g, lo, hi);
+  const int tx = static_cast<int>(threadIdx.x) % gm.txw;
+  const int ty = static_cast<int>(threadIdx.x) / gm.txw;
+  const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
+  const bool active = (col < gm.cv) && (ty < gm.ty);
+  pdl_wait();
+  pdl_trigger();
+  BnCh2<VN> c2;
+  if (active) load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
+  QuantK k;
+  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
+  const bool fast_ok = active && c2.safe && (!QUANT || k.fast);
+  const float floor = relu ? 0.f : -INFINITY;
+  const bool has_da = d_a != nullptr;
   const raw* xv = reinterpret_cast<const raw*>(x);
   const raw* av = reinterpret_cast<const raw*>(a_saved);
   const raw* dav = reinterpret_cast<const raw*>(d_a);
   const raw* dqv = reinterpret_cast<const raw*>(d_q);
   raw* zv = reinterpret_cast<raw*>(dz_out);
-  float sdb[VN], sdg[VN];
+  float2 sdb[VN / 2], sdg[VN / 2];
 #pragma unroll
-  for (int e = 0; e < VN; ++e) { sdb[e] = 0.f; sdg[e] = 0.f; }
-  float acc[1] = {0.f};
-  constexpr int U = RESID ? 2 : kBnqU;      // RESID reads up to four streams per row: two rows in flight are enough
-  const int64_t step = static_cast<int64_t>(gm.ty) * U;
-  for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * step; r0 < gm.rows; r0 += static_cast<int64_t>(gridDim.x) * step) {
-    raw rx[U], ra[U], rda[U], rdq[U];
-    bool ok[U];
+  for (int e = 0; e < VN / 2; ++e) { sdb[e] = make_float2(0.f, 0.f); sdg[e] = make_float2(0.f, 0.f); }
+  float2 acc2 = make_float2(0.f, 0.f);
+  float acc_slow = 0.f;
+
+  // generic per-vector step (guarded arithmetic): the slow path of full tiles and the ragged tile
+  auto generic_vec = [&](const BnCh<VN>& c, int64_t idx, const raw& rxx, const raw& raa, const raw& rdaa, const raw& rdqq) {
+    float fx[VN], fa[VN], fda[VN], fdq[VN], dz[VN];
+    V::unpack(rxx, fx);
+    if (RESID) V::unpack(raa, fa);
+    if (has_da) V::unpack(rdaa, fda);
+    if (QUANT) V::unpack(rdqq, fdq);
+    bnq_dz_vec<T, VN, RESID, QUANT>(fx, fa, has_da ? fda : nullptr, fdq, c, relu != 0, k.p, lo, hi, acc_slow, dz);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t row = r0 + ty + static_cast<int64_t>(u) * gm.ty;
-      ok[u] = active && row < gm.rows;
-      if (ok[u]) {
-        const int64_t idx = row * gm.cv + col;
-        rx[u] = ld_stream(xv + idx);
-        if (RESID) ra[u] = ld_stream(av + idx);
-        if (d_a) rda[u] = ld_stream(dav + idx);
-        if (QUANT) rdq[u] = ld_stream(dqv + idx);
+    for (int e = 0; e < VN; e += 2) {
+      if (zv && sizeof(T) == 2) {
+        dz[e] = to_f32<T>(from_f32<T>(dz[e]));
+        dz[e + 1] = to_f32<T>(from_f32<T>(dz[e + 1]));
+      }
+      const float xh0 = (fx[e] - c.mean[e]) * c.istd[e], xh1 = (fx[e + 1] - c.mean[e + 1]) * c.istd[e + 1];
+      sdb[e / 2].x += dz[e];
+      sdb[e / 2].y += dz[e + 1];
+      sdg[e / 2].x = __fmaf_rn(dz[e], xh0, sdg[e / 2].x);
+      sdg[e / 2].y = __fmaf_rn(dz[e + 1], xh1, sdg[e / 2].y);
+    }
+    if (zv) zv[idx] = V::pack(dz);
+  };
+
+  const TileLoop tl = make_tile_loop(gm, U, ty, col);
+  int64_t off = tl.off;
+  if (active) {
+    for (int64_t t = blockIdx.x; t < tl.nfull; t += gridDim.x, off += tl.stride) {
+      raw rx[U], ra[U], rda[U], rdq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rx[u] = ld_stream(xv + off + u * tl.du);
+        if (RESID) ra[u] = ld_stream(av + off + u * tl.du);
+        if (has_da) rda[u] = ld_stream(dav + off + u * tl.du);
+        if (QUANT) rdq[u] = ld_stream(dqv + off + u * tl.du);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float fx[VN], fa[VN];
+        V::unpack(rx[u], fx);
+        float m = absmax_vec<VN>(fx, 0.f);
+        if (RESID) {
+          V::unpack(ra[u], fa);
+          m = absmax_vec<VN>(fa, m);
+        }
+        if (fast_ok && m <= kBnqSafe) {
+          float fda[VN], fdq[VN], dz[VN];
+          if (has_da) V::unpack(rda[u], fda);
+          if (QUANT) V::unpack(rdq[u], fdq);
+#pragma unroll
+          for (int e = 0; e < VN; e += 2) {
+            const float2 tt = __fadd2_rn(make_float2(fx[e], fx[e + 1]), c2.nmean[e / 2]);
+            float2 act;
+            if (RESID) {
+              act = make_float2(fa[e], fa[e + 1]);
+            } else {
+              act = round_to_storage<T>(act_pair(__ffma2_rn(tt, c2.a[e / 2], c2.b[e / 2]), floor));
+            }
+            float2 d2 = dz_pair<QUANT>(act, QUANT ? make_float2(fdq[e], fdq[e + 1]) : make_float2(0.f, 0.f),
+                                       has_da ? make_float2(fda[e], fda[e + 1]) : make_float2(0.f, 0.f), has_da, floor,
+                                       k, acc2);
+            if (zv) d2 = round_to_storage<T>(d2);   // the dx pass and the identity branch see the stored value
+            dz[e] = d2.x;
+            dz[e + 1] = d2.y;
+            const float2 xh = __fmul2_rn(tt, c2.istd[e / 2]);
+            sdb[e / 2] = __fadd2_rn(sdb[e / 2], d2);
+            sdg[e / 2] = __ffma2_rn(d2, xh, sdg[e / 2]);
+          }
+          if (zv) zv[off + u * tl.du] = V::pack(dz);  // re-read by the dx pass (and the identity branch): default policy
+        } else {
+          generic_vec(unpack_bnch<VN>(c2), off + u * tl.du, rx[u], ra[u], rda[u], rdq[u]);
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!ok[u]) continue;
-      const int64_t idx = (r0 + ty + static_cast<int64_t>(u) * gm.ty) * gm.cv + col;
-      float fx[VN], fa[VN], fda[VN], fdq[VN], dz[VN];
-      V::unpack(rx[u], fx);
-      if (RESID) V::unpack(ra[u], fa);
-      if (d_a) V::unpack(rda[u], fda);
-      if (QUANT) V::unpack(rdq[u], fdq);
-      bnq_dz_vec<T, VN, RESID, QUANT>(fx, fa, d_a ? fda : nullptr, fdq, c, relu != 0, p, lo, hi, acc[0], dz);
-      if (zv) {
-        if (sizeof(T) == 2) {   // the dx pass and the identity branch see the rounded value: reduce the same numbers
-#pragma unroll
-          for (int e = 0; e < VN; ++e) dz[e] = to_f32<T>(from_f32<T>(dz[e]));
-        }
-        zv[idx] = V::pack(dz);  // re-read by the dx pass (and by the identity branch): default cache policy
-      }
-#pragma unroll
-      for (int e = 0; e < VN; ++e) {
-        const float xh = (fx[e] - c.mean[e]) * c.istd[e];
-        sdb[e] += dz[e];
-        sdg[e] = __fmaf_rn(dz[e], xh, sdg[e]);
+    if (tl.tail_r0 >= 0) {
+      const BnCh<VN> c = unpack_bnch<VN>(c2);
+#pragma unroll 1
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = tl.tail_r0 + ty + static_cast<int64_t>(u) * gm.ty;
+        if (row >= gm.rows) break;
+        const int64_t idx = row * gm.cv + col;
+        raw r0 = ld_stream(xv + idx), r1 = r0, r2 = r0, r3 = r0;
+        if (RESID) r1 = ld_stream(av + idx);
+        if (has_da) r2 = ld_stream(dav + idx);
+        if (QUANT) r3 = ld_stream(dqv + idx);
+        generic_vec(c, idx, r0, r1, r2, r3);
       }
     }
   }
-  bnq_store_partials<VN>(sdb, sdg, sm, gm, tx, ty, col, active, part);
+  float s1[VN], s2[VN];
+#pragma unroll
+  for (int e = 0; e < VN; e += 2) {
+    s1[e] = sdb[e / 2].x; s1[e + 1] = sdb[e / 2].y;
+    s2[e] = sdg[e / 2].x; s2[e + 1] = sdg[e / 2].y;
+  }
+  bnq_store_partials<VN>(s1, s2, sm, gm, tx, ty, col, active, part);
   if (QUANT) {
+    float acc[1] = {(acc2.x + acc2.y) + acc_slow};
     block_sum<1>(acc, red);
     if (threadIdx.x == 0) part_s[static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x] = acc[0];
   }
 }
 
-// per-channel d gamma / d beta and the coefficients of the dx pass; the last CTA reduces the scale gradient
+// per-channel d gamma / d beta and the coefficients of the dx pass (one warp per channel, as above); the last CTA
+// reduces the scale gradient
 __global__ void __launch_bounds__(256)
 bnq_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ part_s, BnqGeom gm, int n_part_s,
                         int training, float g, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         float* __restrict__ coef, float* __restrict__ dscale) {
-  __shared__ double sh[2][8][32];
-  const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
+  __shared__ double sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_trigger();
   if (blockIdx.x == gridDim.x - 1) {          // scale gradient: fixed-order sum of the per-CTA partials in double
     double s = 0.0;
-    for (int i = threadIdx.x; i < n_part_s; i += blockDim.x) s += static_cast<double>(part_s[i]);
+    for (int i = threadIdx.x; i < n_part_s; i += blockDim.x) s += static_cast<double>(__ldcg(part_s + i));
     s = warp_sum(s);
-    if (cx == 0) sh[0][by][0] = s;
+    if (lane == 0) sh[warp] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.0;
-      for (int r = 0; r < 8; ++r) t += sh[0][r][0];
+      for (int r = 0; r < 8; ++r) t += sh[r];
       if (dscale) dscale[0] = static_cast<float>(t) * g;     // chain through grad_scale (utils.py:24-27)
     }
     return;
   }
-  const int c = blockIdx.x * 32 + cx;
-  double a1 = 0.0, a2 = 0.0;
-  if (c < gm.C) {
-    for (int b = by; b < gm.nbx; b += 8) {
-      a1 += static_cast<double>(part[static_cast<size_t>(b) * 2 * gm.C + c]);
-      a2 += static_cast<double>(part[static_cast<size_t>(b) * 2 * gm.C + gm.C + c]);
-    }
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= gm.C) return;
+  double db = 0.0, dg = 0.0;
+  const size_t stride = 2 * static_cast<size_t>(gm.C);
+#pragma unroll 4
+  for (int b = lane; b < gm.nbx; b += 32) {
+    db += static_cast<double>(__ldcg(part + b * stride + c));
+    dg += static_cast<double>(__ldcg(part + b * stride + gm.C + c));
   }
-  sh[0][by][cx] = a1;
-  sh[1][by][cx] = a2;
-  __syncthreads();
-  if (by == 0 && c < gm.C) {
-    double db = 0.0, dg = 0.0;
-    for (int r = 0; r < 8; ++r) { db += sh[0][r][cx]; dg += sh[1][r][cx]; }
+  db = warp_sum(db);
+  dg = warp_sum(dg);
+  if (lane == 0) {
     if (dbeta) dbeta[c] = static_cast<float>(db);
     if (dgamma) dgamma[c] = static_cast<float>(dg);
     const double n = static_cast<double>(gm.rows);
@@ -462,13 +729,120 @@ bnq_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict_
 }
 
 // pass 2: dx = gamma*invstd * (dz - mean(dz) - xhat * mean(dz*xhat))     (eval mode: gamma*invstd * dz)
-template <typename T, bool RESID, bool QUANT>
-__global__ void __launch_bounds__(kBnqThreads, 3)
+template <typename T, bool RESID, bool QUANT, int U, int MINB>
+__global__ void __launch_bounds__(kBnqThreads, MINB)
 bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T* __restrict__ d_a,
                   const T* __restrict__ d_q, const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
                   T* __restrict__ dx, BnqGeom gm, int relu, const float* __restrict__ scale,
                   const float* __restrict__ offset, float g, float lo, float hi) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  constexpr int VN = V::N;
+  const int tx = static_cast<int>(threadIdx.x) % gm.txw;
+  const int ty = static_cast<int>(threadIdx.x) / gm.txw;
+  const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
+  pdl_wait();          // coef comes from the finalisation kernel launched just before
+  pdl_trigger();
+  if (col >= gm.cv || ty >= gm.ty) return;
+  BnCh2<VN> c2;
+  load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
+  float2 nc1[VN / 2], c22[VN / 2], nistd[VN / 2];
+#pragma unroll
+  for (int e = 0; e < VN; e += 2) {
+    nc1[e / 2] = make_float2(-__ldcg(coef + col * VN + e), -__ldcg(coef + col * VN + e + 1));
+    c22[e / 2] = make_float2(__ldcg(coef + gm.C + col * VN + e), __ldcg(coef + gm.C + col * VN + e + 1));
+    nistd[e / 2] = make_float2(-c2.istd[e / 2].x, -c2.istd[e / 2].y);
+  }
+  QuantK k;
+  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
+  const bool fast_ok = c2.safe && (!QUANT || k.fast);
+  const float floor = relu ? 0.f : -INFINITY;
+  const bool has_da = d_a != nullptr;
+  const raw* xv = reinterpret_cast<const raw*>(x);
+  const raw* zv = reinterpret_cast<const raw*>(dz_in);
+  const raw* dav = reinterpret_cast<const raw*>(d_a);
+  const raw* dqv = reinterpret_cast<const raw*>(d_q);
+  raw* ov = reinterpret_cast<raw*>(dx);
+
+  // dz of one vector (packed when `fast`), then the BatchNorm input gradient
+  auto finish_vec = [&](const float (&fx)[VN], const float (&f1)[VN], const float (&f2)[VN], bool fast, int64_t idx) {
+    float dzs[VN], o[VN];
+    if (!RESID && !fast) {
+      float dummy = 0.f;
+      bnq_dz_vec<T, VN, false, QUANT>(fx, fx, has_da ? f1 : nullptr, f2, unpack_bnch<VN>(c2), relu != 0, k.p, lo, hi, dummy,
+                                      dzs);
+    }
+#pragma unroll
+    for (int e = 0; e < VN; e += 2) {
+      const float2 tt = __fadd2_rn(make_float2(fx[e], fx[e + 1]), c2.nmean[e / 2]);
+      float2 d2;
+      if (RESID) {
+        d2 = make_float2(f1[e], f1[e + 1]);
+      } else if (fast) {
+        float2 dummy2 = make_float2(0.f, 0.f);
+        const float2 act = round_to_storage<T>(act_pair(__ffma2_rn(tt, c2.a[e / 2], c2.b[e / 2]), floor));
+        d2 = dz_pair<QUANT>(act, QUANT ? make_float2(f2[e], f2[e + 1]) : make_float2(0.f, 0.f),
+                            has_da ? make_float2(f1[e], f1[e + 1]) : make_float2(0.f, 0.f), has_da, floor, k, dummy2);
+      } else {
+        d2 = make_float2(dzs[e], dzs[e + 1]);
+      }
+      // a * ((dz - c1) - xhat * c2), xhat = t * invstd
+      const float2 nxh = __fmul2_rn(tt, nistd[e / 2]);
+      const float2 w = __ffma2_rn(nxh, c22[e / 2], __fadd2_rn(d2, nc1[e / 2]));
+      const float2 r = __fmul2_rn(c2.a[e / 2], w);
+      o[e] = r.x;
+      o[e + 1] = r.y;
+    }
+    st_stream(ov + idx, V::pack(o));
+  };
+
+  const TileLoop tl = make_tile_loop(gm, U, ty, col);
+  int64_t off = tl.off;
+  for (int64_t t = blockIdx.x; t < tl.nfull; t += gridDim.x, off += tl.stride) {
+    raw rx[U], r1[U], r2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      rx[u] = ld_stream(xv + off + u * tl.du);
+      if (RESID) {
+        r1[u] = ld_stream(zv + off + u * tl.du);
+      } else {
+        if (has_da) r1[u] = ld_stream(dav + off + u * tl.du);
+        if (QUANT) r2[u] = ld_stream(dqv + off + u * tl.du);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float fx[VN], f1[VN], f2[VN];
+      V::unpack(rx[u], fx);
+      if (RESID || has_da) V::unpack(r1[u], f1);
+      if (!RESID && QUANT) V::unpack(r2[u], f2);
+      const bool fast = RESID || (fast_ok && absmax_vec<VN>(fx, 0.f) <= kBnqSafe);
+      finish_vec(fx, f1, f2, fast, off + u * tl.du);
+    }
+  }
+  if (tl.tail_r0 >= 0) {
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = tl.tail_r0 + ty + static_cast<int64_t>(u) * gm.ty;
+      if (row >= gm.rows) break;
+      const int64_t idx = row * gm.cv + col;
+      float fx[VN], f1[VN], f2[VN];
+      V::unpack(ld_stream(xv + idx), fx);
+      if (RESID) V::unpack(ld_stream(zv + idx), f1);
+      else if (has_da) V::unpack(ld_stream(dav + idx), f1);
+      if (!RESID && QUANT) V::unpack(ld_stream(dqv + idx), f2);
+      finish_vec(fx, f1, f2, RESID, idx);
+    }
+  }
+}
+
+// A/B aid (DLMCQ_BNQ_DXV=1): the first, scalar version of the dz -> dx pass
+template <typename T>
+__global__ void __launch_bounds__(kBnqThreads, 3)
+bnq_bwd_dx_scalar_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ coef, T* __restrict__ dx, BnqGeom gm) {
   using V = Vec<T>;
   using raw = typename V::raw;
   constexpr int VN = V::N;
@@ -482,15 +856,11 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
     c1[e] = __ldg(coef + col * VN + e);
     c2[e] = __ldg(coef + gm.C + col * VN + e);
   }
-  ChanParams p;
-  if (QUANT) p = make_params<DLMCQ_FORM_AFFINE>(scale, offset, 0, g, lo, hi);
   const raw* xv = reinterpret_cast<const raw*>(x);
   const raw* zv = reinterpret_cast<const raw*>(dz_in);
-  const raw* dav = reinterpret_cast<const raw*>(d_a);
-  const raw* dqv = reinterpret_cast<const raw*>(d_q);
   raw* ov = reinterpret_cast<raw*>(dx);
   for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rpp; r0 < gm.rows; r0 += static_cast<int64_t>(gridDim.x) * rpp) {
-    raw rx[kBnqU], r1[kBnqU], r2[kBnqU];
+    raw rx[kBnqU], r1[kBnqU];
     bool ok[kBnqU];
 #pragma unroll
     for (int u = 0; u < kBnqU; ++u) {
@@ -499,12 +869,7 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
       if (ok[u]) {
         const int64_t idx = row * gm.cv + col;
         rx[u] = ld_stream(xv + idx);
-        if (RESID) {
-          r1[u] = ld_stream(zv + idx);
-        } else {
-          if (d_a) r1[u] = ld_stream(dav + idx);
-          if (QUANT) r2[u] = ld_stream(dqv + idx);
-        }
+        r1[u] = ld_stream(zv + idx);
       }
     }
 #pragma unroll
@@ -513,14 +878,7 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
       const int64_t idx = (r0 + ty + static_cast<int64_t>(u) * gm.ty) * gm.cv + col;
       float fx[VN], dz[VN], o[VN];
       V::unpack(rx[u], fx);
-      if (RESID) {
-        V::unpack(r1[u], dz);
-      } else {
-        float fda[VN], fdq[VN], dummy = 0.f;
-        if (d_a) V::unpack(r1[u], fda);
-        if (QUANT) V::unpack(r2[u], fdq);
-        bnq_dz_vec<T, VN, false, QUANT>(fx, fx, d_a ? fda : nullptr, fdq, c, relu != 0, p, lo, hi, dummy, dz);
-      }
+      V::unpack(r1[u], dz);
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
         const float xh = (fx[e] - c.mean[e]) * c.istd[e];
@@ -535,6 +893,22 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// tuning aids (environment): DLMCQ_BNQ_TILES tiles per CTA of the streaming kernels (default 4), DLMCQ_BNQ_U rows in
+// flight per thread of the recomputing quantizer kernels (2 -> <2 rows, 3 CTAs/SM>, default 4 -> <4 rows, 2 CTAs/SM>)
+static inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+static inline int tiles_per_cta() {
+  static const int v = env_int("DLMCQ_BNQ_TILES", 4);
+  return v;
+}
+static inline int recompute_rows() {
+  static const int v = env_int("DLMCQ_BNQ_U", 4);
+  return v;
+}
+
 static inline int bnq_check(const dlmcq_bnq_desc* d) {
   if (!d || d->rows < 0 || d->channels < 1) return DLMCQ_EINVAL;
   if (d->dtype != DLMCQ_F32 && d->dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
@@ -542,12 +916,16 @@ static inline int bnq_check(const dlmcq_bnq_desc* d) {
   if (d->channels % vn != 0 || d->channels > (int64_t(1) << 20)) return DLMCQ_EUNSUPPORTED;
   return DLMCQ_OK;
 }
-static inline int apply_grid(const BnqGeom& g) {
-  const int64_t rpp = static_cast<int64_t>(g.ty) * kBnqU;
-  int64_t passes = (g.rows + rpp - 1) / rpp;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 1024 / g.gy;      // one 16 KB tile per CTA (as fq_fwd_flat)
-  if (passes > cap) passes = cap;
-  return passes < 1 ? 1 : static_cast<int>(passes);
+// CTAs along the rows for the non-reducing kernels: about four tiles per CTA (amortises the per-thread set-up) but
+// never fewer CTAs than 8 per SM while the tensor has that many tiles
+static inline int apply_grid(const BnqGeom& g, int u = kBnqU) {
+  const int64_t rpp = static_cast<int64_t>(g.ty) * u;
+  const int64_t passes = (g.rows + rpp - 1) / rpp;
+  const int64_t floor_ctas = static_cast<int64_t>(num_sms()) * 8 / g.gy;
+  int64_t n = passes / tiles_per_cta();
+  if (n < floor_ctas) n = floor_ctas;
+  if (n > passes) n = passes;
+  return n < 1 ? 1 : static_cast<int>(n);
 }
 template <int VN>
 static inline size_t bnq_smem(const BnqGeom& g) {
@@ -565,10 +943,12 @@ static int bnq_forward_t(const void* x, const void* idn, const float* gamma, con
   const bool training = (d->flags & DLMCQ_BNQ_TRAINING) != 0;
   const T* xt = static_cast<const T*>(x);
   if (training) {
-    bnq_stats_kernel<T><<<dim3(g.nbx, g.gy), kBnqThreads, bnq_smem<VN>(g), st>>>(xt, g, w.part);
-    DLMCQ_LAUNCH_CHECK();
-    bnq_stats_finalize_kernel<T><<<(g.C + 31) / 32, 256, 0, st>>>(xt, w.part, g, d->eps, d->momentum, rmean, rvar,
-                                                                    smean, sinv);
+    cudaError_t e = launch_pdl(bnq_stats_kernel<T>, dim3(g.nbx, g.gy), dim3(kBnqThreads), bnq_smem<VN>(g), st, xt, g,
+                               w.part);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    e = launch_pdl(bnq_stats_finalize_kernel<T>, dim3((g.C + 7) / 8), dim3(256), 0, st, xt,
+                   static_cast<const float*>(w.part), g, d->eps, d->momentum, rmean, rvar, smean, sinv);
+    if (e != cudaSuccess) return set_cuda_error(e);
   } else {
     bnq_eval_prepare_kernel<<<(g.C + 255) / 256, 256, 0, st>>>(rmean, rvar, g.C, d->eps, smean, sinv);
   }
@@ -583,9 +963,10 @@ static int bnq_forward_t(const void* x, const void* idn, const float* gamma, con
   const dim3 grid(apply_grid(g), g.gy);
   auto k = idn ? (quant ? bnq_apply_kernel<T, true, true> : bnq_apply_kernel<T, true, false>)
                : (quant ? bnq_apply_kernel<T, false, true> : bnq_apply_kernel<T, false, false>);
-  k<<<grid, kBnqThreads, 0, st>>>(xt, static_cast<const T*>(idn), gamma, beta, smean, sinv, static_cast<T*>(a_out),
-                                  static_cast<T*>(q_out), g, relu, sc, of, gq, lo, hi);
-  DLMCQ_LAUNCH_CHECK();
+  cudaError_t e = launch_pdl(k, grid, dim3(kBnqThreads), 0, st, xt, static_cast<const T*>(idn), gamma, beta,
+                             static_cast<const float*>(smean), static_cast<const float*>(sinv), static_cast<T*>(a_out),
+                             static_cast<T*>(q_out), g, relu, sc, of, gq, lo, hi);
+  if (e != cudaSuccess) return set_cuda_error(e);
   return DLMCQ_OK;
 }
 
@@ -611,23 +992,38 @@ static int bnq_backward_t(const void* x, const void* a_saved, const void* d_a, c
   const T* dat = static_cast<const T*>(d_a);
   const T* dqt = static_cast<const T*>(d_q);
   {
-    auto k = resid ? (quant ? bnq_bwd_reduce_kernel<T, true, true> : bnq_bwd_reduce_kernel<T, true, false>)
-                   : (quant ? bnq_bwd_reduce_kernel<T, false, true> : bnq_bwd_reduce_kernel<T, false, false>);
-    k<<<dim3(g.nbx, g.gy), kBnqThreads, bnq_smem<VN>(g), st>>>(xt, at, dat, dqt, gamma, beta, smean, sinv,
-                                                               static_cast<T*>(dz_out), g, relu, sc, of, gq, lo, hi,
-                                                               w.part, w.part_s);
-    DLMCQ_LAUNCH_CHECK();
+    const bool u2 = recompute_rows() == 2;
+    auto k = resid ? (quant ? bnq_bwd_reduce_kernel<T, true, true, 2, 3> : bnq_bwd_reduce_kernel<T, true, false, 2, 3>)
+                   : (quant ? (u2 ? bnq_bwd_reduce_kernel<T, false, true, 2, 3> : bnq_bwd_reduce_kernel<T, false, true, 4, 2>)
+                            : bnq_bwd_reduce_kernel<T, false, false, 4, 3>);
+    cudaError_t e = launch_pdl(k, dim3(g.nbx, g.gy), dim3(kBnqThreads), bnq_smem<VN>(g), st, xt, at, dat, dqt, gamma, beta,
+                               smean, sinv, static_cast<T*>(dz_out), g, relu, sc, of, gq, lo, hi, w.part, w.part_s);
+    if (e != cudaSuccess) return set_cuda_error(e);
   }
-  bnq_bwd_finalize_kernel<<<(g.C + 31) / 32 + 1, 256, 0, st>>>(w.part, w.part_s, g, quant ? g.nbx * g.gy : 0, training,
-                                                                 gq, dgamma, dbeta, w.coef, quant ? dscale : nullptr);
-  DLMCQ_LAUNCH_CHECK();
-  if (dx) {
-    const dim3 grid(apply_grid(g), g.gy);
-    auto k = resid ? bnq_bwd_dx_kernel<T, true, false>
-                   : (quant ? bnq_bwd_dx_kernel<T, false, true> : bnq_bwd_dx_kernel<T, false, false>);
-    k<<<grid, kBnqThreads, 0, st>>>(xt, static_cast<const T*>(dz_out), dat, dqt, gamma, beta, smean, sinv, w.coef,
-                                    static_cast<T*>(dx), g, relu, sc, of, gq, lo, hi);
+  {
+    cudaError_t e = launch_pdl(bnq_bwd_finalize_kernel, dim3((g.C + 7) / 8 + 1), dim3(256), 0, st,
+                               static_cast<const float*>(w.part), static_cast<const float*>(w.part_s), g,
+                               quant ? g.nbx * g.gy : 0, training, gq, dgamma, dbeta, w.coef,
+                               quant ? dscale : static_cast<float*>(nullptr));
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  static const int dxv = env_int("DLMCQ_BNQ_DXV", 0);
+  if (dx && resid && dxv == 1) {
+    const int64_t rpp = static_cast<int64_t>(g.ty) * kBnqU;
+    const int64_t passes = (g.rows + rpp - 1) / rpp;
+    bnq_bwd_dx_scalar_kernel<T><<<dim3(static_cast<unsigned>(passes), g.gy), kBnqThreads, 0, st>>>(
+        xt, static_cast<const T*>(dz_out), gamma, beta, smean, sinv, w.coef, static_cast<T*>(dx), g);
     DLMCQ_LAUNCH_CHECK();
+  } else if (dx) {
+    const bool u2 = !resid && quant && recompute_rows() == 2;
+    const dim3 grid(apply_grid(g, u2 ? 2 : kBnqU), g.gy);
+    auto k = resid ? bnq_bwd_dx_kernel<T, true, false, 4, 3>
+                   : (quant ? (u2 ? bnq_bwd_dx_kernel<T, false, true, 2, 3> : bnq_bwd_dx_kernel<T, false, true, 4, 2>)
+                            : bnq_bwd_dx_kernel<T, false, false, 4, 3>);
+    cudaError_t e = launch_pdl(k, grid, dim3(kBnqThreads), 0, st, xt, static_cast<const T*>(dz_out), dat, dqt, gamma, beta,
+                               smean, sinv, static_cast<const float*>(w.coef), static_cast<T*>(dx), g, relu, sc, of, gq,
+                               lo, hi);
+    if (e != cudaSuccess) return set_cuda_error(e);
   }
   return DLMCQ_OK;
 }

@@ -169,7 +169,8 @@ def test_fused_backward_stages(shape, training, relu, resid, quant, plain_grad):
     close(dbeta, db_ref, "dbeta", rel=1e-5 * max(1.0, n ** 0.5 / 8))
     if resid:
         # d identity IS dz; the oracle chain's own da is (d_q * s) / s - a 1-ulp wobble
-        assert torch.equal(did == 0, dz == 0) and torch.allclose(did, dz, rtol=1e-6, atol=0), "d identity must be dz"
+        # (where da_q and d_a nearly cancel, that ulp is an absolute, not a relative, error: atol from |d_q|)
+        assert torch.allclose(did, dz, rtol=1e-6, atol=2e-7 * float(d_q.abs().max()) if quant else 0), "d identity must be dz"
     if quant:
         floor = 4e-7 * float(d_q.abs().sum()) * hi * g
         assert abs(float(ds) - float(ds_ref)) <= 1e-5 * abs(float(ds_ref)) + floor, (float(ds), float(ds_ref))
@@ -225,6 +226,12 @@ def _resnet(kind):
 
 @pytest.mark.parametrize("kind", ["tv18", "tv50"])
 def test_rewired_model_is_identical_when_kernels_are_disabled_and_close_when_enabled(kind, monkeypatch):
+    """(1) Wiring: with the fused kernels switched off the rewired model IS the original model, bit for bit.
+    (2) Kernels on: every residual block, fed the reference model's own input to that block (a deep random-initialised
+    W4A4 network amplifies a single flipped code chaotically - profiles/debug_fuse.py - so blocks are compared one at
+    a time), reproduces the reference block's output up to BatchNorm rounding: almost all elements within 1e-4 of the
+    tensor's scale, the rest (code flips downstream of a tie) bounded; same for two consecutive blocks through the
+    pre-quantised hand-off, and for the block's gradients."""
     from dlmc_quant_b200 import fuse, quantize_model
     base = _resnet(kind).cuda().to(memory_format=torch.channels_last)
     quantize_model(base, copy.deepcopy(CFG), None)
@@ -243,7 +250,6 @@ def test_rewired_model_is_identical_when_kernels_are_disabled_and_close_when_ena
         TF.cross_entropy(y, t).backward()
         return y.detach(), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
 
-    # (1) wiring: with the fused kernels switched off, bit-identical to the original model (forward, all gradients, BN buffers)
     monkeypatch.setattr(fuse, "fusable", lambda *a, **k: False)
     off = copy.deepcopy(base)
     h_off = fuse.fuse_bn_act_quant(off)
@@ -258,26 +264,68 @@ def test_rewired_model_is_identical_when_kernels_are_disabled_and_close_when_ena
     h_off.unfuse()
     monkeypatch.undo()
 
-    # (2) fused kernels on: same function up to BatchNorm rounding (a flipped code moves one activation by one step)
-    y2, g2 = step(fused)
-    assert g2.keys() == g0.keys()
-    assert float((y2 - y0).abs().max()) <= 0.05 * float(y0.abs().max()) + 1e-3, float((y2 - y0).abs().max())
-    for (n0, b0), (n1, b1) in zip(ref.named_buffers(), fused.named_buffers()):
-        if "running" in n0:
-            assert torch.allclose(b0, b1, rtol=2e-3, atol=2e-4), n0
-        elif "num_batches" in n0:
-            assert torch.equal(b0, b1), n0
-    cos = []
-    for n in g0:
-        a_, b_ = g0[n].flatten().double(), g2[n].flatten().double()
-        if float(a_.norm()) > 0:
-            cos.append(float(torch.dot(a_, b_) / (a_.norm() * b_.norm() + 1e-30)))
-    assert min(cos) > 0.9 and sum(cos) / len(cos) > 0.99, (min(cos), sum(cos) / len(cos))
-    # eval mode uses the running buffers
-    fused.eval(); ref.eval()
+    # BatchNorm buffers after ONE training forward of the whole model from the same state: batch counters agree
+    # everywhere, running statistics agree in the stem and the first block (deeper ones see chaotically different inputs)
+    ref3, fused3 = copy.deepcopy(base), copy.deepcopy(base)
+    fuse.fuse_bn_act_quant(fused3)
     with torch.no_grad():
-        ye, yr = fused(x), ref(x)
-    assert float((ye - yr).abs().max()) <= 0.05 * float(yr.abs().max()) + 1e-3
+        ref3(x), fused3(x)
+    for (n0, b0), (n1, b1) in zip(ref3.named_buffers(), fused3.named_buffers()):
+        if "num_batches" in n0:
+            assert torch.equal(b0, b1), n0
+        elif "running" in n0 and (n0.startswith("bn1") or n0.startswith("layer1.0")):
+            assert torch.allclose(b0, b1, rtol=1e-3, atol=1e-4), n0
+
+    # (2) block by block on the reference's own block inputs
+    ref2 = copy.deepcopy(base)
+    io = {}
+    hooks = [m.register_forward_hook(lambda mod, i, o, n=n: io.__setitem__(n, (i[0].detach(), o.detach())))
+             for n, m in ref2.named_modules() if n.startswith("layer") and n.count(".") == 1]
+    with torch.no_grad():
+        ref2(x)
+    for hk in hooks:
+        hk.remove()
+    names = list(io)
+    fblocks = dict(fused.named_modules())
+    rblocks = dict(ref2.named_modules())
+
+    def check(got, want, what, frac_tol, max_steps=3.0):
+        scale = float(want.abs().max())
+        d = (got - want).abs()
+        frac = float((d > 1e-4 * scale).float().mean())
+        assert frac <= frac_tol, (what, frac)
+        assert float(d.max()) <= 0.5 * scale, (what, float(d.max()), scale)
+
+    with torch.no_grad():
+        for n in names:
+            inp, out = io[n]
+            check(fblocks[n](inp), out, n, 0.03)
+        for n0, n1 in zip(names, names[1:]):
+            if n0.split(".")[0] != n1.split(".")[0]:
+                continue                                          # hand-off within a stage
+            mid = fblocks[n0](io[n0][0])
+            assert getattr(mid, "_dlmcq_q", None) is not None and mid._dlmcq_q[0] is fblocks[n1].conv1
+            check(fblocks[n1](mid), io[n1][1], n0 + "->" + n1, 0.15)
+    # gradients of one block, same input and upstream gradient on both sides
+    n = names[1]
+    inp, out = io[n]
+    gy = torch.randn_like(out)
+    grads = []
+    for blk in (rblocks[n], fblocks[n]):
+        blk.zero_grad(set_to_none=True)
+        xi = inp.clone().requires_grad_(True)
+        blk(xi).backward(gy)
+        grads.append([xi.grad] + [p.grad for p in blk.parameters()])
+    for a_, b_ in zip(*grads):
+        a_, b_ = a_.flatten().double(), b_.flatten().double()
+        if float(a_.norm()) > 0:
+            cos = float(torch.dot(a_, b_) / (a_.norm() * b_.norm()))
+            assert cos > 0.995, cos
+    # eval mode uses the running buffers: first block, same input
+    fused.eval(); ref2.eval()
+    with torch.no_grad():
+        inp, _ = io[names[0]]
+        check(fblocks[names[0]](inp), rblocks[names[0]](inp), "eval " + names[0], 0.03)
     h.unfuse()
     with torch.no_grad():
         assert torch.equal(fused(x), fused(x)) and 'forward' not in fused.layer1[0].__dict__
