@@ -41,6 +41,7 @@ struct BnqGeom {
   int32_t ty;    // rows covered by one "thread row" step
   int32_t gy;    // CTAs across a row (cv > 256)
   int32_t nbx;   // CTAs along the rows for the REDUCING kernels (= number of per-channel partials)
+  int64_t nfull4, nfull2;   // full row tiles with 4 / 2 rows per thread (host-side: no 64-bit division per thread)
 };
 
 template <typename T>
@@ -64,23 +65,32 @@ static inline BnqGeom make_bnq_geom(int64_t rows, int64_t C) {
   if (nbx > cap) nbx = cap;
   if (nbx < 1) nbx = 1;
   g.nbx = static_cast<int32_t>(nbx);
+  g.nfull4 = rows / (static_cast<int64_t>(g.ty) * 4);
+  g.nfull2 = rows / (static_cast<int64_t>(g.ty) * 2);
   return g;
 }
 
-// workspace: [header 256 B][partials nbx*2*C][scale partials nbx*gy][coef 2*C]
+// workspace: [header 256 B][partials nbx*2*C][scale partials nbx*gy][coef 2*C][keep mask: one word per (tile, thread)]
 struct BnqWs {
   float* part;
   float* part_s;
   float* coef;
+  uint32_t* mask;
 };
+static inline size_t bnq_mask_words(const BnqGeom& g) {
+  const int64_t tile_rows = static_cast<int64_t>(g.ty) * kBnqU;
+  return static_cast<size_t>((g.rows + tile_rows - 1) / tile_rows) * g.gy * kBnqThreads;
+}
 static inline size_t bnq_ws_floats(const BnqGeom& g) {
-  return static_cast<size_t>(g.nbx) * 2 * g.C + static_cast<size_t>(g.nbx) * g.gy + 2 * static_cast<size_t>(g.C);
+  return static_cast<size_t>(g.nbx) * 2 * g.C + static_cast<size_t>(g.nbx) * g.gy + 2 * static_cast<size_t>(g.C) +
+         bnq_mask_words(g);
 }
 static inline BnqWs bnq_ws(void* ws, const BnqGeom& g) {
   BnqWs w;
   w.part = ws_partials(ws);
   w.part_s = w.part + static_cast<size_t>(g.nbx) * 2 * g.C;
   w.coef = w.part_s + static_cast<size_t>(g.nbx) * g.gy;
+  w.mask = reinterpret_cast<uint32_t*>(w.coef + 2 * static_cast<size_t>(g.C));
   return w;
 }
 
@@ -355,6 +365,46 @@ __device__ __forceinline__ void load_bnch2(BnCh2<VN>& c2, const float* __restric
   load_bnch2<VN>(c2, c);
 }
 
+// Per-channel values written by the kernel launched just before (mean / invstd / coef): a normal cached load issued
+// AFTER griddepcontrol.wait.  Not ld.global.nc (the producer may still have been running when this kernel started), and
+// not ld.global.cg either: every CTA of an SM reads the same few hundred bytes, which L1 serves after the first CTA -
+// with .cg each of the thousands of CTAs sent 2048 more requests to L2 (measured: one-tile-per-CTA kernels 3x slower).
+__device__ __forceinline__ float ld_ca(const float* p) {
+  float v;
+  asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// constants in two phases: gamma / beta exist long before the kernel, mean / invstd may come from the kernel just before
+template <int VN>
+struct GammaBeta {
+  float g[VN], b[VN];
+};
+template <int VN>
+__device__ __forceinline__ GammaBeta<VN> load_gamma_beta(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         int ch0) {
+  GammaBeta<VN> gb;
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    gb.g[e] = gamma ? __ldg(gamma + ch0 + e) : 1.f;
+    gb.b[e] = beta ? __ldg(beta + ch0 + e) : 0.f;
+  }
+  return gb;
+}
+template <int VN>
+__device__ __forceinline__ void finish_bnch2(BnCh2<VN>& c2, const GammaBeta<VN>& gb, const float* __restrict__ mean,
+                                             const float* __restrict__ invstd, int ch0) {
+  BnCh<VN> c;
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+    c.mean[e] = ld_ca(mean + ch0 + e);
+    c.istd[e] = ld_ca(invstd + ch0 + e);
+    c.a[e] = gb.g[e] * c.istd[e];
+    c.b[e] = gb.b[e];
+  }
+  load_bnch2<VN>(c2, c);
+}
+
 struct TileLoop {
   int64_t nfull;      // number of full tiles
   int64_t off;        // this thread's first vector of the CTA's first tile
@@ -365,11 +415,12 @@ struct TileLoop {
 __device__ __forceinline__ TileLoop make_tile_loop(const BnqGeom& gm, int U, int ty, int col) {
   TileLoop t;
   const int64_t tile_rows = static_cast<int64_t>(gm.ty) * U;
-  t.nfull = gm.rows / tile_rows;
+  t.nfull = U == 4 ? gm.nfull4 : gm.nfull2;
   t.du = static_cast<int64_t>(gm.ty) * gm.cv;
   t.off = (static_cast<int64_t>(blockIdx.x) * tile_rows + ty) * gm.cv + col;
   t.stride = static_cast<int64_t>(gridDim.x) * tile_rows * gm.cv;
-  const bool mine = (t.nfull * tile_rows < gm.rows) && (static_cast<int64_t>(blockIdx.x) == t.nfull % gridDim.x);
+  const bool mine = (t.nfull * tile_rows < gm.rows) &&
+                    (blockIdx.x == static_cast<unsigned>(static_cast<uint64_t>(t.nfull) % gridDim.x));
   t.tail_r0 = mine ? t.nfull * tile_rows : -1;
   return t;
 }
@@ -403,28 +454,39 @@ bnq_apply_kernel(const T* __restrict__ x, const T* __restrict__ idn, const float
   const int tx = static_cast<int>(threadIdx.x) % gm.txw;
   const int ty = static_cast<int>(threadIdx.x) / gm.txw;
   const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
-  pdl_wait();          // mean / invstd come from the finalisation kernel launched just before
-  pdl_trigger();
-  if (col >= gm.cv || ty >= gm.ty) return;
-  BnCh2<VN> c2;
-  load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
-  QuantK k;
-  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
-  const bool fast_ok = c2.safe && (!QUANT || k.fast);
-  const float floor = relu ? 0.f : -INFINITY;
+  const bool active = (col < gm.cv) && (ty < gm.ty);
   const raw* xv = reinterpret_cast<const raw*>(x);
   const raw* iv = reinterpret_cast<const raw*>(idn);
   raw* av = reinterpret_cast<raw*>(a_out);
   raw* qv = reinterpret_cast<raw*>(q_out);
   const TileLoop tl = make_tile_loop(gm, U, ty, col);
   int64_t off = tl.off;
-  for (int64_t t = blockIdx.x; t < tl.nfull; t += gridDim.x, off += tl.stride) {
-    raw rx[U], ri[U];
+  int64_t t = blockIdx.x;
+  raw rx[U], ri[U];
+  // the first tile's loads go out BEFORE griddepcontrol.wait: x and the identity were written by kernels older than
+  // the statistics pass, so they are valid as soon as this CTA runs; only mean / invstd depend on the finalisation
+  // kernel launched just before, and its run time now overlaps these loads instead of preceding them
+  if (active && t < tl.nfull) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       rx[u] = ld_stream(xv + off + u * tl.du);
       if (HAS_ID) ri[u] = ld_stream(iv + off + u * tl.du);
     }
+  }
+  GammaBeta<VN> gb;
+  QuantK k;
+  if (active) {
+    gb = load_gamma_beta<VN>(gamma, beta, col * VN);
+    if (QUANT) k = make_quantk(scale, offset, g, lo, hi);    // the consumer layer's parameters: older than this op
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (!active) return;
+  BnCh2<VN> c2;
+  finish_bnch2<VN>(c2, gb, mean, invstd, col * VN);
+  const bool fast_ok = c2.safe && (!QUANT || k.fast);
+  const float floor = relu ? 0.f : -INFINITY;
+  while (t < tl.nfull) {
     float fx[U][VN], fi[U][VN];
     float m = 0.f;
 #pragma unroll
@@ -467,6 +529,15 @@ bnq_apply_kernel(const T* __restrict__ x, const T* __restrict__ idn, const float
         apply_generic_vec<T, VN, QUANT>(fx[u], HAS_ID ? fi[u] : nullptr, c, relu != 0, k.p, lo, hi, act, y);
         if (av) av[off + u * tl.du] = V::pack(act);
         if (QUANT) st_stream(qv + off + u * tl.du, V::pack(y));
+      }
+    }
+    t += gridDim.x;
+    off += tl.stride;
+    if (t < tl.nfull) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rx[u] = ld_stream(xv + off + u * tl.du);
+        if (HAS_ID) ri[u] = ld_stream(iv + off + u * tl.du);
       }
     }
   }
@@ -529,10 +600,14 @@ __device__ __forceinline__ void bnq_dz_vec(const float (&fx)[VN], const float (&
 }
 
 // packed: dz for one pair.  `act` is the (storage-rounded) activation.
+// keep0/1: the element passes d_q straight through (inside the clamp range AND above the ReLU floor)
 template <bool QUANT>
 __device__ __forceinline__ float2 dz_pair(float2 act, float2 dq, float2 da_in, bool has_da, float floor, const QuantK& k,
-                                          float2& acc2) {
+                                          float2& acc2, bool& keep0, bool& keep1) {
   float2 da = make_float2(0.f, 0.f);
+  const bool up0 = act.x > floor, up1 = act.y > floor;
+  keep0 = false;
+  keep1 = false;
   if (QUANT) {
     float2 q, c, cd;
     quant_pair(act, k, q, c, cd);
@@ -540,9 +615,11 @@ __device__ __forceinline__ float2 dz_pair(float2 act, float2 dq, float2 da_in, b
     const bool in0 = (c.x == q.x), in1 = (c.y == q.y);        // in range <=> the clamp was the identity (NaN: false)
     acc2 = __ffma2_rn(dq, make_float2(in0 ? df.x : cd.x, in1 ? df.y : cd.y), acc2);
     da = make_float2(in0 ? dq.x : 0.f, in1 ? dq.y : 0.f);
+    keep0 = in0 && up0;
+    keep1 = in1 && up1;
   }
   if (has_da) da = __fadd2_rn(da, da_in);
-  return make_float2(act.x > floor ? da.x : 0.f, act.y > floor ? da.y : 0.f);
+  return make_float2(up0 ? da.x : 0.f, up1 ? da.y : 0.f);
 }
 
 // U / MINB: rows in flight per thread and resident CTAs per SM.  The recomputing quantizer variants carry ~100 live
@@ -553,7 +630,11 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
                       const T* __restrict__ d_q, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ mean, const float* __restrict__ invstd, T* __restrict__ dz_out,
                       BnqGeom gm, int relu, const float* __restrict__ scale, const float* __restrict__ offset, float g,
-                      float lo, float hi, float* __restrict__ part, float* __restrict__ part_s) {
+                      float lo, float hi, float* __restrict__ part, float* __restrict__ part_s,
+                      uint32_t* __restrict__ keep_mask) {
+  // keep_mask (plain quantizer chain, U == kBnqU): bit (u * VN + e) of word [(tile * gy + blockIdx.y) * 256 + thread]
+  // says "dz == d_q" for that element (inside the clamp range and above the ReLU floor), so that the dx pass needs
+  // neither the quantizer arithmetic nor its ~60 extra registers - 1/8 byte per element written here, read there.
   using V = Vec<T>;
   using raw = typename V::raw;
   constexpr int VN = V::N;
@@ -563,20 +644,36 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
   const int ty = static_cast<int>(threadIdx.x) / gm.txw;
   const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
   const bool active = (col < gm.cv) && (ty < gm.ty);
-  pdl_wait();
-  pdl_trigger();
-  BnCh2<VN> c2;
-  if (active) load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
-  QuantK k;
-  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
-  const bool fast_ok = active && c2.safe && (!QUANT || k.fast);
-  const float floor = relu ? 0.f : -INFINITY;
   const bool has_da = d_a != nullptr;
   const raw* xv = reinterpret_cast<const raw*>(x);
   const raw* av = reinterpret_cast<const raw*>(a_saved);
   const raw* dav = reinterpret_cast<const raw*>(d_a);
   const raw* dqv = reinterpret_cast<const raw*>(d_q);
   raw* zv = reinterpret_cast<raw*>(dz_out);
+  const TileLoop tl = make_tile_loop(gm, U, ty, col);
+  int64_t off = tl.off;
+  int64_t t = blockIdx.x;
+  raw rx[U], ra[U], rda[U], rdq[U];
+  auto load_tile = [&](int64_t o) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      rx[u] = ld_stream(xv + o + u * tl.du);
+      if (RESID) ra[u] = ld_stream(av + o + u * tl.du);
+      if (has_da) rda[u] = ld_stream(dav + o + u * tl.du);
+      if (QUANT) rdq[u] = ld_stream(dqv + o + u * tl.du);
+    }
+  };
+  pdl_wait();          // the upstream gradients are the output of the previous operation on the stream
+  pdl_trigger();
+  // the first tile's loads are issued before the per-channel constants and the quantizer's scale are fetched: the
+  // two latencies overlap instead of adding up (the constants used to cost a CTA a full extra memory round trip)
+  if (active && t < tl.nfull) load_tile(off);
+  BnCh2<VN> c2;
+  if (active) load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
+  QuantK k;
+  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
+  const bool fast_ok = active && c2.safe && (!QUANT || k.fast);
+  const float floor = relu ? 0.f : -INFINITY;
   float2 sdb[VN / 2], sdg[VN / 2];
 #pragma unroll
   for (int e = 0; e < VN / 2; ++e) { sdb[e] = make_float2(0.f, 0.f); sdg[e] = make_float2(0.f, 0.f); }
@@ -584,7 +681,8 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
   float acc_slow = 0.f;
 
   // generic per-vector step (guarded arithmetic): the slow path of full tiles and the ragged tile
-  auto generic_vec = [&](const BnCh<VN>& c, int64_t idx, const raw& rxx, const raw& raa, const raw& rdaa, const raw& rdqq) {
+  auto generic_vec = [&](const BnCh<VN>& c, int64_t idx, const raw& rxx, const raw& raa, const raw& rdaa, const raw& rdqq,
+                         uint32_t& bits, int shift) {
     float fx[VN], fa[VN], fda[VN], fdq[VN], dz[VN];
     V::unpack(rxx, fx);
     if (RESID) V::unpack(raa, fa);
@@ -602,22 +700,16 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
       sdb[e / 2].y += dz[e + 1];
       sdg[e / 2].x = __fmaf_rn(dz[e], xh0, sdg[e / 2].x);
       sdg[e / 2].y = __fmaf_rn(dz[e + 1], xh1, sdg[e / 2].y);
+      // without d_a, dz is either d_q or 0: "dz != 0 or NaN" reproduces it from d_q (a zero d_q gives zero either way)
+      bits |= (dz[e] != 0.f || dz[e] != dz[e] ? 1u : 0u) << (shift + e);
+      bits |= (dz[e + 1] != 0.f || dz[e + 1] != dz[e + 1] ? 1u : 0u) << (shift + e + 1);
     }
     if (zv) zv[idx] = V::pack(dz);
   };
 
-  const TileLoop tl = make_tile_loop(gm, U, ty, col);
-  int64_t off = tl.off;
   if (active) {
-    for (int64_t t = blockIdx.x; t < tl.nfull; t += gridDim.x, off += tl.stride) {
-      raw rx[U], ra[U], rda[U], rdq[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        rx[u] = ld_stream(xv + off + u * tl.du);
-        if (RESID) ra[u] = ld_stream(av + off + u * tl.du);
-        if (has_da) rda[u] = ld_stream(dav + off + u * tl.du);
-        if (QUANT) rdq[u] = ld_stream(dqv + off + u * tl.du);
-      }
+    while (t < tl.nfull) {
+      uint32_t bits = 0u;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         float fx[VN], fa[VN];
@@ -640,9 +732,12 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
             } else {
               act = round_to_storage<T>(act_pair(__ffma2_rn(tt, c2.a[e / 2], c2.b[e / 2]), floor));
             }
+            bool k0, k1;
             float2 d2 = dz_pair<QUANT>(act, QUANT ? make_float2(fdq[e], fdq[e + 1]) : make_float2(0.f, 0.f),
                                        has_da ? make_float2(fda[e], fda[e + 1]) : make_float2(0.f, 0.f), has_da, floor,
-                                       k, acc2);
+                                       k, acc2, k0, k1);
+            bits |= (k0 ? 1u : 0u) << (u * VN + e);
+            bits |= (k1 ? 1u : 0u) << (u * VN + e + 1);
             if (zv) d2 = round_to_storage<T>(d2);   // the dx pass and the identity branch see the stored value
             dz[e] = d2.x;
             dz[e + 1] = d2.y;
@@ -652,12 +747,17 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
           }
           if (zv) zv[off + u * tl.du] = V::pack(dz);  // re-read by the dx pass (and the identity branch): default policy
         } else {
-          generic_vec(unpack_bnch<VN>(c2), off + u * tl.du, rx[u], ra[u], rda[u], rdq[u]);
+          generic_vec(unpack_bnch<VN>(c2), off + u * tl.du, rx[u], ra[u], rda[u], rdq[u], bits, u * VN);
         }
       }
+      if (keep_mask) keep_mask[(static_cast<size_t>(t) * gridDim.y + blockIdx.y) * kBnqThreads + threadIdx.x] = bits;
+      t += gridDim.x;
+      off += tl.stride;
+      if (t < tl.nfull) load_tile(off);
     }
     if (tl.tail_r0 >= 0) {
       const BnCh<VN> c = unpack_bnch<VN>(c2);
+      uint32_t bits = 0u;
 #pragma unroll 1
       for (int u = 0; u < U; ++u) {
         const int64_t row = tl.tail_r0 + ty + static_cast<int64_t>(u) * gm.ty;
@@ -667,8 +767,9 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
         if (RESID) r1 = ld_stream(av + idx);
         if (has_da) r2 = ld_stream(dav + idx);
         if (QUANT) r3 = ld_stream(dqv + idx);
-        generic_vec(c, idx, r0, r1, r2, r3);
+        generic_vec(c, idx, r0, r1, r2, r3, bits, u * VN);
       }
+      if (keep_mask) keep_mask[(static_cast<size_t>(tl.nfull) * gridDim.y + blockIdx.y) * kBnqThreads + threadIdx.x] = bits;
     }
   }
   float s1[VN], s2[VN];
@@ -742,28 +843,49 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
   const int tx = static_cast<int>(threadIdx.x) % gm.txw;
   const int ty = static_cast<int>(threadIdx.x) / gm.txw;
   const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
-  pdl_wait();          // coef comes from the finalisation kernel launched just before
-  pdl_trigger();
-  if (col >= gm.cv || ty >= gm.ty) return;
-  BnCh2<VN> c2;
-  load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
-  float2 nc1[VN / 2], c22[VN / 2], nistd[VN / 2];
-#pragma unroll
-  for (int e = 0; e < VN; e += 2) {
-    nc1[e / 2] = make_float2(-__ldcg(coef + col * VN + e), -__ldcg(coef + col * VN + e + 1));
-    c22[e / 2] = make_float2(__ldcg(coef + gm.C + col * VN + e), __ldcg(coef + gm.C + col * VN + e + 1));
-    nistd[e / 2] = make_float2(-c2.istd[e / 2].x, -c2.istd[e / 2].y);
-  }
-  QuantK k;
-  if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
-  const bool fast_ok = c2.safe && (!QUANT || k.fast);
-  const float floor = relu ? 0.f : -INFINITY;
+  const bool active = (col < gm.cv) && (ty < gm.ty);
   const bool has_da = d_a != nullptr;
   const raw* xv = reinterpret_cast<const raw*>(x);
   const raw* zv = reinterpret_cast<const raw*>(dz_in);
   const raw* dav = reinterpret_cast<const raw*>(d_a);
   const raw* dqv = reinterpret_cast<const raw*>(d_q);
   raw* ov = reinterpret_cast<raw*>(dx);
+  const TileLoop tl = make_tile_loop(gm, U, ty, col);
+  int64_t off = tl.off;
+  int64_t t = blockIdx.x;
+  raw rx[U], r1[U], r2[U];
+  auto load_tile = [&](int64_t o) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      rx[u] = ld_stream(xv + o + u * tl.du);
+      if (RESID) {
+        r1[u] = ld_stream(zv + o + u * tl.du);
+      } else {
+        if (has_da) r1[u] = ld_stream(dav + o + u * tl.du);
+        if (QUANT) r2[u] = ld_stream(dqv + o + u * tl.du);
+      }
+    }
+  };
+  // everything except coef is older than the finalisation kernel this launch depends on: fetch it before the wait
+  if (active && t < tl.nfull) load_tile(off);
+  BnCh2<VN> c2;
+  QuantK k;
+  if (active) {
+    load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);
+    if (QUANT) k = make_quantk(scale, offset, g, lo, hi);
+  }
+  pdl_wait();          // coef comes from the finalisation kernel launched just before
+  pdl_trigger();
+  if (!active) return;
+  float2 nc1[VN / 2], c22[VN / 2], nistd[VN / 2];
+#pragma unroll
+  for (int e = 0; e < VN; e += 2) {
+    nc1[e / 2] = make_float2(-ld_ca(coef + col * VN + e), -ld_ca(coef + col * VN + e + 1));
+    c22[e / 2] = make_float2(ld_ca(coef + gm.C + col * VN + e), ld_ca(coef + gm.C + col * VN + e + 1));
+    nistd[e / 2] = make_float2(-c2.istd[e / 2].x, -c2.istd[e / 2].y);
+  }
+  const bool fast_ok = c2.safe && (!QUANT || k.fast);
+  const float floor = relu ? 0.f : -INFINITY;
 
   // dz of one vector (packed when `fast`), then the BatchNorm input gradient
   auto finish_vec = [&](const float (&fx)[VN], const float (&f1)[VN], const float (&f2)[VN], bool fast, int64_t idx) {
@@ -781,9 +903,11 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
         d2 = make_float2(f1[e], f1[e + 1]);
       } else if (fast) {
         float2 dummy2 = make_float2(0.f, 0.f);
+        bool k0, k1;
         const float2 act = round_to_storage<T>(act_pair(__ffma2_rn(tt, c2.a[e / 2], c2.b[e / 2]), floor));
         d2 = dz_pair<QUANT>(act, QUANT ? make_float2(f2[e], f2[e + 1]) : make_float2(0.f, 0.f),
-                            has_da ? make_float2(f1[e], f1[e + 1]) : make_float2(0.f, 0.f), has_da, floor, k, dummy2);
+                            has_da ? make_float2(f1[e], f1[e + 1]) : make_float2(0.f, 0.f), has_da, floor, k, dummy2, k0,
+                            k1);
       } else {
         d2 = make_float2(dzs[e], dzs[e + 1]);
       }
@@ -797,20 +921,7 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
     st_stream(ov + idx, V::pack(o));
   };
 
-  const TileLoop tl = make_tile_loop(gm, U, ty, col);
-  int64_t off = tl.off;
-  for (int64_t t = blockIdx.x; t < tl.nfull; t += gridDim.x, off += tl.stride) {
-    raw rx[U], r1[U], r2[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      rx[u] = ld_stream(xv + off + u * tl.du);
-      if (RESID) {
-        r1[u] = ld_stream(zv + off + u * tl.du);
-      } else {
-        if (has_da) r1[u] = ld_stream(dav + off + u * tl.du);
-        if (QUANT) r2[u] = ld_stream(dqv + off + u * tl.du);
-      }
-    }
+  while (t < tl.nfull) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float fx[VN], f1[VN], f2[VN];
@@ -820,6 +931,9 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
       const bool fast = RESID || (fast_ok && absmax_vec<VN>(fx, 0.f) <= kBnqSafe);
       finish_vec(fx, f1, f2, fast, off + u * tl.du);
     }
+    t += gridDim.x;
+    off += tl.stride;
+    if (t < tl.nfull) load_tile(off);
   }
   if (tl.tail_r0 >= 0) {
 #pragma unroll 1
@@ -833,6 +947,99 @@ bnq_bwd_dx_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, const T*
       else if (has_da) V::unpack(ld_stream(dav + idx), f1);
       if (!RESID && QUANT) V::unpack(ld_stream(dqv + idx), f2);
       finish_vec(fx, f1, f2, RESID, idx);
+    }
+  }
+}
+
+// pass 2, light form: dz comes from memory - the stored dz (residual form) or d_q gated by the keep mask (plain
+// quantizer chain) - so only the BatchNorm input-gradient arithmetic is left (~10 packed instructions per element, 64
+// registers).  One tile per CTA; the tile's loads are issued BEFORE griddepcontrol.wait: x, d_q, dz and the mask were
+// all written (or read) by kernels older than the finalisation kernel this launch depends on, so they are valid as
+// soon as this CTA runs, and their latency overlaps the finalisation kernel instead of following it.
+template <typename T, bool MASKED>
+__global__ void __launch_bounds__(kBnqThreads, 3)
+bnq_bwd_dx_light_kernel(const T* __restrict__ x, const T* __restrict__ src /* dz, or d_q when MASKED */,
+                        const uint32_t* __restrict__ keep_mask, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ coef, T* __restrict__ dx, BnqGeom gm) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  constexpr int VN = V::N;
+  constexpr int U = kBnqU;
+  const int tx = static_cast<int>(threadIdx.x) % gm.txw;
+  const int ty = static_cast<int>(threadIdx.x) / gm.txw;
+  const int col = static_cast<int>(blockIdx.y) * gm.txw + tx;
+  const bool active = (col < gm.cv) && (ty < gm.ty);
+  const raw* xv = reinterpret_cast<const raw*>(x);
+  const raw* sv = reinterpret_cast<const raw*>(src);
+  raw* ov = reinterpret_cast<raw*>(dx);
+  const TileLoop tl = make_tile_loop(gm, U, ty, col);
+  int64_t off = tl.off;
+  int64_t t = blockIdx.x;
+  raw rx[U], rs[U];
+  uint32_t bits = 0u;
+  if (active && t < tl.nfull) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      rx[u] = ld_stream(xv + off + u * tl.du);
+      rs[u] = ld_stream(sv + off + u * tl.du);
+    }
+    if (MASKED) bits = __ldcg(keep_mask + (static_cast<size_t>(t) * gridDim.y + blockIdx.y) * kBnqThreads + threadIdx.x);
+  }
+  BnCh2<VN> c2;
+  if (active) load_bnch2<VN>(c2, gamma, beta, mean, invstd, col * VN);   // forward-pass results: older than this op
+  pdl_wait();          // only coef comes from the finalisation kernel launched just before
+  pdl_trigger();
+  if (!active) return;
+  float2 nc1[VN / 2], c22[VN / 2], nistd[VN / 2];
+#pragma unroll
+  for (int e = 0; e < VN; e += 2) {
+    nc1[e / 2] = make_float2(-ld_ca(coef + col * VN + e), -ld_ca(coef + col * VN + e + 1));
+    c22[e / 2] = make_float2(ld_ca(coef + gm.C + col * VN + e), ld_ca(coef + gm.C + col * VN + e + 1));
+    nistd[e / 2] = make_float2(-c2.istd[e / 2].x, -c2.istd[e / 2].y);
+  }
+  auto one = [&](const raw& rxx, const raw& rss, uint32_t b, int shift, int64_t idx) {
+    float fx[VN], fs[VN], o[VN];
+    V::unpack(rxx, fx);
+    V::unpack(rss, fs);
+#pragma unroll
+    for (int e = 0; e < VN; e += 2) {
+      float2 d2 = make_float2(fs[e], fs[e + 1]);
+      if (MASKED) {
+        d2.x = (b >> (shift + e)) & 1u ? d2.x : 0.f;
+        d2.y = (b >> (shift + e + 1)) & 1u ? d2.y : 0.f;
+      }
+      const float2 tt = __fadd2_rn(make_float2(fx[e], fx[e + 1]), c2.nmean[e / 2]);
+      const float2 nxh = __fmul2_rn(tt, nistd[e / 2]);
+      const float2 w = __ffma2_rn(nxh, c22[e / 2], __fadd2_rn(d2, nc1[e / 2]));
+      const float2 r = __fmul2_rn(c2.a[e / 2], w);
+      o[e] = r.x;
+      o[e + 1] = r.y;
+    }
+    st_stream(ov + idx, V::pack(o));
+  };
+  while (t < tl.nfull) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(rx[u], rs[u], bits, u * VN, off + u * tl.du);
+    t += gridDim.x;
+    off += tl.stride;
+    if (t < tl.nfull) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rx[u] = ld_stream(xv + off + u * tl.du);
+        rs[u] = ld_stream(sv + off + u * tl.du);
+      }
+      if (MASKED) bits = __ldcg(keep_mask + (static_cast<size_t>(t) * gridDim.y + blockIdx.y) * kBnqThreads + threadIdx.x);
+    }
+  }
+  if (tl.tail_r0 >= 0) {
+    const uint32_t b = MASKED ? __ldcg(keep_mask + (static_cast<size_t>(tl.nfull) * gridDim.y + blockIdx.y) * kBnqThreads + threadIdx.x) : 0u;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = tl.tail_r0 + ty + static_cast<int64_t>(u) * gm.ty;
+      if (row >= gm.rows) break;
+      const int64_t idx = row * gm.cv + col;
+      one(ld_stream(xv + idx), ld_stream(sv + idx), b, u * VN, idx);
     }
   }
 }
@@ -893,15 +1100,14 @@ bnq_bwd_dx_scalar_kernel(const T* __restrict__ x, const T* __restrict__ dz_in, c
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-// tuning aids (environment): DLMCQ_BNQ_TILES tiles per CTA of the streaming kernels (default 4), DLMCQ_BNQ_U rows in
+// tuning aids (environment): DLMCQ_BNQ_TILES tiles per CTA of the streaming kernels (default 8), DLMCQ_BNQ_U rows in
 // flight per thread of the recomputing quantizer kernels (2 -> <2 rows, 3 CTAs/SM>, default 4 -> <4 rows, 2 CTAs/SM>)
 static inline int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
-  const int v = e ? atoi(e) : 0;
-  return v > 0 ? v : dflt;
+  return (e && e[0]) ? atoi(e) : dflt;
 }
 static inline int tiles_per_cta() {
-  static const int v = env_int("DLMCQ_BNQ_TILES", 4);
+  static const int v = env_int("DLMCQ_BNQ_TILES", 8);
   return v;
 }
 static inline int recompute_rows() {
@@ -918,11 +1124,11 @@ static inline int bnq_check(const dlmcq_bnq_desc* d) {
 }
 // CTAs along the rows for the non-reducing kernels: about four tiles per CTA (amortises the per-thread set-up) but
 // never fewer CTAs than 8 per SM while the tensor has that many tiles
-static inline int apply_grid(const BnqGeom& g, int u = kBnqU) {
+static inline int apply_grid(const BnqGeom& g, int u = kBnqU, int tiles = 0) {
   const int64_t rpp = static_cast<int64_t>(g.ty) * u;
   const int64_t passes = (g.rows + rpp - 1) / rpp;
   const int64_t floor_ctas = static_cast<int64_t>(num_sms()) * 8 / g.gy;
-  int64_t n = passes / tiles_per_cta();
+  int64_t n = passes / (tiles > 0 ? tiles : tiles_per_cta());
   if (n < floor_ctas) n = floor_ctas;
   if (n > passes) n = passes;
   return n < 1 ? 1 : static_cast<int>(n);
@@ -991,13 +1197,17 @@ static int bnq_backward_t(const void* x, const void* a_saved, const void* d_a, c
   const T* at = static_cast<const T*>(a_saved);
   const T* dat = static_cast<const T*>(d_a);
   const T* dqt = static_cast<const T*>(d_q);
+  static const int light = env_int("DLMCQ_BNQ_LIGHT", 1);
+  // plain quantizer chain without a plain-output gradient: the reduce pass leaves a keep mask for a light dx pass
+  const bool masked = light == 1 && !resid && quant && d_a == nullptr && dx != nullptr && recompute_rows() != 2;
   {
     const bool u2 = recompute_rows() == 2;
     auto k = resid ? (quant ? bnq_bwd_reduce_kernel<T, true, true, 2, 3> : bnq_bwd_reduce_kernel<T, true, false, 2, 3>)
                    : (quant ? (u2 ? bnq_bwd_reduce_kernel<T, false, true, 2, 3> : bnq_bwd_reduce_kernel<T, false, true, 4, 2>)
                             : bnq_bwd_reduce_kernel<T, false, false, 4, 3>);
     cudaError_t e = launch_pdl(k, dim3(g.nbx, g.gy), dim3(kBnqThreads), bnq_smem<VN>(g), st, xt, at, dat, dqt, gamma, beta,
-                               smean, sinv, static_cast<T*>(dz_out), g, relu, sc, of, gq, lo, hi, w.part, w.part_s);
+                               smean, sinv, static_cast<T*>(dz_out), g, relu, sc, of, gq, lo, hi, w.part, w.part_s,
+                               masked ? w.mask : static_cast<uint32_t*>(nullptr));
     if (e != cudaSuccess) return set_cuda_error(e);
   }
   {
@@ -1014,6 +1224,13 @@ static int bnq_backward_t(const void* x, const void* a_saved, const void* d_a, c
     bnq_bwd_dx_scalar_kernel<T><<<dim3(static_cast<unsigned>(passes), g.gy), kBnqThreads, 0, st>>>(
         xt, static_cast<const T*>(dz_out), gamma, beta, smean, sinv, w.coef, static_cast<T*>(dx), g);
     DLMCQ_LAUNCH_CHECK();
+  } else if (dx && light == 1 && (resid || masked)) {
+    static const int light_tiles = env_int("DLMCQ_BNQ_TILES_LIGHT", 8);
+    auto k = resid ? bnq_bwd_dx_light_kernel<T, false> : bnq_bwd_dx_light_kernel<T, true>;
+    cudaError_t e = launch_pdl(k, dim3(apply_grid(g, kBnqU, light_tiles), g.gy), dim3(kBnqThreads), 0, st, xt,
+                               resid ? static_cast<const T*>(dz_out) : dqt, static_cast<const uint32_t*>(w.mask), gamma,
+                               beta, smean, sinv, static_cast<const float*>(w.coef), static_cast<T*>(dx), g);
+    if (e != cudaSuccess) return set_cuda_error(e);
   } else if (dx) {
     const bool u2 = !resid && quant && recompute_rows() == 2;
     const dim3 grid(apply_grid(g, u2 ? 2 : kBnqU), g.gy);
