@@ -429,7 +429,7 @@ def _eager_reference_modules(model):
     return model
 
 
-def _qat_arm(arm, channels_last, batch, steps, rank, world, device):
+def _qat_arm(arm, channels_last, batch, steps, rank, world, device, graphed=False):
     """One arm of the QAT benchmark, with the reference harness's methodology (example/benchmark/benchmark.py:168-197:
     SGD nesterov lr 0.01 wd 5e-4 momentum 0.9, cross-entropy, 2 warm-up steps, wall clock over the remaining steps,
     images = batch * n_gpu per step; benchmark.yaml:14 cudnn.benchmark on; DDP for N > 1)."""
@@ -472,6 +472,10 @@ def _qat_arm(arm, channels_last, batch, steps, rank, world, device):
         opt.step()
         return loss
 
+    if graphed:                         # whole step (forward, backward, optimizer) replayed as one CUDA graph
+        from dlmc_quant_b200.graph import graph_train_step
+        gstep = graph_train_step(model, opt, crit, x, t)
+        step = lambda: gstep(x, t)      # noqa: E731  (the per-step input copy into the static buffers is included)
     for _ in range(2):
         step()
     torch.cuda.synchronize()
@@ -530,6 +534,17 @@ def run_qat(args, rank, world, device):
                 res[fmt][arm] = _qat_arm(arm, cl, args.qat_batch, args.qat_steps, rank, world, device)
             except Exception as e:                      # an arm that fails must not take the headline metric down
                 res[fmt][arm] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+    # small per-GPU batch: the step is host-bound for the module path (~40 us of Python + ctypes per quantizer call);
+    # the same step captured once and replayed as ONE CUDA graph (dlmc_quant_b200.graph) removes the host from it
+    if world == 1 and (not only or "small_batch" in only):
+        sb = res["channels_last_small_batch"] = {"per_gpu_batch": args.qat_small_batch}
+        for arm, graphed in (("fp32", False), ("fp32", True), ("ours_fused", False), ("ours_fused", True)):
+            key = arm + ("_graphed" if graphed else "")
+            try:
+                sb[key] = _qat_arm(arm, True, args.qat_small_batch, 2 * args.qat_steps, rank, world, device, graphed)
+            except Exception as e:
+                sb[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
     return res
 
@@ -636,6 +651,7 @@ def main():
                                                    "'channels_last' or 'fp32,ours_fused'")
     ap.add_argument("--qat-only", action="store_true", help="skip the kernel metric; print only the QAT arms (diagnostic)")
     ap.add_argument("--qat-batch", type=int, default=128, help="per-GPU batch of the QAT arms")
+    ap.add_argument("--qat-small-batch", type=int, default=32, help="per-GPU batch of the host-bound / CUDA-graph arms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libdlmcq.so")
 F32, BF16 = 0, 1
 FORM_A1, FORM_AFFINE, FORM_ZP, FORM_SYM = 0, 1, 2, 3
 STATS_PER_CHANNEL = 4
+DIV_IEEE, DIV_CUDA_EAGER = 0, 1
 SWEEP_CANDIDATES = 80
 ROOTQ_STATE_FLOATS = 8
 
@@ -107,6 +108,7 @@ SIGNATURES = {
     "dlmcq_rootq_wt_backward_grouped": (_I, [_P, _P, _I, _L, _I, _P, _P]),
     "dlmcq_obs_stats": (_I, [_P, _P, _LP, _I, _P, _Z, _P]),
     "dlmcq_obs_minmax_finalize": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
+    "dlmcq_obs_minmax_finalize_mode": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "dlmcq_obs_absmean_finalize": (_I, [_P, _P, _L, _D, _D, _D, _I, _P]),
     "dlmcq_obs_kth_state_bytes": (_Z, []),
     "dlmcq_obs_kth_begin": (_I, [_P, _L, _L, _P]),

@@ -261,18 +261,23 @@ stats_finalize_kernel(const Stat4* __restrict__ part, int64_t per, int64_t inner
 }
 
 // ops.py:20-34 / 121-140
+// recip_mul: `tensor / python_scalar` as eager PyTorch evaluates it ON CUDA - ATen's true-division kernel multiplies
+// by the reciprocal of a CPU-scalar divisor, a * (1.0f / b) (BinaryDivTrueKernel.cu, "may lose one bit of precision") -
+// instead of the IEEE division the CPU kernels (and the committed fixtures, minted on the CPU) perform.
 __global__ void minmax_finalize_kernel(const float* __restrict__ stats, float* __restrict__ scale,
                                        float* __restrict__ offset, int64_t channels, float qdiv, int is_signed,
-                                       int allow_offset) {
+                                       int allow_offset, int recip_mul) {
   const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (c >= channels) return;
   const float* s = stats + 4 * c;
+  const float inv = 1.0f / qdiv;
   if (is_signed) {
-    scale[c] = s[2] / qdiv;            // abs().max() / (2^(n-1)-1)
+    scale[c] = recip_mul ? s[2] * inv : s[2] / qdiv;            // abs().max() / (2^(n-1)-1)
     offset[c] = 0.f;
   } else {
     const float lo = allow_offset ? s[0] : 0.f;
-    scale[c] = (s[1] - lo) / qdiv;     // (max - min) / (2^n - 1)
+    const float range = s[1] - lo;
+    scale[c] = recip_mul ? range * inv : range / qdiv;          // (max - min) / (2^n - 1)
     offset[c] = lo;
   }
 }
@@ -883,15 +888,23 @@ extern "C" int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* 
   return DLMCQ_EINVAL;
 }
 
-extern "C" int dlmcq_obs_minmax_finalize(const float* stats, float* scale, float* offset, int64_t channels,
-                                         int n_bits, int is_signed, int allow_offset, void* stream) {
+extern "C" int dlmcq_obs_minmax_finalize_mode(const float* stats, float* scale, float* offset, int64_t channels,
+                                              int n_bits, int is_signed, int allow_offset, int scalar_div_mode,
+                                              void* stream) {
   if (!stats || !scale || !offset || channels < 1 || n_bits < 1 || n_bits > 24) return DLMCQ_EINVAL;
+  if (scalar_div_mode != DLMCQ_DIV_IEEE && scalar_div_mode != DLMCQ_DIV_CUDA_EAGER) return DLMCQ_EINVAL;
   const float qdiv = is_signed ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
   const int blocks = static_cast<int>((channels + 127) / 128);
-  minmax_finalize_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, scale, offset, channels, qdiv,
-                                                                                is_signed, allow_offset);
+  minmax_finalize_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, scale, offset, channels, qdiv, is_signed, allow_offset, scalar_div_mode == DLMCQ_DIV_CUDA_EAGER ? 1 : 0);
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_minmax_finalize(const float* stats, float* scale, float* offset, int64_t channels,
+                                         int n_bits, int is_signed, int allow_offset, void* stream) {
+  return dlmcq_obs_minmax_finalize_mode(stats, scale, offset, channels, n_bits, is_signed, allow_offset, DLMCQ_DIV_IEEE,
+                                        stream);
 }
 
 extern "C" int dlmcq_obs_absmean_finalize(const float* stats, float* out, int64_t channels, double count,

@@ -257,13 +257,31 @@ def obs_stats(x, ch_axis=None, abs_input=False):
     return stats
 
 
-def minmax_from_stats(stats, n_bits, signed, allow_offset=True):
+SCALAR_DIVISION = "ieee"
+
+
+def set_scalar_division(mode):
+    """How the min/max observers evaluate `range / (2**n - 1)` (ops.py:23,32,126,135, a python-scalar divisor):
+    "ieee"        true float32 division - the reference on the CPU, what the committed fixtures pin (default);
+    "cuda_eager"  multiply by the float32 reciprocal - what eager PyTorch computes for the same expression ON CUDA
+                  (ATen's true-division kernel special-cases CPU-scalar divisors), i.e. the reference as its users
+                  run it on a GPU; up to 1 ulp away from "ieee".  Returns the previous mode."""
+    global SCALAR_DIVISION
+    if mode not in ("ieee", "cuda_eager"):
+        raise DlmcqError("scalar division mode is 'ieee' or 'cuda_eager'")
+    prev, SCALAR_DIVISION = SCALAR_DIVISION, mode
+    return prev
+
+
+def minmax_from_stats(stats, n_bits, signed, allow_offset=True, division=None):
     ch = stats.shape[0]
     scale = torch.empty(ch, dtype=torch.float32, device=stats.device)
     offset = torch.empty(ch, dtype=torch.float32, device=stats.device)
+    mode = _lib.DIV_CUDA_EAGER if (division or SCALAR_DIVISION) == "cuda_eager" else _lib.DIV_IEEE
     with torch.cuda.device(stats.device):
-        _lib.check(_lib.lib().dlmcq_obs_minmax_finalize(_ptr(stats), _ptr(scale), _ptr(offset), ch, int(n_bits),
-                                                        int(bool(signed)), int(bool(allow_offset)), _stream_ptr()))
+        _lib.check(_lib.lib().dlmcq_obs_minmax_finalize_mode(_ptr(stats), _ptr(scale), _ptr(offset), ch, int(n_bits),
+                                                             int(bool(signed)), int(bool(allow_offset)), mode,
+                                                             _stream_ptr()))
     return scale, offset
 
 

@@ -76,6 +76,16 @@ class _Plan:
         self._table = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
     def _upload(self):
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: the copy node re-reads its pinned source on every replay, so each captured upload
+            # gets a staging buffer of its own that is never rewritten (the pointers in it - graph-pool allocations
+            # and parameters - are the same on every replay), and no event may be waited on while capturing
+            pin = torch.empty(C.sizeof(self.arr), dtype=torch.uint8).pin_memory()
+            self._captured = getattr(self, "_captured", [])
+            self._captured.append(pin)
+            C.memmove(pin.data_ptr(), C.addressof(self.arr), pin.numel())
+            self._table.copy_(pin, non_blocking=True)
+            return self._table
         k = self._ring_i
         self._ring_i = (k + 1) % len(self._ring)
         if self._ring_ev[k] is None:

@@ -233,6 +233,15 @@ int dlmcq_obs_stats(const void* x, float* stats, const dlmcq_layout* layout, int
  * unsigned: s = (max-min)/(2^n-1), off = min (or 0 when allow_offset==0). */
 int dlmcq_obs_minmax_finalize(const float* stats, float* scale, float* offset, int64_t channels,
                               int n_bits, int is_signed, int allow_offset, void* stream);
+/* Same with the divisor convention made explicit.  `x / python_scalar` is not the same float32 operation on the two
+ * devices the reference runs on: the CPU kernel divides (IEEE), the CUDA kernel multiplies by the float32 reciprocal of
+ * the scalar (ATen BinaryDivTrueKernel.cu) - up to 1 ulp apart.  DLMCQ_DIV_IEEE reproduces the reference on the CPU
+ * (what the committed fixtures pin; dlmcq_obs_minmax_finalize uses it), DLMCQ_DIV_CUDA_EAGER reproduces the reference
+ * evaluated by eager PyTorch on the GPU, bit for bit (tests/test_gpu_parity_edges.py). */
+#define DLMCQ_DIV_IEEE 0
+#define DLMCQ_DIV_CUDA_EAGER 1
+int dlmcq_obs_minmax_finalize_mode(const float* stats, float* scale, float* offset, int64_t channels,
+                                   int n_bits, int is_signed, int allow_offset, int scalar_div_mode, void* stream);
 /* mean|x| based initialisers; `count` = elements behind each stats row.
  *   mode 0: out = (mul_a*mean)/mul_b   modules/base.py:84,119 LSQ init 2*mean|x|/sqrt(qmax)
  *   mode 1: out = (mul_a*mean)*mul_b   RootQ/base.py:115-116   +-2*mean|w|*sqrt(qmax)        */
