@@ -154,7 +154,9 @@ class QBase(Module):
     def _quant_weight(self, input):
         """base.py:106-133 (`input` is only used by the output-aware observers)."""
         q = self.qconfig
-        grouped = self.__dict__.pop('_wq', None)         # set by group_weight_quantizers' pre-hook for this step
+        # set by group_weight_quantizers' pre-hook for this step (membership test first: no dict mutation on the
+        # common path, which also keeps the method traceable by torch.compile)
+        grouped = self.__dict__.pop('_wq') if '_wq' in self.__dict__ else None
         if not q['weight']['enable']:
             return self.weight
         if grouped is not None:

@@ -9,6 +9,7 @@ behaviour here; FunLSQ, the only one whose backward works upstream, is reproduce
 import torch
 
 from ... import functional as F
+from ... import torch_ops  # noqa: F401  (registers torch.ops.dlmcq.* - the path taken under torch.compile)
 from ..._lib import FORM_A1, FORM_AFFINE, FORM_SYM, FORM_ZP  # noqa: F401
 from ..utils import _view3, infer_ch_axis
 
@@ -38,6 +39,12 @@ class FakeQuantFunction(torch.autograd.Function):
 def fake_quantize(x, scale, offset, lo, hi, form, g=0.0):
     """Differentiable fake-quant; the channel axis is inferred from the scale's broadcast shape."""
     run = infer_ch_axis(x, scale)
+    if torch.compiler.is_compiling() and (run is None or run[0] == run[1]):
+        # under torch.compile the quantizer is one opaque registered op (dlmc_quant_b200/torch_ops.py)
+        ax = -1 if run is None else run[0]
+        off = offset if isinstance(offset, torch.Tensor) else None
+        v = x if (x.is_contiguous() or F.dense_as_is(x, None if ax < 0 else ax)) else x.contiguous()
+        return torch.ops.dlmcq.fq_forward(v, scale, off, int(lo), int(hi), int(form), float(g), ax)
     if run is None or run[0] == run[1]:                      # the common cases: no reshape, no extra autograd node
         ax = None if run is None else run[0]
         v = x if (x.is_contiguous() or F.dense_as_is(x, ax)) else x.contiguous()   # channels_last passes through

@@ -507,3 +507,44 @@ def test_grouped_weights_follow_reset_qparams_and_checkpoints():
     fresh.load_state_dict(ref.state_dict(), strict=True)
     assert torch.equal(fresh(x), ref(x))
     handle.remove()
+
+
+def test_torch_compile_traces_through_the_quantizers():
+    """SURVEY.md 8b (last row): the kernels are registered `torch.library` ops (torch.ops.dlmcq.*, fake / meta
+    implementations + autograd formulas), so torch.compile captures a quantised model in ONE graph - no graph break at
+    the quantizers - and the compiled forward / backward equal the eager module path bit for bit."""
+    import torch._dynamo
+    from dlmc_quant_b200 import quantize_model
+    cfg = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 4, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+    torch.manual_seed(2333)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 8, 3, padding=1),
+                              torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(8, 5)).cuda()
+    quantize_model(net, copy.deepcopy(cfg), None)
+    x = torch.rand(4, 3, 16, 16, device="cuda")
+    with torch.no_grad():
+        net(x)                                           # lazy observer init (reads statistics back: eager only)
+    ref = copy.deepcopy(net)
+    torch._dynamo.reset()
+    explain = torch._dynamo.explain(net)(x)
+    assert explain.graph_break_count == 0, explain.break_reasons
+    ops = [str(n.target) for g in explain.graphs for n in g.graph.nodes if n.op == "call_function"]
+    assert sum("dlmcq.fq_forward" in o for o in ops) == 6, ops          # 3 layers x (input, weight)
+    compiled = torch.compile(net, backend="aot_eager", fullgraph=True)
+    y, y_ref = compiled(x), ref(x)
+    assert torch.equal(y, y_ref)
+    y.square().sum().backward()
+    y_ref.square().sum().backward()
+    for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and q.grad is not None, n
+        if n.endswith("scale"):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7), n
+        else:
+            assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-6), n
+    # the registered ops on their own: same numbers as the functional wrappers
+    s, o = torch.tensor([0.07], device="cuda"), torch.zeros(1, device="cuda")
+    from dlmc_quant_b200 import functional as Fm
+    assert torch.equal(torch.ops.dlmcq.fq_forward(x, s, o, 0, 15, 1, 0.01, -1), Fm.fq_forward(x, s, o, 0, 15, 1, g=0.01))
+    torch.library.opcheck(torch.ops.dlmcq.fq_forward.default, (x, s, o, 0, 15, 1, 0.01, -1),
+                          test_utils=("test_schema", "test_faketensor"))
