@@ -12,7 +12,7 @@ def __getattr__(name):
     if name == "quantize_model":
         from .quantize import quantize_model
         return quantize_model
-    if name in ("functional", "scalar", "dist", "quantize", "build", "reparam", "recon", "fuse", "graph"):
+    if name in ("functional", "scalar", "dist", "quantize", "build", "reparam", "recon", "fuse", "graph", "calibrate"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -60,6 +60,13 @@ class FinalizeItem(C.Structure):
     _fields_ = [("partials", C.c_void_p), ("dscale", C.c_void_p)]
 
 
+class SweepItem(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("scale", C.c_void_p), ("offset", C.c_void_p), ("channels", C.c_int64),
+                ("inner", C.c_int64), ("n_bits", C.c_int32), ("is_signed", C.c_int32), ("wpr", C.c_int32),
+                ("row_floats", C.c_int32), ("staged", C.c_int32), ("pad", C.c_int32), ("smem_bytes", C.c_int64),
+                ("ctas", C.c_int64)]
+
+
 class BnqDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("channels", C.c_int64), ("dtype", C.c_int32), ("flags", C.c_int32),
                 ("eps", C.c_float), ("momentum", C.c_float)]
@@ -119,7 +126,10 @@ SIGNATURES = {
     "dlmcq_obs_sweep_tensor_finalize": (_I, [_P, _P, _D, _I, _I, _P, _P, _P, _P]),
     "dlmcq_obs_sweep_channel": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P]),
     "dlmcq_obs_sweep_channel_geom": (_I, [_P, _L, _L, _I, _I, _I, _L, _P, _P, _P]),
+    "dlmcq_obs_sweep_channel_plan": (_I, [C.POINTER(SweepItem), _L]),
+    "dlmcq_obs_sweep_channel_grouped": (_I, [_P, _P, _I, _L, _I, _L, _P]),
     "dlmcq_obs_l2norm_step": (_I, [_P, _L, _L, _I, _P, _P, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "dlmcq_obs_l2norm_resident": (_I, [_P, _L, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "dlmcq_fq_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
     "dlmcq_fq_backward_grouped": (_I, [_P, _P, _P, _I, _L, _L, _I, _P, _P]),
     "dlmcq_fold_grouped": (_I, [_P, _P, _I, _L, _P]),

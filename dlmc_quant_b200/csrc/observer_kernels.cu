@@ -534,17 +534,17 @@ struct SweepRowGroup {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kSweepWarps * 32)
-sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, float qmax, float signed_div,
-                     int is_signed, float* __restrict__ scale, float* __restrict__ offset, int wpr, int row_floats,
-                     int staged) {
+__device__ __forceinline__ void sweep_channel_body(const T* __restrict__ x, int64_t channels, int64_t inner, float qmax,
+                                                   float signed_div, int is_signed, float* __restrict__ scale,
+                                                   float* __restrict__ offset, int wpr, int row_floats, int staged,
+                                                   int64_t cta) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) unsigned long long bars[kSweepWarps];
   __shared__ float red_all[kSweepWarps][2][kSweepWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int group = warp / wpr, wig = warp - group * wpr;
   const int rows_per_cta = kSweepWarps / wpr;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * rows_per_cta + group;
+  const int64_t row = cta * rows_per_cta + group;
   if (row >= channels) return;                 // a whole row group exits together; barriers are per group
   const int tg = wig * 32 + lane, gt = wpr * 32;
   SweepRowGroup grp{&red_all[group][0][0], wpr, wig, lane, group + 1, 0};
@@ -645,6 +645,36 @@ sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, f
     }
   }
   if (tg == 0) { scale[row] = cur_scale; offset[row] = cur_off; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSweepWarps * 32)
+sweep_channel_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, float qmax, float signed_div,
+                     int is_signed, float* __restrict__ scale, float* __restrict__ offset, int wpr, int row_floats,
+                     int staged) {
+  sweep_channel_body<T>(x, channels, inner, qmax, signed_div, is_signed, scale, offset, wpr, row_floats, staged,
+                        blockIdx.x);
+}
+
+// All per-channel weight sweeps of a model in ONE launch: a CNN's 23-54 weight tensors are swept in 50-150 us each
+// when launched one by one (the 80 dependent candidates set a ~45 us floor per launch however few rows a tensor has).
+// CTA b finds its tensor by a binary search over the CTA prefix; every tensor keeps the geometry (warps per row,
+// staging) its own launch would use, so the result is bit-identical to the per-tensor call.
+template <typename T>
+__global__ void __launch_bounds__(kSweepWarps * 32)
+sweep_channel_grouped_kernel(const dlmcq_sweep_item* __restrict__ items, const int64_t* __restrict__ cta_prefix,
+                             int n_items) {
+  int lo = 0, hi = n_items - 1;
+  const int64_t b = blockIdx.x;
+  while (lo < hi) {                                     // last item whose first CTA is <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (cta_prefix[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  const dlmcq_sweep_item it = items[lo];
+  const float qmax = static_cast<float>((1 << it.n_bits) - 1);
+  const float sdiv = static_cast<float>((1 << (it.n_bits - 1)) - 1);
+  sweep_channel_body<T>(static_cast<const T*>(it.x), it.channels, it.inner, qmax, sdiv, it.is_signed, it.scale,
+                        it.offset, it.wpr, it.row_floats, it.staged, b - cta_prefix[lo]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -830,6 +860,198 @@ l2norm_finalize_channels_kernel(const float* __restrict__ part, RowGeom gm, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// l2norm fixed point, RESIDENT form: the whole loop of ops.py:71-83 / 198-215 in ONE launch.
+//
+// The step-wise form above re-reads the tensor from HBM on every one of the 50-100 iterations and needs two launches
+// plus a host poll per few iterations.  A per-channel weight matrix (<= 9.4 MB for a CNN layer) fits in the GPU's
+// shared memory (148 x 200 KB), so: every CTA stages its (row, 2048-element segment) items ONCE, then all CTAs iterate
+// on chip - per iteration one warp pass over each staged item (A1 codes, the two dot products), a grid barrier, one
+// thread per row forming the new scale and its share of the convergence norm, a second grid barrier, and every CTA
+// evaluating the same convergence test from the same G partials in the same order (so no third barrier).  Launched
+// cooperatively (all CTAs co-resident); the barrier is a monotonically increasing arrival counter.  Deterministic.
+// ---------------------------------------------------------------------------------------
+constexpr int kResSeg = 2048;                       // floats per staged item (one warp sweeps it)
+constexpr int kResSlots = 24;                       // items per CTA at most: 24 x 8 KB = 192 KB
+constexpr int kResWarps = 8;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+// Work distribution: a row and all its 2048-element segments live in ONE CTA (row r -> CTA r % G), so a row's new
+// scale never leaves the CTA: after the warps' pass over the staged items, one thread per local row folds the row's
+// segment sums (shared memory), forms s_new and the row's share of the convergence norm; only the CTA's (num, den)
+// pair goes to global memory - ONE grid barrier per iteration - and every CTA then evaluates the same test from the
+// same G pairs in the same order.  The per-tensor form (one row spread over all CTAs, item i -> CTA i % G) exchanges
+// the CTA's (sum x*code, sum code^2) instead and every CTA forms the same s_new.  Scales stay in shared memory /
+// registers during the loop and are written back once.
+template <typename T>
+__global__ void __launch_bounds__(kResWarps * 32, 1)
+l2norm_resident_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, int segs, float* __restrict__ scale,
+                       const float* __restrict__ offset, float lo, float hi, int max_iters, float* __restrict__ diff,
+                       int32_t* __restrict__ done, int32_t* __restrict__ iters, double* __restrict__ cta_part,
+                       unsigned int* __restrict__ counters) {
+  extern __shared__ __align__(16) float stage[];                        // [slots][kResSeg]
+  __shared__ double sh[2][kResWarps];
+  __shared__ float item_a[kResSlots], item_b[kResSlots], s_loc[kResSlots];
+  __shared__ int s_stop;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = gridDim.x;
+  const bool single = channels == 1;
+  // local items: single row: items blockIdx.x, +G, ...; otherwise rows blockIdx.x, +G, ... with `segs` slots each
+  const int64_t total_items = channels * segs;
+  int n_slots = 0;
+  if (single) n_slots = static_cast<int>((total_items - blockIdx.x + G - 1) / G);
+  else n_slots = static_cast<int>((channels - blockIdx.x + G - 1) / G) * segs;
+  if (n_slots < 0) n_slots = 0;
+  auto slot_row = [&](int slot) -> int64_t { return single ? 0 : blockIdx.x + static_cast<int64_t>(slot / segs) * G; };
+  auto slot_seg = [&](int slot) -> int64_t { return single ? blockIdx.x + static_cast<int64_t>(slot) * G : slot % segs; };
+  for (int slot = 0; slot < n_slots; ++slot) {                          // stage once, zero-padded
+    const int64_t row = slot_row(slot), beg = slot_seg(slot) * kResSeg;
+    const int64_t len = (inner - beg) < kResSeg ? (inner - beg) : kResSeg;
+    const T* xr = x + row * inner + beg;
+    float* dst = stage + slot * kResSeg;
+    for (int j = threadIdx.x; j < kResSeg; j += blockDim.x) dst[j] = j < len ? to_f32<T>(xr[j]) : 0.f;
+  }
+  const int n_rows_loc = single ? 1 : n_slots / segs;
+  if (threadIdx.x < n_rows_loc) s_loc[threadIdx.x] = scale[single ? 0 : blockIdx.x + static_cast<int64_t>(threadIdx.x) * G];
+  __syncthreads();
+  unsigned int barrier_no = 0;
+  int it_count = 0;
+  while (true) {
+    // ---- one warp per staged item: sum x*code and sum(code*code + 1e-7)
+    for (int slot = warp; slot < n_slots; slot += kResWarps) {
+      const int64_t row = slot_row(slot), beg = slot_seg(slot) * kResSeg;
+      const int len = static_cast<int>((inner - beg) < kResSeg ? (inner - beg) : kResSeg);
+      ChanParams p;                                                   // A1 form: divisor s + 1e-7, multiplier s
+      {
+        const float sc = s_loc[single ? 0 : slot / segs];
+        p.off = offset ? __ldg(offset + row) : 0.f;
+        p.div = sc + 1e-7f;
+        p.mul = sc;
+        p.fd = make_fastdiv(p.div);
+        p.fd.ok = p.fd.ok && (fabsf(lo) <= 0x1p21f) && (fabsf(hi) <= 0x1p21f) && (fabsf(p.off) <= kFastDivMaxX);
+      }
+      const float* src = stage + slot * kResSeg;
+      const bool fast_p = p.fd.ok && fabsf(p.off) <= 0x1p59f;
+      float a = 0.f, b = 0.f;
+      float2 a2 = make_float2(0.f, 0.f), b2 = make_float2(0.f, 0.f);
+      const int nvec = len / 4;
+      for (int v = lane; v < nvec; v += 32) {
+        const float4 q = reinterpret_cast<const float4*>(src)[v];
+        const float f[4] = {q.x, q.y, q.z, q.w};
+        const float m = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[1])), fmaxf(fabsf(f[2]), fabsf(f[3])));
+        if (fast_p && m <= 0x1p59f) {
+          l2norm_pair_fast(make_float2(f[0], f[1]), p, lo, hi, a2, b2);
+          l2norm_pair_fast(make_float2(f[2], f[3]), p, lo, hi, a2, b2);
+        } else {
+          float code[4], y[4];
+          fq_vec<DLMCQ_FORM_A1, 4>(f, p, lo, hi, code, y);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { a += f[e] * code[e]; b += code[e] * code[e] + 1e-7f; }
+        }
+      }
+      for (int j = nvec * 4 + lane; j < len; j += 32) {
+        float code, y;
+        fq_elem<DLMCQ_FORM_A1>(src[j], p, lo, hi, code, y);
+        a += src[j] * code;
+        b += code * code + 1e-7f;
+      }
+      a += a2.x + a2.y;
+      b += b2.x + b2.y;
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) { item_a[slot] = a; item_b[slot] = b; }
+    }
+    __syncthreads();
+    // ---- per-row new scale (local) or the CTA's share of the single row's sums; one (num, den) pair per CTA
+    double num = 0.0, den = 0.0;
+    float s_new_loc = 0.f;
+    if (single) {
+      if (threadIdx.x == 0) {
+        for (int sl = 0; sl < n_slots; ++sl) { num += static_cast<double>(item_a[sl]); den += static_cast<double>(item_b[sl]); }
+      }
+    } else if (threadIdx.x < n_rows_loc) {
+      double a = 0.0, b = 0.0;
+      for (int sg = 0; sg < segs; ++sg) {
+        a += static_cast<double>(item_a[threadIdx.x * segs + sg]);
+        b += static_cast<double>(item_b[threadIdx.x * segs + sg]);
+      }
+      const float s_old = s_loc[threadIdx.x];
+      s_new_loc = static_cast<float>(a) / static_cast<float>(b);       // ops.py:207
+      const float d = s_new_loc - s_old;
+      num = static_cast<double>(d * d);
+      den = static_cast<double>(s_old * s_old);
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    if (lane == 0) { sh[0][warp] = num; sh[1][warp] = den; }
+    __syncthreads();
+    if (!single && threadIdx.x < n_rows_loc) s_loc[threadIdx.x] = s_new_loc;
+    if (threadIdx.x == 0) {
+      double tn = 0.0, td = 0.0;
+      for (int w = 0; w < kResWarps; ++w) { tn += sh[0][w]; td += sh[1][w]; }
+      cta_part[2 * blockIdx.x] = tn;
+      cta_part[2 * blockIdx.x + 1] = td;
+    }
+    barrier_no += 1;
+    grid_barrier(counters, barrier_no * G);
+    // ---- the same decision in every CTA, from the same G pairs in the same order (warp 0: lane-strided partial sums,
+    // fixed shuffle tree - identical in every CTA)
+    it_count += 1;
+    double tn = 0.0, td = 0.0;
+    if (warp == 0) {
+      for (int b = lane; b < G; b += 32) { tn += __ldcg(cta_part + 2 * b); td += __ldcg(cta_part + 2 * b + 1); }
+      tn = warp_sum(tn);
+      td = warp_sum(td);
+    }
+    if (threadIdx.x == 0) {
+      float df;
+      if (single) {
+        const float s_old = s_loc[0];
+        const float s_new = static_cast<float>(tn) / static_cast<float>(td);          // ops.py:79
+        df = fabsf(s_new - s_old) / s_old;                                            // ops.py:80
+        s_loc[0] = s_new;
+      } else {
+        df = sqrtf(static_cast<float>(tn)) / sqrtf(static_cast<float>(td));           // ops.py:209
+      }
+      const bool conv = !(df > 1e-5f);                                                // `while diff > epsilon`
+      s_stop = (conv || it_count >= max_iters) ? 1 : 0;
+      if (blockIdx.x == 0) {
+        diff[0] = df;
+        iters[0] = it_count;
+        done[0] = conv ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;
+    // the next iteration's exchange reuses cta_part: nobody may overwrite it before every CTA has read this round's
+    // values - guaranteed, because a CTA writes cta_part only after its own pass over the items AND the others can
+    // only reach their next write after the same barrier count; a slow reader is still protected by parity:
+    cta_part += 2 * G * ((it_count & 1) ? 1 : -1);
+  }
+  if (threadIdx.x < n_rows_loc && (!single || blockIdx.x == 0))
+    scale[single ? 0 : blockIdx.x + static_cast<int64_t>(threadIdx.x) * G] = s_loc[threadIdx.x];
+  // leave the workspace counters zeroed: the last CTA out resets them
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(counters + 1, 1u) == static_cast<unsigned int>(G) - 1u) {
+      counters[0] = 0u;
+      counters[1] = 0u;
+    }
+  }
+}
+
 template <typename T, bool ABS>
 static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = l->outer * l->channels * l->inner;
@@ -963,15 +1185,10 @@ extern "C" int dlmcq_obs_sweep_channel(const void* x, int64_t channels, int64_t 
   return dlmcq_obs_sweep_channel_geom(x, channels, inner, dtype, n_bits, is_signed, channels, scale, offset, stream);
 }
 
-extern "C" int dlmcq_obs_sweep_channel_geom(const void* x, int64_t channels, int64_t inner, int dtype, int n_bits,
-                                            int is_signed, int64_t geom_channels, float* scale, float* offset,
-                                            void* stream) {
-  if (!x || !scale || !offset || channels < 1 || inner < 1 || n_bits < 1 || n_bits > 24) return DLMCQ_EINVAL;
-  if (geom_channels < channels) return DLMCQ_EINVAL;
-  if (dtype != DLMCQ_F32 && dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const float qmax = static_cast<float>((1 << n_bits) - 1);
-  const float sdiv = static_cast<float>((1 << (n_bits - 1)) - 1);
+extern "C" int dlmcq_obs_sweep_channel_plan(dlmcq_sweep_item* item, int64_t geom_channels) {
+  if (!item || item->channels < 1 || item->inner < 1) return DLMCQ_EINVAL;
+  if (geom_channels < item->channels) geom_channels = item->channels;
+  const int64_t inner = item->inner;
   // warps per row: enough warps to fill the GPU (>= 8 per SM) when the tensor has few rows - every warp of
   // a row repeats the per-candidate prologue (candidate scale, zero-point, reciprocal: ~100 instructions),
   // so more warps per row than that only add issue slots - and at least 256-512 elements per warp; fewer rows
@@ -990,8 +1207,57 @@ extern "C" int dlmcq_obs_sweep_channel_geom(const void* x, int64_t channels, int
   while (wpr < kSweepWarps && (kSweepWarps / wpr) * row_floats > kSweepSmemFloats) wpr *= 2;
   const int staged = (kSweepWarps / wpr) * row_floats <= kSweepSmemFloats ? 1 : 0;
   const int rows_per_cta = kSweepWarps / wpr;
-  const size_t smem = staged ? static_cast<size_t>(rows_per_cta) * row_floats * sizeof(float) : 0;
-  const int64_t blocks = (channels + rows_per_cta - 1) / rows_per_cta;
+  item->wpr = wpr;
+  item->row_floats = static_cast<int32_t>(row_floats);
+  item->staged = staged;
+  item->smem_bytes = staged ? static_cast<int64_t>(rows_per_cta) * row_floats * static_cast<int64_t>(sizeof(float)) : 0;
+  item->ctas = (item->channels + rows_per_cta - 1) / rows_per_cta;
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_sweep_channel_grouped(const dlmcq_sweep_item* items, const int64_t* cta_prefix, int n_items,
+                                               int64_t total_ctas, int dtype, int64_t smem_bytes, void* stream) {
+  if (!items || !cta_prefix || n_items < 1 || total_ctas < 1 || smem_bytes < 0) return DLMCQ_EINVAL;
+  if (smem_bytes > static_cast<int64_t>(kSweepSmemFloats * sizeof(float)) || total_ctas > 0x7fffffffLL)
+    return DLMCQ_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (dtype == DLMCQ_F32) {
+    e = cudaFuncSetAttribute(sweep_channel_grouped_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kSweepSmemFloats * sizeof(float)));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    sweep_channel_grouped_kernel<float><<<static_cast<unsigned>(total_ctas), kSweepWarps * 32,
+                                          static_cast<size_t>(smem_bytes), st>>>(items, cta_prefix, n_items);
+  } else if (dtype == DLMCQ_BF16) {
+    e = cudaFuncSetAttribute(sweep_channel_grouped_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kSweepSmemFloats * sizeof(float)));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    sweep_channel_grouped_kernel<__nv_bfloat16><<<static_cast<unsigned>(total_ctas), kSweepWarps * 32,
+                                                  static_cast<size_t>(smem_bytes), st>>>(items, cta_prefix, n_items);
+  } else {
+    return DLMCQ_EINVAL;
+  }
+  DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_sweep_channel_geom(const void* x, int64_t channels, int64_t inner, int dtype, int n_bits,
+                                            int is_signed, int64_t geom_channels, float* scale, float* offset,
+                                            void* stream) {
+  if (!x || !scale || !offset || channels < 1 || inner < 1 || n_bits < 1 || n_bits > 24) return DLMCQ_EINVAL;
+  if (geom_channels < channels) return DLMCQ_EINVAL;
+  if (dtype != DLMCQ_F32 && dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float qmax = static_cast<float>((1 << n_bits) - 1);
+  const float sdiv = static_cast<float>((1 << (n_bits - 1)) - 1);
+  dlmcq_sweep_item plan = {};
+  plan.channels = channels;
+  plan.inner = inner;
+  if (int e = dlmcq_obs_sweep_channel_plan(&plan, geom_channels)) return e;
+  const int wpr = plan.wpr, staged = plan.staged;
+  const int64_t row_floats = plan.row_floats;
+  const size_t smem = static_cast<size_t>(plan.smem_bytes);
+  const int64_t blocks = plan.ctas;
   if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
   cudaError_t e;
   if (dtype == DLMCQ_F32) {
@@ -1049,5 +1315,63 @@ extern "C" int dlmcq_obs_l2norm_step(const void* x, int64_t channels, int64_t in
                                                             ws_counter(workspace, 1));
   }
   DLMCQ_LAUNCH_CHECK();
+  return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_obs_l2norm_resident(const void* x, int64_t channels, int64_t inner, int dtype, float* scale,
+                                         const float* offset, int lo, int hi, int max_iters, float* diff,
+                                         int32_t* done, int32_t* iters, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  if (!x || !scale || !diff || !done || !iters || !workspace || channels < 1 || inner < 1 || max_iters < 1)
+    return DLMCQ_EINVAL;
+  if (dtype != DLMCQ_F32 && dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
+  const int64_t segs = (inner + kResSeg - 1) / kResSeg;
+  const int sms = num_sms();
+  int grid;
+  int64_t slots;
+  if (channels == 1) {                               // one row spread over the CTAs
+    if (segs > static_cast<int64_t>(sms) * kResSlots) return DLMCQ_EUNSUPPORTED;
+    grid = static_cast<int>(segs < sms ? segs : sms);
+    slots = (segs + grid - 1) / grid;
+  } else {                                           // whole rows per CTA
+    if (segs > kResSlots) return DLMCQ_EUNSUPPORTED;
+    grid = static_cast<int>(channels < sms ? channels : sms);
+    slots = ((channels + grid - 1) / grid) * segs;
+    if (slots > kResSlots) return DLMCQ_EUNSUPPORTED;                   // not resident
+  }
+  const size_t smem = static_cast<size_t>(slots) * kResSeg * sizeof(float);
+  // workspace: [counters][cta_part: 2 parities x 2*grid doubles]
+  const size_t need = kWsHeaderBytes + 4 * static_cast<size_t>(grid) * sizeof(double) + 16;
+  if (workspace_bytes < need) return DLMCQ_EWORKSPACE;
+  double* cta_part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws_partials(workspace)) + 15) & ~uintptr_t(15));
+  unsigned int* counters = ws_counter(workspace, 2);                    // [2], [3]: zero between calls
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float flo = static_cast<float>(lo), fhi = static_cast<float>(hi);
+  const int segs_i = static_cast<int>(segs);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kResWarps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;        // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (dtype == DLMCQ_F32) {
+    e = cudaFuncSetAttribute(l2norm_resident_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kResSlots * kResSeg * sizeof(float)));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    e = cudaLaunchKernelEx(&cfg, l2norm_resident_kernel<float>, static_cast<const float*>(x), channels, inner, segs_i,
+                           scale, offset, flo, fhi, max_iters, diff, done, iters, cta_part, counters);
+  } else {
+    e = cudaFuncSetAttribute(l2norm_resident_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kResSlots * kResSeg * sizeof(float)));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    e = cudaLaunchKernelEx(&cfg, l2norm_resident_kernel<__nv_bfloat16>, static_cast<const __nv_bfloat16*>(x), channels,
+                           inner, segs_i, scale, offset, flo, fhi, max_iters, diff, done, iters, cta_part, counters);
+  }
+  if (e != cudaSuccess) return set_cuda_error(e);
   return DLMCQ_OK;
 }

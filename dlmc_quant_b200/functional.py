@@ -13,7 +13,7 @@ from ._lib import (BF16, F32, FORM_A1, FORM_AFFINE, FORM_SYM, FORM_ZP, ROOTQ_STA
                    SWEEP_CANDIDATES, DlmcqError, Layout, QParams)
 
 __all__ = ["fq_forward", "fq_backward", "dequantize", "obs_stats", "minmax_from_stats", "absmean_from_stats",
-           "sweep_tensor", "sweep_channel", "kth_values", "l2norm_fixed_point", "adaround_forward", "adaround_backward",
+           "sweep_tensor", "sweep_channel", "sweep_channel_grouped", "kth_values", "l2norm_fixed_point", "adaround_forward", "adaround_backward",
            "adaround_init_alpha", "rootq_act_prepare", "rootq_act_forward", "rootq_act_backward", "rootq_wt_prepare",
            "rootq_wt_forward", "rootq_wt_backward", "GroupedFakeQuant", "GroupedRootQ", "HostFakeQuant", "layout_of"]
 
@@ -370,7 +370,50 @@ def sweep_channel(rows2d, n_bits, signed, geom_channels=None):
     return scale, offset
 
 
-def l2norm_fixed_point(rows2d, scale, offset, lo, hi, max_iters=1000, poll_every=8):
+def sweep_channel_grouped(rows_list, n_bits, signed):
+    """ops.py:169-196 for MANY [channels_i, inner_i] matrices (all weight tensors of a model) in one launch per
+    shared-memory class (rows that stage in <= 48 KB per CTA / the rest) instead of one launch per tensor.  Every
+    tensor keeps the launch geometry of its own call, so the (scale, offset) vectors are bit-identical to
+    sweep_channel(rows_i).  Returns [(scale_i, offset_i)]."""
+    if not rows_list:
+        return []
+    rows_list = [r.detach().contiguous() for r in rows_list]
+    dev, dt = rows_list[0].device, rows_list[0].dtype
+    for r in rows_list:
+        _require_cuda(r, "tensor")
+        if r.dim() != 2 or r.device != dev or r.dtype != dt:
+            raise DlmcqError("sweep_channel_grouped takes [channels, inner] matrices of one dtype on one device")
+    h = _lib.lib()
+    total_ch = sum(r.shape[0] for r in rows_list)
+    flat = torch.empty(2, total_ch, dtype=torch.float32, device=dev)
+    items, outs, c0 = [], [], 0
+    for r in rows_list:
+        ch, inner = r.shape
+        it = _lib.SweepItem()
+        it.x, it.channels, it.inner, it.n_bits, it.is_signed = r.data_ptr(), ch, inner, int(n_bits), int(bool(signed))
+        it.scale, it.offset = flat[0, c0:].data_ptr(), flat[1, c0:].data_ptr()
+        _lib.check(h.dlmcq_obs_sweep_channel_plan(C.byref(it), ch))
+        items.append(it)
+        outs.append((flat[0, c0:c0 + ch], flat[1, c0:c0 + ch]))
+        c0 += ch
+    with torch.cuda.device(dev):
+        for cls in (lambda b: b <= 48 * 1024, lambda b: b > 48 * 1024):
+            sel = [it for it in items if cls(it.smem_bytes)]
+            if not sel:
+                continue
+            arr = (_lib.SweepItem * len(sel))(*sel)
+            prefix, acc = [], 0
+            for it in sel:
+                prefix.append(acc)
+                acc += it.ctas
+            tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            pre = torch.tensor(prefix, dtype=torch.int64).to(dev)
+            _lib.check(h.dlmcq_obs_sweep_channel_grouped(_ptr(tab), _ptr(pre), len(sel), acc, _dtype_code(rows_list[0]),
+                                                         max(it.smem_bytes for it in sel), _stream_ptr()))
+    return outs
+
+
+def l2norm_fixed_point(rows2d, scale, offset, lo, hi, max_iters=1000, poll_every=8, resident=True):
     """ops.py:71-83 / 198-215: iterate s <- sum(x q)/sum(q q + 1e-7) on device until the relative
     change is <= 1e-5.  The loop runs on the device; the host only polls a flag every `poll_every`
     launches.  `max_iters` bounds the search (the reference loops forever on some inputs)."""
@@ -386,6 +429,16 @@ def l2norm_fixed_point(rows2d, scale, offset, lo, hi, max_iters=1000, poll_every
     h = _lib.lib()
     with torch.cuda.device(dev):
         ws, n = _ws_for(rows2d, lay)
+        if resident:
+            # the whole loop in one cooperative launch when the tensor fits in shared memory (every CNN weight matrix)
+            st = h.dlmcq_obs_l2norm_resident(_ptr(rows2d), ch, inner, lay.dtype, _ptr(scale), _ptr(offset), int(lo),
+                                             int(hi), int(max_iters), _ptr(diff), C.c_void_p(flags.data_ptr()),
+                                             C.c_void_p(flags.data_ptr() + 4), _ptr(ws), n, _stream_ptr())
+            if st == 0:
+                f = flags.tolist()
+                return scale, int(f[1]), bool(f[0])
+            if st != -5:                        # anything but "not resident": a real error
+                _lib.check(st)
         it = 0
         while it < max_iters:
             for _ in range(min(poll_every, max_iters - it)):

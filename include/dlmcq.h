@@ -289,6 +289,24 @@ int dlmcq_obs_sweep_channel_geom(const void* x, int64_t channels, int64_t inner,
                                  int is_signed, int64_t geom_channels, float* scale, float* offset,
                                  void* stream);
 
+/* All per-channel sweeps of a model in ONE launch (the 23-54 weight tensors of a CNN cost 50-150 us each when swept
+ * one by one).  Fill x / scale / offset / channels / inner / n_bits / is_signed, let dlmcq_obs_sweep_channel_plan choose
+ * the launch geometry of each item (the same the per-tensor call uses, hence bit-identical results), build
+ * cta_prefix[k] = sum_{j<k} ctas_j (k = 0..n_items-1) and copy both tables to DEVICE memory; smem_bytes = the largest
+ * smem_bytes of the items in the launch (callers may split a model into launches by shared-memory class). */
+typedef struct {
+  const void* x;
+  float* scale;  /* [channels] */
+  float* offset; /* [channels] */
+  int64_t channels, inner;
+  int32_t n_bits, is_signed;
+  int32_t wpr, row_floats, staged, pad; /* filled by dlmcq_obs_sweep_channel_plan */
+  int64_t smem_bytes, ctas;             /* filled by dlmcq_obs_sweep_channel_plan */
+} dlmcq_sweep_item;
+int dlmcq_obs_sweep_channel_plan(dlmcq_sweep_item* item_host, int64_t geom_channels);
+int dlmcq_obs_sweep_channel_grouped(const dlmcq_sweep_item* items, const int64_t* cta_prefix, int n_items,
+                                    int64_t total_ctas, int dtype, int64_t smem_bytes, void* stream);
+
 /* ops.py:71-83,198-215 l2norm fixed point, one iteration over rows [channels, inner]
  * (channels=1 for the per-tensor form):
  *   q = A1 codes(x, scale, offset);  new_scale[c] = sum(x*q)/sum(q*q + 1e-7)
@@ -299,6 +317,16 @@ int dlmcq_obs_l2norm_step(const void* x, int64_t channels, int64_t inner, int dt
                           float* scale, const float* offset, int lo, int hi,
                           float* diff, int32_t* done, int32_t* iters,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* The whole fixed-point loop in ONE launch for tensors that fit in the GPU's shared memory (channels * ceil(inner/2048)
+ * <= 24 * #SMs staged 8 KB items, i.e. up to ~7 M elements - every per-channel CNN weight matrix): rows are staged on
+ * chip once and iterated there, convergence is decided on the device (grid barriers, cooperative launch), no HBM
+ * re-reads and no host polling.  `scale` holds the starting scales and receives the result; *iters the iteration count,
+ * *done whether `diff <= 1e-5` was reached within max_iters, *diff the last convergence measure.
+ * Returns DLMCQ_EUNSUPPORTED when the tensor is too large to be resident (use dlmcq_obs_l2norm_step then). */
+int dlmcq_obs_l2norm_resident(const void* x, int64_t channels, int64_t inner, int dtype, float* scale,
+                              const float* offset, int lo, int hi, int max_iters, float* diff, int32_t* done,
+                              int32_t* iters, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- grouped (multi-tensor) launches --------------------------------------------------
  * All weight tensors of a model in ONE launch: the per-layer tensors of a CNN (<= 9.4 MB)
