@@ -122,6 +122,8 @@ SIGNATURES = {
     "dlmcq_obs_kth_hist": (_I, [_P, _L, _I, _I, _I, _P, _P]),
     "dlmcq_obs_kth_select": (_I, [_I, _P, _P]),
     "dlmcq_obs_kth_values": (_I, [_P, _P, _P]),
+    "dlmcq_obs_kth_fast_workspace_bytes": (_Z, [_L]),
+    "dlmcq_obs_kth_fast": (_I, [_P, _L, _I, _I, _L, _L, _P, _P, _P, _Z, _P]),
     "dlmcq_obs_sweep_tensor_sse": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _Z, _P]),
     "dlmcq_obs_sweep_tensor_finalize": (_I, [_P, _P, _D, _I, _I, _P, _P, _P, _P]),
     "dlmcq_obs_sweep_channel": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P]),

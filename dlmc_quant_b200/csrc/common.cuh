@@ -154,6 +154,21 @@ __device__ __forceinline__ bool take_last_ticket(unsigned int* counter, unsigned
   return is_last;
 }
 
+// Grid-wide barrier for cooperatively launched kernels (all CTAs co-resident): a monotonically increasing arrival
+// counter; barrier number b (1-based) completes when it reaches b * gridDim.x.  The counter must be zero at launch.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
 // Workspace layout: [0,256) bytes = ticket counters, then float partials.
 constexpr size_t kWsHeaderBytes = 256;
 __host__ __device__ inline float* ws_partials(void* ws) {

@@ -875,26 +875,6 @@ constexpr int kResSeg = 2048;                       // floats per staged item (o
 constexpr int kResSlots = 24;                       // items per CTA at most: 24 x 8 KB = 192 KB
 constexpr int kResWarps = 8;
 
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-    } while (seen < target);
-  }
-  __syncthreads();
-}
-
-// Work distribution: a row and all its 2048-element segments live in ONE CTA (row r -> CTA r % G), so a row's new
-// scale never leaves the CTA: after the warps' pass over the staged items, one thread per local row folds the row's
-// segment sums (shared memory), forms s_new and the row's share of the convergence norm; only the CTA's (num, den)
-// pair goes to global memory - ONE grid barrier per iteration - and every CTA then evaluates the same test from the
-// same G pairs in the same order.  The per-tensor form (one row spread over all CTAs, item i -> CTA i % G) exchanges
-// the CTA's (sum x*code, sum code^2) instead and every CTA forms the same s_new.  Scales stay in shared memory /
-// registers during the loop and are written back once.
 template <typename T>
 __global__ void __launch_bounds__(kResWarps * 32, 1)
 l2norm_resident_kernel(const T* __restrict__ x, int64_t channels, int64_t inner, int segs, float* __restrict__ scale,

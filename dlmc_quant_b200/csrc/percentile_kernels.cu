@@ -179,6 +179,315 @@ __global__ void radix_values_kernel(const RadixState* __restrict__ state, float*
   if (threadIdx.x < state->n_ranks) values[threadIdx.x] = radix_unkey(state->prefix[threadIdx.x]);
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path: ONE full read instead of three.
+//
+// An order statistic near the tails (what a percentile-clipping observer asks for) can be bracketed from a small
+// sample: with S pseudo-randomly placed samples the k-th of N elements lies, with probability ~1 - 1e-9, between the
+// sample order statistics of rank k*S/N -+ (6*sqrt(S*p*(1-p)) + 3).  So:
+//   1. kth_sample_kernel   (1 CTA): gather S = 16384 keys, radix-select the two bracketing sample keys per rank;
+//   2. kth_collect_kernel  (full read, streaming): per rank count the elements BELOW the bracket (registers) and append
+//                          the few inside it (<= ~1 % of N for p >= 0.99; warp-aggregated appends);
+//   3. kth_resolve_kernel  (1 CTA): the answer is the (k - below)-th smallest candidate - exact radix select over the
+//                          candidate keys; if the bracket missed (k - below outside [1, #candidates], or the
+//                          candidate buffer overflowed) the status word says so and the caller runs the three-pass
+//                          histogram select above.  Exactness never depends on the sample, only the speed does.
+// ---------------------------------------------------------------------------------------
+constexpr int kKthSample = 16384;
+constexpr int kKthCtaThreads = 1024;
+
+struct KthFastState {
+  unsigned int lo_key[2], hi_key[2];     // bracket per rank (inclusive)
+  unsigned long long below[2];           // elements with key < lo_key
+  unsigned long long eq_lo[2], eq_hi[2]; // elements equal to a bracket end: counted, never stored (post-ReLU zeros,
+                                         // saturated maxima: one value may be half of the tensor)
+  unsigned int n_cand[2];                // elements strictly inside the bracket (stored)
+  unsigned int overflow;
+  unsigned int n_ranks;
+  unsigned long long rank[2];
+};
+
+// Digit selection shared by the single-CTA and the cooperative selects: `hist` (2048 bins in shared memory, unused
+// bins zero) holds the histogram of digit `pass` among the keys that match `prefix`; finds the bin that contains the
+// 1-based rank *rank_io (shared), appends its digit to `prefix` and reduces the rank.  blockDim.x == 1024.
+__device__ unsigned int cta_scan_select(const unsigned int* hist, unsigned long long* rank_io, unsigned int prefix,
+                                        int pass) {
+  __shared__ unsigned int s_warp[32];
+  __shared__ unsigned int s_digit;
+  const unsigned int b0 = hist[2 * threadIdx.x], b1 = hist[2 * threadIdx.x + 1];
+  unsigned int incl = b0 + b1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;                           // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned long long rank = *rank_io;
+  const unsigned long long excl = (warp ? s_warp[warp - 1] : 0u) + static_cast<unsigned long long>(incl - (b0 + b1));
+  __syncthreads();
+  if (rank > excl && rank <= excl + b0 + b1) {  // exactly one thread (rank <= population by construction)
+    const bool second = rank > excl + b0;
+    s_digit = 2 * threadIdx.x + (second ? 1 : 0);
+    *rank_io = rank - excl - (second ? b0 : 0u);
+  }
+  __syncthreads();
+  const unsigned int out = (pass == 0 ? 0u : prefix << (pass == 2 ? 10 : 11)) | s_digit;
+  __syncthreads();
+  return out;
+}
+
+// r-th smallest (1-based) of keys[0..n) by an 11/11/10-bit radix select run by one whole CTA (blockDim 1024);
+// hist: 2048 unsigned ints of shared memory.  Every thread returns the key.
+__device__ unsigned int cta_radix_select(const unsigned int* __restrict__ keys, unsigned int n, unsigned long long r,
+                                         unsigned int* hist) {
+  __shared__ unsigned long long s_rank;
+  unsigned int prefix = 0;
+  if (threadIdx.x == 0) s_rank = r;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = radix_shift(pass);
+    const unsigned int mask = radix_mask(pass);
+    const int up = pass == 0 ? 32 : radix_shift(pass - 1);
+    for (int k = threadIdx.x; k < kRadixBins; k += blockDim.x) hist[k] = 0u;
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int key = keys[i];
+      if (pass == 0 || (key >> up) == prefix) atomicAdd(hist + ((key >> shift) & mask), 1u);
+    }
+    __syncthreads();
+    prefix = cta_scan_select(hist, &s_rank, prefix, pass);
+  }
+  return prefix;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kKthCtaThreads)
+kth_sample_kernel(const T* __restrict__ x, int64_t n, int abs_input, unsigned long long rank0, unsigned long long rank1,
+                  unsigned int n_ranks, KthFastState* __restrict__ st, unsigned int* __restrict__ sample) {
+  __shared__ unsigned int hist[kRadixBins];
+  for (int i = threadIdx.x; i < kKthSample; i += blockDim.x) {
+    // multiplicative hash -> a fixed pseudo-random position in [0, n): regular strides would alias with periodic data
+    const unsigned int hsh = static_cast<unsigned int>(i) * 2654435761u + 0x9e3779b9u;
+    const int64_t idx = static_cast<int64_t>((static_cast<unsigned long long>(hsh) * static_cast<unsigned long long>(n)) >> 32);
+    sample[i] = radix_key(to_f32<T>(x[idx]), abs_input != 0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->below[0] = st->below[1] = 0ull;
+    st->eq_lo[0] = st->eq_lo[1] = st->eq_hi[0] = st->eq_hi[1] = 0ull;
+    st->n_cand[0] = st->n_cand[1] = 0u;
+    st->overflow = 0u;
+    st->n_ranks = n_ranks;
+    st->rank[0] = rank0;
+    st->rank[1] = rank1;
+  }
+  for (unsigned int j = 0; j < n_ranks; ++j) {
+    const double k = static_cast<double>(j == 0 ? rank0 : rank1);
+    const double p = k / static_cast<double>(n);
+    const double ks = p * kKthSample;
+    const double delta = 6.0 * sqrt(kKthSample * p * (1.0 - p)) + 3.0;
+    const long long i_lo = static_cast<long long>(floor(ks - delta)), i_hi = static_cast<long long>(ceil(ks + delta));
+    unsigned int lo_key = 0u, hi_key = 0xffffffffu;
+    if (i_lo >= 1) lo_key = cta_radix_select(sample, kKthSample, static_cast<unsigned long long>(i_lo), hist);
+    if (i_hi <= kKthSample) hi_key = cta_radix_select(sample, kKthSample, static_cast<unsigned long long>(i_hi), hist);
+    if (threadIdx.x == 0) { st->lo_key[j] = lo_key; st->hi_key[j] = hi_key; }
+  }
+}
+
+// One rank's share of a vector: counters from float compares (the key order is the float order; NaN fails every
+// compare and is - correctly - neither below nor inside any bracket), and - rarely - the append of the elements strictly
+// inside the bracket: per-lane count -> warp exclusive scan -> ONE atomic per warp -> ordered stores.
+struct KthRank {
+  unsigned int lo, hi;       // bracket keys
+  float flo, fhi;            // their float images
+  unsigned int below, el, eh;
+};
+template <int N, bool ABS>
+__device__ __forceinline__ void kth_visit_vec(const float (&f)[N], bool ok, KthRank& r, unsigned int* __restrict__ n_cand,
+                                              unsigned int* __restrict__ cand, unsigned int cap,
+                                              unsigned int* __restrict__ overflow, int lane) {
+  unsigned int nb = 0, ne = 0, nh = 0, na = 0;
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+    const float v = ABS ? fabsf(f[e]) : f[e];
+    nb += v < r.flo ? 1u : 0u;
+    ne += v == r.flo ? 1u : 0u;
+    nh += v == r.fhi ? 1u : 0u;
+    na += v > r.fhi ? 1u : 0u;
+  }
+  if (r.hi == r.lo) nh = 0;                       // a degenerate bracket: equality is counted once
+  if (ok) { r.below += nb; r.el += ne; r.eh += nh; }
+  const bool maybe_inside = ok && (nb + ne + nh + na != N);      // something strictly inside, or a NaN
+  if (__any_sync(0xffffffffu, maybe_inside)) {
+    unsigned int keys[N], cnt = 0;
+    bool in[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      keys[e] = radix_key(f[e], ABS);
+      in[e] = ok && keys[e] > r.lo && keys[e] < r.hi;
+      cnt += in[e] ? 1u : 0u;
+    }
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      unsigned int base = 0;
+      if (lane == 0) base = atomicAdd(n_cand, total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      unsigned int pos = base + incl - cnt;
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        if (in[e]) {
+          if (pos < cap) cand[pos] = keys[e]; else *overflow = 1u;
+          ++pos;
+        }
+      }
+    }
+  }
+}
+
+template <typename T, bool ABS, bool TWO>
+__global__ void __launch_bounds__(kThreads, 4)
+kth_collect_kernel(const T* __restrict__ x, int64_t n, KthFastState* __restrict__ st,
+                   unsigned int* __restrict__ cand /* [2][cap] */, unsigned int cap) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  const int lane = threadIdx.x & 31;
+  KthRank r0{st->lo_key[0], st->hi_key[0], radix_unkey(st->lo_key[0]), radix_unkey(st->hi_key[0]), 0u, 0u, 0u};
+  KthRank r1{0u, 0u, 0.f, 0.f, 0u, 0u, 0u};
+  if (TWO) r1 = KthRank{st->lo_key[1], st->hi_key[1], radix_unkey(st->lo_key[1]), radix_unkey(st->hi_key[1]), 0u, 0u, 0u};
+  auto visit = [&](const float (&f)[V::N], bool ok) {
+    kth_visit_vec<V::N, ABS>(f, ok, r0, &st->n_cand[0], cand, cap, &st->overflow, lane);
+    if (TWO) kth_visit_vec<V::N, ABS>(f, ok, r1, &st->n_cand[1], cand + cap, cap, &st->overflow, lane);
+  };
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+  const int64_t nvec = aligned ? n / V::N : 0;
+  const raw* xv = reinterpret_cast<const raw*>(x);
+  constexpr int U = 4;
+  const int64_t full = nvec / (U * stride) * (U * stride);       // whole warps take part in every shuffle
+  for (; i < full; i += U * stride) {
+    raw r[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) r[k] = ld_stream(xv + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      float f[V::N];
+      V::unpack(r[k], f);
+      visit(f, true);
+    }
+  }
+  const int64_t tail_iters = (nvec - full + stride - 1) / stride;
+  for (int64_t t = 0; t < tail_iters; ++t, i += stride) {
+    const bool ok = i < nvec;
+    float f[V::N];
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) f[e] = 0.f;
+    if (ok) V::unpack(ld_stream(xv + i), f);
+    visit(f, ok);
+  }
+  // scalar remainder (and everything, for an unaligned pointer): one element per lane in slot 0 of a vector
+  const int64_t rest0 = nvec * V::N;
+  const int64_t rest_iters = (n - rest0 + stride - 1) / stride;
+  int64_t j = rest0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int64_t t = 0; t < rest_iters; ++t, j += stride) {
+    const bool ok = j < n;
+    float f[V::N];
+    // padding values must classify as "above" so that they change no counter: NaN does (fails every compare)
+    const float pad = __uint_as_float(0x7fc00000u);
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) f[e] = pad;
+    if (ok) f[0] = to_f32<T>(x[j]);
+    // count only slot 0: temporarily classify the padded vector, then undo nothing (NaN pads add to no counter)
+    visit(f, ok);
+  }
+  unsigned long long c[6] = {r0.below, r1.below, r0.el, r1.el, r0.eh, r1.eh};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
+  }
+  if (lane == 0) {
+    if (c[0]) atomicAdd(&st->below[0], c[0]);
+    if (c[1]) atomicAdd(&st->below[1], c[1]);
+    if (c[2]) atomicAdd(&st->eq_lo[0], c[2]);
+    if (c[3]) atomicAdd(&st->eq_lo[1], c[3]);
+    if (c[4]) atomicAdd(&st->eq_hi[0], c[4]);
+    if (c[5]) atomicAdd(&st->eq_hi[1], c[5]);
+  }
+}
+
+// Resolve, cooperatively: every CTA histograms its slice of the candidate keys (shared memory, then the non-empty
+// bins into a global histogram), a grid barrier, and every CTA finds the same digit from the same global histogram -
+// three digits per rank, six barriers at most, whatever the candidate count (a single CTA needed ~100 us per pass for
+// the ~0.3 % of a 2^28-element tensor a tail bracket collects).
+__global__ void __launch_bounds__(kKthCtaThreads, 1)
+kth_resolve_kernel(const KthFastState* __restrict__ st, const unsigned int* __restrict__ cand, unsigned int cap,
+                   unsigned int* __restrict__ ghist /* [2 ranks][3 passes][2048], zeroed */,
+                   unsigned int* __restrict__ counter /* zeroed */, float* __restrict__ values,
+                   int32_t* __restrict__ status) {
+  __shared__ unsigned int hist[kRadixBins];
+  __shared__ unsigned long long s_rank;
+  bool ok = st->overflow == 0u;
+  const unsigned int nr = st->n_ranks;
+  unsigned int barrier_no = 0;
+  for (unsigned int j = 0; j < nr; ++j) {
+    const unsigned long long k = st->rank[j], below = st->below[j], el = st->eq_lo[j], eh = st->eq_hi[j];
+    const unsigned int nc = st->n_cand[j];
+    if (!ok || nc > cap || k <= below || k > below + el + nc + eh) { ok = false; continue; }   // the bracket missed
+    const unsigned long long r = k - below;
+    unsigned int key;
+    if (r <= el) {
+      key = st->lo_key[j];
+    } else if (r > el + nc) {
+      key = st->hi_key[j];
+    } else {                                   // uniform across the grid: every CTA takes the same branch
+      const unsigned int* keys = cand + static_cast<size_t>(j) * cap;
+      unsigned int prefix = 0;
+      if (threadIdx.x == 0) s_rank = r - el;
+      for (int pass = 0; pass < 3; ++pass) {
+        const int shift = radix_shift(pass);
+        const unsigned int mask = radix_mask(pass);
+        const int up = pass == 0 ? 32 : radix_shift(pass - 1);
+        unsigned int* gh = ghist + (static_cast<size_t>(j) * 3 + pass) * kRadixBins;
+        for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[b] = 0u;
+        __syncthreads();
+        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+          const unsigned int kk = __ldcg(keys + i);
+          if (pass == 0 || (kk >> up) == prefix) atomicAdd(hist + ((kk >> shift) & mask), 1u);
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x)
+          if (hist[b]) atomicAdd(gh + b, hist[b]);
+        barrier_no += 1;
+        grid_barrier(counter, barrier_no * gridDim.x);
+        for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[b] = __ldcg(gh + b);
+        __syncthreads();
+        prefix = cta_scan_select(hist, &s_rank, prefix, pass);
+      }
+      key = prefix;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) values[j] = radix_unkey(key);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = ok ? 1 : 0;
+}
+
 }  // namespace dlmcq
 
 using namespace dlmcq;
@@ -238,3 +547,73 @@ extern "C" int dlmcq_obs_kth_values(const void* state, float* values, void* stre
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
 }
+
+extern "C" size_t dlmcq_obs_kth_fast_workspace_bytes(int64_t numel) {
+  if (numel < 1) return 0;
+  int64_t cap = numel / 16;
+  if (cap < 65536) cap = 65536;
+  return 512 + static_cast<size_t>(kKthSample) * 4 + 6 * static_cast<size_t>(kRadixBins) * 4 +
+         2 * static_cast<size_t>(cap) * 4;
+}
+
+extern "C" int dlmcq_obs_kth_fast(const void* x, int64_t numel, int dtype, int flags, int64_t rank0, int64_t rank1,
+                                  float* values, int32_t* status, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (!x || !values || !status || !workspace || numel < 1 || rank0 < 1 || rank1 < 0) return DLMCQ_EINVAL;
+  if (rank0 > numel || rank1 > numel) return DLMCQ_EINVAL;
+  if (dtype != DLMCQ_F32 && dtype != DLMCQ_BF16) return DLMCQ_EINVAL;
+  if (workspace_bytes < dlmcq_obs_kth_fast_workspace_bytes(numel)) return DLMCQ_EWORKSPACE;
+  if (numel < 4 * kKthSample) return DLMCQ_EUNSUPPORTED;          // small tensors: the three-pass select is already cheap
+  int64_t cap64 = numel / 16;
+  if (cap64 < 65536) cap64 = 65536;
+  if (cap64 > 0x7fffffffLL) cap64 = 0x7fffffffLL;
+  const unsigned int cap = static_cast<unsigned int>(cap64);
+  KthFastState* st = static_cast<KthFastState*>(workspace);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 256);
+  unsigned int* sample = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 512);
+  unsigned int* ghist = sample + kKthSample;
+  unsigned int* cand = ghist + 6 * kRadixBins;
+  cudaStream_t stm = static_cast<cudaStream_t>(stream);
+  const int abs_input = (flags & DLMCQ_STATS_ABS_INPUT) ? 1 : 0;
+  const unsigned int nr = rank1 > 0 ? 2u : 1u;
+  const unsigned long long k0 = static_cast<unsigned long long>(rank0), k1 = static_cast<unsigned long long>(rank1);
+  const int64_t vn = dtype == DLMCQ_F32 ? 4 : 8;
+  const int grid = stream_grid((numel / vn + kThreads * 4 - 1) / (kThreads * 4), 8);
+#define DLMCQ_KTH_LAUNCH(T)                                                                                        \
+  do {                                                                                                             \
+    const T* xt = static_cast<const T*>(x);                                                                        \
+    kth_sample_kernel<T><<<1, kKthCtaThreads, 0, stm>>>(xt, numel, abs_input, k0, k1, nr, st, sample);            \
+    DLMCQ_LAUNCH_CHECK();                                                                                          \
+    if (abs_input) {                                                                                               \
+      if (nr > 1) kth_collect_kernel<T, true, true><<<grid, kThreads, 0, stm>>>(xt, numel, st, cand, cap);         \
+      else kth_collect_kernel<T, true, false><<<grid, kThreads, 0, stm>>>(xt, numel, st, cand, cap);               \
+    } else {                                                                                                       \
+      if (nr > 1) kth_collect_kernel<T, false, true><<<grid, kThreads, 0, stm>>>(xt, numel, st, cand, cap);        \
+      else kth_collect_kernel<T, false, false><<<grid, kThreads, 0, stm>>>(xt, numel, st, cand, cap);              \
+    }                                                                                                              \
+  } while (0)
+  if (dtype == DLMCQ_F32) DLMCQ_KTH_LAUNCH(float);
+  else DLMCQ_KTH_LAUNCH(__nv_bfloat16);
+#undef DLMCQ_KTH_LAUNCH
+  DLMCQ_LAUNCH_CHECK();
+  // barrier counter + the six global histograms of the cooperative resolve
+  cudaError_t e = cudaMemsetAsync(counter, 0, 256, stm);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  e = cudaMemsetAsync(ghist, 0, 6 * kRadixBins * sizeof(unsigned int), stm);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms());
+  cfg.blockDim = dim3(kKthCtaThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stm;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;        // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kth_resolve_kernel, static_cast<const KthFastState*>(st),
+                         static_cast<const unsigned int*>(cand), cap, ghist, counter, values, status);
+  if (e != cudaSuccess) return set_cuda_error(e);
+  return DLMCQ_OK;
+}
+

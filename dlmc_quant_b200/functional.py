@@ -294,7 +294,7 @@ def absmean_from_stats(stats, count, mul_a, mul_b, mode):
     return out
 
 
-def kth_values(x, ranks, abs_input=False, reduce_hist=None):
+def kth_values(x, ranks, abs_input=False, reduce_hist=None, fast=True):
     """Exact order statistics: the ranks[j]-th smallest elements (1-based, at most two ranks) of x or |x| by a
     3-pass radix select - equal to torch.kthvalue.  reduce_hist (multi-GPU): called on the int32 histogram of each
     pass (e.g. an all-reduce SUM) so that the result is the order statistic of the union of all ranks' tensors."""
@@ -304,9 +304,21 @@ def kth_values(x, ranks, abs_input=False, reduce_hist=None):
     if not 1 <= len(ranks) <= 2 or min(ranks) < 1:
         raise DlmcqError("kth_values takes one or two ranks >= 1")
     h = _lib.lib()
-    state = torch.zeros(h.dlmcq_obs_kth_state_bytes(), dtype=torch.uint8, device=x.device)
     values = torch.empty(2, dtype=torch.float32, device=x.device)
     flags = 1 if abs_input else 0
+    if reduce_hist is None and fast and x.numel() >= 65536:
+        # single GPU: one full read (sample bracket -> count + collect -> exact select among the candidates); the
+        # status word (one host read, calibration time only) says whether the bracket held - else the 3-pass select
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            nws = h.dlmcq_obs_kth_fast_workspace_bytes(x.numel())
+            ws = _workspace(x.device, nws)
+            _lib.check(h.dlmcq_obs_kth_fast(_ptr(x), x.numel(), _dtype_code(x), flags, ranks[0],
+                                            ranks[1] if len(ranks) > 1 else 0, _ptr(values),
+                                            C.c_void_p(status.data_ptr()), _ptr(ws), nws, _stream_ptr()))
+        if int(status.item()) == 1:
+            return values[:len(ranks)]
+    state = torch.zeros(h.dlmcq_obs_kth_state_bytes(), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         st = _stream_ptr()
         _lib.check(h.dlmcq_obs_kth_begin(_ptr(state), ranks[0], ranks[1] if len(ranks) > 1 else 0, st))

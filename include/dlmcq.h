@@ -264,6 +264,16 @@ int dlmcq_obs_kth_hist(const void* x, int64_t numel, int dtype, int flags, int p
 int dlmcq_obs_kth_select(int pass, void* state, void* stream);
 int dlmcq_obs_kth_values(const void* state, float* values, void* stream);
 
+/* The same order statistics in ONE full read (single GPU): the k-th element is bracketed from 16 384 pseudo-randomly
+ * placed samples, the read counts what lies below the bracket and collects the few elements inside it, and an exact
+ * radix select over those candidates gives the answer.  *status (device) = 1: values[] hold the exact result;
+ * 0: the bracket missed or the candidate buffer overflowed (probability ~1e-9 per call; also any
+ * adversarial input) - run the three-pass select above.  Returns DLMCQ_EUNSUPPORTED for numel < 65 536 (use the
+ * three-pass form).  Never approximate: the sample only decides the speed. */
+size_t dlmcq_obs_kth_fast_workspace_bytes(int64_t numel);
+int dlmcq_obs_kth_fast(const void* x, int64_t numel, int dtype, int flags, int64_t rank0, int64_t rank1, float* values,
+                       int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ops.py:36-68 quantize_l2loss_tensor (unsigned branch): 80-candidate clip-ratio sweep.
  * Pass 1 (dlmcq_obs_stats) gives min/max; this pass accumulates the 80 squared-error sums
  * sse[80] in one read of x; the finalize picks the first strict minimum below 1000 of
