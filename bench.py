@@ -305,32 +305,41 @@ def run_ours(args, rank, world, device):
 
 
 def run_e2e(args, wl, rank, world, device):
-    """Same workload through the host-buffer C-ABI call: pinned host x, dy in; y, dx, dscale out."""
+    """Same workload through the host-buffer C-ABI calls (caller-owned dlmcq_host_ctx): pinned HOST x, dy in, results
+    back in host memory, H2D / D2H inside the timed region.
+
+    Headline (`value`): the compact LOSSLESS result format - packed 4-bit codes (y = code * s' + offset, bit-identical
+    to the fp32 forward) and one keep bit per element (dx = keep ? dy : 0) - through dlmcq_host_ctx_fq_codes; inputs
+    stay fp32, the arithmetic is the same fp32 arithmetic as `value` above.  `full_format` repeats the measurement with
+    y and dx returned as fp32 tensors (dlmcq_host_ctx_fq_forward_backward, the round-1 format)."""
     import torch.distributed as dist
     if args.no_e2e:
         return None
     F, lib = wl.F, wl.lib
     steps = max(1, min(args.steps, args.e2e_steps))
     hq = F.HostFakeQuant(device, chunk_elems=1 << 22)
-    # One pinned buffer set sized to the largest layer, reused by all 54 layers: the bytes that cross PCIe
-    # per step are exactly the workload's (every layer's x, dy in and y, dx out), while host memory stays
-    # at 4 x 411 MB per rank instead of 4 x 5.5 GB (8 ranks would not fit the box's RAM otherwise).
+    # INPUTS: one pinned (x, dy) pair sized to the largest layer, read by all 54 layers - the bytes that cross PCIe per
+    # step are exactly the workload's, while pinned memory stays at 2 x 411 MB per rank (8 ranks x 54 layers of fp32
+    # inputs would not fit the box's RAM).  OUTPUTS: every layer owns its slice, so all results of a step are
+    # consumable after the step.
     nmax = max(a["n"] for a in wl.acts)
     big = max(wl.acts, key=lambda a: a["n"])
     hx_all, hdy_all = big["x"].reshape(-1).cpu().pin_memory(), big["dy"].reshape(-1).cpu().pin_memory()
-    hy_all, hdx_all = torch.empty(nmax).pin_memory(), torch.empty(nmax).pin_memory()
-    host = []
+    codes_all = torch.empty(sum((a["n"] + 1) // 2 for a in wl.acts), dtype=torch.uint8).pin_memory()
+    keep_all = torch.empty(sum((a["n"] + 7) // 8 for a in wl.acts), dtype=torch.uint8).pin_memory()
+    host, c0, k0 = [], 0, 0
     for a in wl.acts:
         n = a["n"]
-        host.append((hx_all[:n], hdy_all[:n], hy_all[:n], hdx_all[:n], float(a["scale"]), float(a["off"]),
-                     a["qp"].lo, a["qp"].hi, a["qp"].g))
+        host.append((hx_all[:n], hdy_all[:n], codes_all[c0:c0 + (n + 1) // 2], keep_all[k0:k0 + (n + 7) // 8],
+                     float(a["scale"]), float(a["off"]), a["qp"].lo, a["qp"].hi, a["qp"].g))
+        c0 += (n + 1) // 2
+        k0 += (n + 7) // 8
     hw = [(w["x"].cpu().pin_memory(), w["dy"].cpu().pin_memory(), torch.empty_like(w["x"], device="cpu").pin_memory(),
            torch.empty_like(w["x"], device="cpu").pin_memory()) for w in wl.wts]
     hds = torch.empty(wl.dscale.numel(), dtype=torch.float32).pin_memory()
+    hy_full = hdx_full = None
 
-    def step():
-        for i, (hx, hdy, hy, hdx, s, o, lo, hi, g) in enumerate(host):       # enqueue all layers, drain once
-            hq.forward_backward_async(hx, hdy, hy, hdx, hds[i:i + 1], s, o, lo, hi, form=lib.FORM_AFFINE, g=g)
+    def weights_roundtrip():
         for w, (hx, hdy, hy, hdx) in zip(wl.wts, hw):
             w["x"].copy_(hx, non_blocking=True)
             w["dy"].copy_(hdy, non_blocking=True)
@@ -339,29 +348,62 @@ def run_e2e(args, wl, rank, world, device):
             hy.copy_(w["y"], non_blocking=True)
             hdx.copy_(w["dx"], non_blocking=True)
         hds[len(host):].copy_(wl.dscale[len(host):], non_blocking=True)
+
+    def step_compact():
+        for i, (hx, hdy, hc, hk, s, o, lo, hi, g) in enumerate(host):       # enqueue all layers, drain once
+            hq.codes_async(hx, hdy, hc, hk, hds[i:i + 1], s, o, lo, hi, form=lib.FORM_AFFINE, g=g, pack4=True)
+        weights_roundtrip()
         hq.synchronize()
         torch.cuda.synchronize()
 
-    step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    if world > 1:
-        dist.barrier()
-    dt = torch.tensor([time.perf_counter() - t0], device=device)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt)
-    h2d = 2 * 4 * wl.elems
-    d2h = 2 * 4 * wl.elems + 4 * wl.dscale.numel()
-    return {"value": round(wl.elems * world * steps * (BYTES_FWD + BYTES_BWD) / dt / 1e9, 2), "unit": UNIT,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-            "ms_per_step": round(dt / steps * 1e3, 2), "host_buffers": "pinned, one set sized to the largest layer, reused by all layers",
-            "api": "dlmcq_host_fq_forward_backward_async per layer + one dlmcq_host_synchronize (activations); H2D/grouped launch/D2H (weights)"}
+    def step_full():
+        for i, (hx, hdy, hc, hk, s, o, lo, hi, g) in enumerate(host):
+            n = hx.numel()
+            hq.forward_backward_async(hx, hdy, hy_full[:n], hdx_full[:n], hds[i:i + 1], s, o, lo, hi,
+                                      form=lib.FORM_AFFINE, g=g)
+        weights_roundtrip()
+        hq.synchronize()
+        torch.cuda.synchronize()
 
+    def timed(step):
+        step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        if world > 1:
+            dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt)
+
+    dt = timed(step_compact)
+    wbytes = 4 * wl.wt_elems
+    h2d = 2 * 4 * wl.act_elems + 2 * wbytes
+    d2h = codes_all.numel() + keep_all.numel() + 2 * wbytes + 4 * wl.dscale.numel()
+    out = {"value": round(wl.elems * world * steps * (BYTES_FWD + BYTES_BWD) / dt / 1e9, 2), "unit": UNIT,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps, "ms_per_step": round(dt / steps * 1e3, 2),
+           "result_format": "activations: packed 4-bit codes + 1 keep bit per element (lossless: y = code*s'+offset, "
+                            "dx = keep ? dy : 0); weights: fp32 y, dx",
+           "host_buffers": "pinned; inputs: one (x, dy) pair sized to the largest layer, read by all layers; outputs: "
+                           "every layer has its own slice (all results of a step are consumable)",
+           "api": "dlmcq_host_ctx_fq_codes per layer on a caller-owned dlmcq_host_ctx + one dlmcq_host_ctx_synchronize "
+                  "(activations); H2D / grouped launch / D2H (weights)"}
+    try:
+        hy_full, hdx_full = torch.empty(nmax).pin_memory(), torch.empty(nmax).pin_memory()
+        dtf = timed(step_full)
+        out["full_format"] = {"value": round(wl.elems * world * steps * (BYTES_FWD + BYTES_BWD) / dtf / 1e9, 2),
+                              "ms_per_step": round(dtf / steps * 1e3, 2), "h2d_bytes_per_step": h2d,
+                              "d2h_bytes_per_step": 2 * 4 * wl.act_elems + 2 * wbytes + 4 * wl.dscale.numel(),
+                              "result_format": "fp32 y and dx (outputs share one buffer pair: not consumable per layer)",
+                              "api": "dlmcq_host_ctx_fq_forward_backward"}
+    except Exception as e:
+        out["full_format"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    hq.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------

@@ -139,10 +139,11 @@ SIGNATURES = {
     "dlmcq_bnq_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(BnqDesc), _QP, _P, _Z, _P]),
     "dlmcq_bnq_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(BnqDesc), _QP, _P, _Z,
                                 _P]),
-    "dlmcq_host_staging_bytes": (_Z, [_L, _I]),
-    "dlmcq_host_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
-    "dlmcq_host_fq_forward_backward_async": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P, _Z, _L]),
-    "dlmcq_host_synchronize": (_I, []),
+    "dlmcq_host_ctx_create": (_I, [C.POINTER(C.c_void_p), _L]),
+    "dlmcq_host_ctx_destroy": (_I, [_P]),
+    "dlmcq_host_ctx_synchronize": (_I, [_P]),
+    "dlmcq_host_ctx_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F]),
+    "dlmcq_host_ctx_fq_codes": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _I]),
 }
 
 

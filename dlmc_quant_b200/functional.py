@@ -747,38 +747,62 @@ class GroupedRootQ:
 
 
 class HostFakeQuant:
-    """End-to-end path for HOST tensors (pinned memory): forward + backward with the H2D / D2H
-    copies pipelined against the kernels (dlmcq_host_fq_forward_backward[_async])."""
+    """End-to-end path for HOST tensors (pinned memory) on a caller-owned `dlmcq_host_ctx`: forward + backward with the
+    H2D / D2H copies pipelined against the kernels.  All calls enqueue; `synchronize()` waits.
+
+    forward_backward*  y, dx come back in the tensor's dtype;
+    codes_async        compact lossless result: packed integer codes (y = code * s' + offset) and one keep bit per
+                       element (dx = keep ? dy : 0) - 8.6 instead of 16 bytes per fp32 element over PCIe."""
 
     def __init__(self, device, chunk_elems=1 << 22, dtype=torch.float32):
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.chunk = int(chunk_elems)
         self.code = F32 if dtype == torch.float32 else BF16
-        n = _lib.lib().dlmcq_host_staging_bytes(self.chunk, self.code)
-        self.staging = torch.zeros(n, dtype=torch.uint8, device=self.device)      # ticket counters start at 0
-        self.nbytes = n
-
-    def _call(self, fn, x, dy, y, dx, ds_ptr, scale, offset, lo, hi, form, g):
-        for t in (x, dy, y, dx):
-            if t.is_cuda or not t.is_contiguous():
-                raise DlmcqError("host path takes contiguous CPU tensors")
+        self._ctx = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(fn(_ptr(x), _ptr(dy), _ptr(y), _ptr(dx), ds_ptr, x.numel(), self.code, int(form), int(lo),
-                          int(hi), float(g), float(scale), float(offset), _ptr(self.staging), self.nbytes, self.chunk))
+            _lib.check(_lib.lib().dlmcq_host_ctx_create(C.byref(self._ctx), self.chunk))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            _lib.lib().dlmcq_host_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _host(*tensors):
+        for t in tensors:
+            if t is not None and (t.is_cuda or not t.is_contiguous()):
+                raise DlmcqError("host path takes contiguous CPU tensors")
+
+    def forward_backward_async(self, x, dy, y, dx, dscale_out, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
+        """Enqueue only; `dscale_out` is a 1-element pinned float32 tensor that receives the scale gradient."""
+        self._host(x, dy, y, dx, dscale_out)
+        _lib.check(_lib.lib().dlmcq_host_ctx_fq_forward_backward(
+            self._ctx, _ptr(x), _ptr(dy), _ptr(y), _ptr(dx), C.c_void_p(dscale_out.data_ptr()), x.numel(), self.code,
+            int(form), int(lo), int(hi), float(g), float(scale), float(offset)))
 
     def forward_backward(self, x, dy, y, dx, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
         """x, dy: host inputs; y, dx: host outputs (same shape/dtype).  Returns dscale (python float)."""
-        ds = C.c_float(0.0)
-        self._call(_lib.lib().dlmcq_host_fq_forward_backward, x, dy, y, dx, C.cast(C.byref(ds), C.c_void_p), scale,
-                   offset, lo, hi, form, g)
-        return ds.value
+        ds = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.forward_backward_async(x, dy, y, dx, ds, scale, offset, lo, hi, form, g)
+        self.synchronize()
+        return float(ds)
 
-    def forward_backward_async(self, x, dy, y, dx, dscale_out, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0):
-        """Enqueue only; `dscale_out` is a 1-element pinned float32 tensor that receives the scale
-        gradient.  Call synchronize() before reading any output."""
-        self._call(_lib.lib().dlmcq_host_fq_forward_backward_async, x, dy, y, dx, C.c_void_p(dscale_out.data_ptr()),
-                   scale, offset, lo, hi, form, g)
+    def codes_async(self, x, dy, codes, keep, dscale_out, scale, offset, lo, hi, form=FORM_AFFINE, g=0.0, pack4=False):
+        """codes: uint8/int8 host tensor of numel (or ceil(numel/2) with pack4) bytes; keep: uint8 host tensor of
+        ceil(numel/8) bytes (dy, keep, dscale_out may be None: forward only)."""
+        self._host(x, dy, codes, keep, dscale_out)
+        _lib.check(_lib.lib().dlmcq_host_ctx_fq_codes(
+            self._ctx, _ptr(x), _ptr(dy), _ptr(codes), _ptr(keep),
+            C.c_void_p(dscale_out.data_ptr()) if dscale_out is not None else None, x.numel(), self.code, int(form),
+            int(lo), int(hi), float(g), float(scale), float(offset), int(bool(pack4))))
 
     def synchronize(self):
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().dlmcq_host_synchronize())
+        _lib.check(_lib.lib().dlmcq_host_ctx_synchronize(self._ctx))

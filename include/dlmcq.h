@@ -11,7 +11,7 @@
  *   - plain C: raw DEVICE pointers, sizes, a CUDA stream passed as void* (cudaStream_t).
  *   - no allocation and no host synchronisation on the device-pointer entry points: outputs
  *     and workspaces are provided by the caller and every launch goes to `stream`.  The only
- *     process state is a cached SM count and the stream pool of the host-buffer entry.
+ *     process state is a cached SM count; the host-buffer entries keep theirs in a caller-owned context.
  *   - returns DLMCQ_OK (0) or a negative dlmcq_status; CUDA launch errors are reported
  *     as DLMCQ_ECUDA and the text is available from dlmcq_last_cuda_error().
  *   - arithmetic is IEEE fp32, one rounding per reference op, no FMA contraction, true
@@ -436,26 +436,35 @@ int dlmcq_bnq_backward(const void* x, const void* a_saved, const void* d_a, cons
                        const dlmcq_bnq_desc* desc, const dlmcq_qparams* qp, void* workspace,
                        size_t workspace_bytes, void* stream);
 
-/* ---- host-buffer entry (end-to-end path) ----------------------------------------------
- * Same arithmetic as dlmcq_fq_forward + dlmcq_fq_backward on a per-tensor-scale tensor that
- * lives in (pinned) HOST memory: x, dy in; y, dx and dscale out.  Chunks are pipelined
- * H2D -> kernels -> D2H over internal streams through a caller-provided device staging buffer
- * (dlmcq_host_staging_bytes(); must be ZERO-initialised once by the caller).
- *   _async      returns when the work is enqueued, so successive tensors (the layers of a model)
- *               keep the copy engines busy; outputs (incl. *dscale_host, which should be pinned)
- *               are valid after dlmcq_host_synchronize().
- *   (plain)     = _async + dlmcq_host_synchronize(). */
-size_t dlmcq_host_staging_bytes(int64_t chunk_elems, int dtype);
-int dlmcq_host_fq_forward_backward_async(const void* x_host, const void* dy_host, void* y_host,
-                                         void* dx_host, float* dscale_host, int64_t numel, int dtype,
-                                         int form, int lo, int hi, float g, float scale, float offset,
-                                         void* device_staging, size_t staging_bytes,
-                                         int64_t chunk_elems);
-int dlmcq_host_synchronize(void);
-int dlmcq_host_fq_forward_backward(const void* x_host, const void* dy_host, void* y_host,
-                                   void* dx_host, float* dscale_host, int64_t numel, int dtype,
-                                   int form, int lo, int hi, float g, float scale, float offset,
-                                   void* device_staging, size_t staging_bytes, int64_t chunk_elems);
+/* ---- host-buffer entries (end-to-end path), on a caller-owned context ----------------------
+ * For callers whose tensors live in (pinned) HOST memory: per-tensor-scale fake-quant forward + backward with the
+ * H2D / kernel / D2H stages of successive chunks pipelined over the context's own streams.  A context owns its
+ * streams, events and device staging memory; the library keeps NO process-global state for this path.  One context is
+ * used by one thread at a time (calls on it are serialised); different contexts are independent.  The device current
+ * at dlmcq_host_ctx_create() is the context's device.  chunk_elems: elements per pipeline chunk, a multiple of 8
+ * (4 M is a good value: 4 staging buffers of chunk_elems * 4 bytes per pipeline slot, 4 slots).
+ *
+ * Both calls ENQUEUE and return: host outputs (including *dscale_host, which should be pinned) are valid after
+ * dlmcq_host_ctx_synchronize().  Inputs must stay untouched until then.
+ *   dlmcq_host_ctx_fq_forward_backward   x, dy in; y, dx out in the tensor's dtype - same arithmetic as
+ *                                        dlmcq_fq_forward + dlmcq_fq_backward.
+ *   dlmcq_host_ctx_fq_codes              compact, LOSSLESS result format (the path is PCIe-bound: 8.6 instead of 16
+ *                                        bytes per fp32 element cross the bus): codes_host receives the integer codes,
+ *                                        one byte each (two's complement when lo < 0) or two 4-bit codes per byte with
+ *                                        pack4 (low nibble = even element) - y is code * s' + offset, exactly what
+ *                                        dlmcq_import_codes returns; keep_host receives one bit per element (bit e of
+ *                                        byte i/8, LSB first): dx = keep ? dy : 0 with the dy the caller holds.
+ *                                        dy_host == NULL: forward only (keep_host, dscale_host unused). */
+typedef struct dlmcq_host_ctx dlmcq_host_ctx;
+int dlmcq_host_ctx_create(dlmcq_host_ctx** ctx, int64_t chunk_elems);
+int dlmcq_host_ctx_destroy(dlmcq_host_ctx* ctx);
+int dlmcq_host_ctx_synchronize(dlmcq_host_ctx* ctx);
+int dlmcq_host_ctx_fq_forward_backward(dlmcq_host_ctx* ctx, const void* x_host, const void* dy_host, void* y_host,
+                                       void* dx_host, float* dscale_host, int64_t numel, int dtype, int form, int lo,
+                                       int hi, float g, float scale, float offset);
+int dlmcq_host_ctx_fq_codes(dlmcq_host_ctx* ctx, const void* x_host, const void* dy_host, void* codes_host,
+                            void* keep_host, float* dscale_host, int64_t numel, int dtype, int form, int lo, int hi,
+                            float g, float scale, float offset, int pack4);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,9 @@ def test_workspace_query_needs_no_gpu(libpath):
     assert base >= 256 + 2048 * 80 * 4          # 80 sweep partials per CTA fit
     lay = _lib.Layout(64, 2048, 49, 0)
     assert h.dlmcq_workspace_bytes(ctypes.byref(lay)) >= 256 + 64 * 2048 * 16
-    assert h.dlmcq_host_staging_bytes(1 << 20, 0) > 3 * 4 * (1 << 22)
+    ctx = ctypes.c_void_p()
+    assert h.dlmcq_host_ctx_create(ctypes.byref(ctx), 12345) == -1          # chunk must be a multiple of 8
+    assert h.dlmcq_host_ctx_synchronize(None) == -1 and h.dlmcq_host_ctx_destroy(None) == 0
 
 
 def test_argument_validation_without_gpu(libpath):

@@ -304,6 +304,49 @@ def test_host_pipeline_matches_device_path():
         assert torch.equal(dxk, dxd.cpu()) and abs(float(dsk) - float(dsd)) <= 1e-5 * abs(float(dsd)) + 1e-7
 
 
+def test_host_compact_wire_format_is_lossless():
+    """dlmcq_host_ctx_fq_codes: packed integer codes + one keep bit per element come back over PCIe instead of y and dx
+    (8.6 instead of 16 bytes per fp32 element); both reconstruct the full-precision results bit for bit:
+    y == import_codes(codes) == fq_forward(x), dx == where(keep, dy, 0) == fq_backward(x, dy)."""
+    import numpy as np
+    from dlmc_quant_b200.functional import HostFakeQuant
+    gen = torch.Generator().manual_seed(16)
+    n = (1 << 20) + 1003                                   # ragged: not a multiple of 8, several chunks
+    x = (torch.relu(torch.randn(n, generator=gen)) * 2).pin_memory()
+    dy = torch.randn(n, generator=gen).pin_memory()
+    hq = HostFakeQuant("cuda", chunk_elems=1 << 18)
+    g = R.lsq_g(n, 15)
+    s, o = dev(torch.tensor([0.23])), dev(torch.tensor([0.0]))
+    y_ref = F().fq_forward(dev(x), s, o, 0, 15, 1, g=g).cpu()
+    dx_ref, ds_ref = F().fq_backward(dev(x), dev(dy), s, o, 0, 15, 1, g=g)
+    for pack4 in (True, False):
+        codes = torch.zeros((n + 1) // 2 if pack4 else n, dtype=torch.uint8).pin_memory()
+        keep = torch.zeros((n + 7) // 8, dtype=torch.uint8).pin_memory()
+        ds = torch.zeros(1).pin_memory()
+        hq.codes_async(x, dy, codes, keep, ds, 0.23, 0.0, 0, 15, form=1, g=g, pack4=pack4)
+        hq.synchronize()
+        want = F().export_codes(dev(x), s, o, 0, 15, 1, g=g, pack4=pack4).cpu().reshape(-1)
+        assert torch.equal(codes, want)
+        y = F().import_codes(dev(codes), (n,), s, o, 0, 15, 1, g=g, pack4=pack4).cpu()
+        assert torch.equal(y, y_ref)
+        bits = torch.from_numpy(np.unpackbits(keep.numpy(), bitorder="little")[:n].astype(bool))
+        assert torch.equal(torch.where(bits, dy, torch.zeros(())), dx_ref.cpu())
+        assert abs(float(ds) - float(ds_ref)) <= 1e-5 * abs(float(ds_ref)) + 1e-7
+    # signed 8-bit weights, SYM form, forward only
+    w = (torch.randn(70001, generator=gen) * 0.05).pin_memory()
+    c8 = torch.zeros(70001, dtype=torch.int8).pin_memory()
+    hq.codes_async(w, None, c8, None, None, 0.0011, 0.0, -127, 127, form=3)
+    hq.synchronize()
+    sw = dev(torch.tensor([0.0011]))
+    assert torch.equal(c8, F().export_codes(dev(w), sw, None, -127, 127, 3).cpu().reshape(-1))
+    # two contexts are independent; a context can be closed and another created
+    hq2 = HostFakeQuant("cuda", chunk_elems=1 << 16)
+    y2, dx2 = torch.empty(n).pin_memory(), torch.empty(n).pin_memory()
+    assert abs(hq2.forward_backward(x, dy, y2, dx2, 0.23, 0.0, 0, 15, form=1, g=g) - float(ds_ref)) <= 1e-5 * abs(float(ds_ref)) + 1e-7
+    assert torch.equal(y2, y_ref) and torch.equal(dx2, dx_ref.cpu())
+    hq.close(); hq2.close()
+
+
 # --------------------------------------------------------------------------------------
 # geometry coverage of the observer kernels added in the second half of round 1
 def test_sweep_channel_unstaged_rows_bf16_and_block_geometry():
