@@ -23,6 +23,19 @@ _ALIASES = {
     "dlmc.quantization.scalar.modules": "dlmc_quant_b200.scalar.modules",
     "dlmc.quantization.scalar.RootQ": "dlmc_quant_b200.scalar.RootQ",
     "dlmc.quantization.scalar.FSPTQuant": "dlmc_quant_b200.scalar.FSPTQuant",
+    # submodules the reference imports by full path (e.g. trainer/fsptq_trainer.py:9 `from dlmc.quantization.scalar.
+    # FSPTQuant.base import FSPTQBase`): they must be the SAME module objects, or isinstance() checks see two classes
+    "dlmc.quantization.scalar.modules.base": "dlmc_quant_b200.scalar.modules.base",
+    "dlmc.quantization.scalar.modules.function": "dlmc_quant_b200.scalar.modules.function",
+    "dlmc.quantization.scalar.modules.conv": "dlmc_quant_b200.scalar.modules.conv",
+    "dlmc.quantization.scalar.modules.linear": "dlmc_quant_b200.scalar.modules.linear",
+    "dlmc.quantization.scalar.RootQ.base": "dlmc_quant_b200.scalar.RootQ.base",
+    "dlmc.quantization.scalar.RootQ.function": "dlmc_quant_b200.scalar.RootQ.function",
+    "dlmc.quantization.scalar.RootQ.conv": "dlmc_quant_b200.scalar.RootQ.conv",
+    "dlmc.quantization.scalar.RootQ.linear": "dlmc_quant_b200.scalar.RootQ.linear",
+    "dlmc.quantization.scalar.FSPTQuant.base": "dlmc_quant_b200.scalar.FSPTQuant.base",
+    "dlmc.quantization.scalar.FSPTQuant.conv": "dlmc_quant_b200.scalar.FSPTQuant.conv",
+    "dlmc.quantization.scalar.FSPTQuant.linear": "dlmc_quant_b200.scalar.FSPTQuant.linear",
     "dlmc.utils.quantize": "dlmc_quant_b200.quantize",
     "dlmc.utils.merge_bn": "dlmc_quant_b200.reparam",
 }

@@ -32,7 +32,13 @@ class _StopForward(Exception):
 
 class FSPTQReconstructor:
     def __init__(self, model, fp_model, block_types=(), epochs=0, criterion=l2_loss, minibatch=64, log_every=500,
-                 logger=None):
+                 logger=None, scale_lr=None):
+        """scale_lr: the reference gives parameters whose name ends in "scales" a learning rate of 1e-3
+        (fsptq_trainer.py:143), but its quantizer parameters are called `in_scale` / `wt_scale` - so with the
+        reference's own modules that branch never fires and scales train at the default 1e-5.  None (default)
+        reproduces that behaviour exactly; a number gives names ending in "scale" or "scales" that learning rate
+        (evidently what was meant)."""
+        self.scale_lr = scale_lr
         self.model, self.fp_model = model, fp_model
         self.block_types = tuple(block_types)
         self.epochs, self.criterion, self.minibatch = epochs, criterion, minibatch
@@ -57,6 +63,8 @@ class FSPTQReconstructor:
                 lr = 1e-5
             elif name.endswith("scales"):
                 lr = 1e-3
+            elif self.scale_lr is not None and name.endswith("scale"):
+                lr = self.scale_lr
             elif name.endswith("gamma") or name.endswith("beta"):
                 lr = 0.1
             else:
