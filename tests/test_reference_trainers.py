@@ -59,6 +59,8 @@ def reference_trainers():
         def add_scalar(self, *a, **k): pass
     lg.TensorboardWriter = TensorboardWriter
     sys.modules["logger"] = lg
+    for k in [k for k in sys.modules if k == "trainer" or k.startswith("trainer.")]:
+        del sys.modules[k]                                # e.g. the oracle shim's namespace stubs from earlier tests
     tr = types.ModuleType("trainer")
     tr.__path__ = [os.path.join(REF, "trainer")]          # bypass trainer/__init__.py (imports a missing file)
     sys.modules["trainer"] = tr
@@ -72,11 +74,14 @@ def reference_trainers():
         for k in list(sys.modules):
             if k not in saved_modules and (k == "dlmc" or k.startswith(mine)):
                 del sys.modules[k]
-        for k in ("utils", "logger", "trainer", "base"):
+        for k in ("utils", "logger", "base"):
             if k in saved_modules:
                 sys.modules[k] = saved_modules[k]
             else:
                 sys.modules.pop(k, None)
+        for k, v in saved_modules.items():
+            if k == "trainer" or k.startswith("trainer."):
+                sys.modules[k] = v
 
 
 class _Config(dict):
