@@ -97,6 +97,18 @@ def _workspace(device, nbytes):
     return ws
 
 
+_scratches = {}
+
+
+def _scratch(device, nbytes):
+    """Plain scratch memory (no zero contract), one buffer per (device, stream), grown on demand."""
+    key = (device.index, _raw_stream(device.index))
+    buf = _scratches.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _scratches[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    return buf
+
+
 _ws_bytes = {}
 
 
@@ -312,7 +324,7 @@ def kth_values(x, ranks, abs_input=False, reduce_hist=None, fast=True):
         status = torch.zeros(1, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
             nws = h.dlmcq_obs_kth_fast_workspace_bytes(x.numel())
-            ws = _workspace(x.device, nws)
+            ws = _scratch(x.device, nws)          # NOT the shared zero-contract workspace: this call scribbles on all of it
             _lib.check(h.dlmcq_obs_kth_fast(_ptr(x), x.numel(), _dtype_code(x), flags, ranks[0],
                                             ranks[1] if len(ranks) > 1 else 0, _ptr(values),
                                             C.c_void_p(status.data_ptr()), _ptr(ws), nws, _stream_ptr()))

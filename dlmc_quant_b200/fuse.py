@@ -39,7 +39,7 @@ def _bnq_ws(device, desc):
     n = _ws_cache.get(key)
     if n is None:
         n = _ws_cache[key] = _lib.lib().dlmcq_bnq_workspace_bytes(C.byref(desc))
-    return F._workspace(device, n), n
+    return F._scratch(device, n), n      # no zero contract needed: the bnq kernels use no ticket counters
 
 
 def _rows_channels(x):
