@@ -162,6 +162,12 @@ class WeightQuantGroup:
         per_channel = s.numel() == w.shape[0] and s.numel() > 1 and tuple(s.shape[1:]) == (1,) * (w.dim() - 1)
         return (s.numel() == 1 or per_channel) and F.dense_as_is(w, 0)
 
+    @staticmethod
+    def _offset_in_place(m):
+        o = m.wt_offset
+        return o.dtype is torch.float32 and o.is_contiguous() and o.numel() == m.wt_scale.numel() and \
+            o.device == m.weight.device
+
     def _refresh(self):
         if self._candidates is None:
             self._candidates = [m for m in self.model.modules() if isinstance(m, QBase)]
@@ -177,9 +183,13 @@ class WeightQuantGroup:
                 mods = [m for m in mods if m.weight.device == dev and m.weight.dtype == dt]
         else:
             mods = self._mods
-        # wt_offset._version: an in-place update of the buffer (load_state_dict) must refresh our fp32 copy of it
-        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(), m.wt_offset._version,
-                     m.weight.stride(), m.weight.dtype) for m in mods)
+        # An in-place update of an offset buffer (load_state_dict; DistributedDataParallel re-broadcasts every buffer on
+        # every forward) must refresh the plan only when the plan holds a converted COPY of it; a float32 buffer with
+        # one entry per channel is used in place (the plan's `off` is a view of it), so its _version is irrelevant -
+        # keying on it rebuilt the whole plan on every DDP step
+        key = tuple((id(m), m.weight.data_ptr(), m.wt_scale.data_ptr(), m.wt_offset.data_ptr(),
+                     0 if self._offset_in_place(m) else m.wt_offset._version, m.weight.stride(), m.weight.dtype)
+                    for m in mods)
         if key == self._key:
             return
         self._key, self._mods = key, mods
