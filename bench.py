@@ -502,10 +502,14 @@ def _qat_arm(arm, channels_last, batch, steps, rank, world, device, graphed=Fals
         from dlmc_quant_b200.fuse import fuse_bn_act_quant
         h = fuse_bn_act_quant(model)
         fused_sites = {"blocks": h.blocks, "sequentials": h.sequentials, "batchnorms": h.batchnorms}
-    if world > 1:
-        model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=5e-4)
     crit = nn.CrossEntropyLoss()
+    if world > 1:
+        if graphed:                     # DDP built on a side stream so that its all-reduces can be captured (graph.py)
+            from dlmc_quant_b200.graph import wrap_ddp
+            model = wrap_ddp(model, device_ids=[device.index])
+        else:
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=5e-4)
 
     def step():
         opt.zero_grad()
@@ -514,7 +518,7 @@ def _qat_arm(arm, channels_last, batch, steps, rank, world, device, graphed=Fals
         opt.step()
         return loss
 
-    if graphed:                         # whole step (forward, backward, optimizer) replayed as one CUDA graph
+    if graphed:                         # whole step (forward, backward, gradient all-reduce, optimizer): one CUDA graph
         from dlmc_quant_b200.graph import graph_train_step
         gstep = graph_train_step(model, opt, crit, x, t)
         step = lambda: gstep(x, t)      # noqa: E731  (the per-step input copy into the static buffers is included)
@@ -562,10 +566,13 @@ def run_qat(args, rank, world, device):
            "arms": {"fp32": "un-quantised model", "eager": "reference eager op chain + autograd on this GPU",
                     "ours": "dlmc_quant_b200.quantize_model + group_weight_quantizers",
                     "ours_fused": "ours + fuse_bn_act_quant (BatchNorm+ReLU+next layer's input fake-quant in one "
-                                  "kernel per direction; channels_last only)"}}
+                                  "kernel per direction; channels_last only)",
+                    "*_graphed": "the same step (forward, backward, gradient all-reduce, optimizer) captured once as a "
+                                 "CUDA graph and replayed: the eager DDP step is host-bound"}}
     only = set(args.qat_arms.split(",")) if args.qat_arms else None
     for fmt, cl, arms in (("nchw", False, ("fp32", "eager", "ours")),
-                          ("channels_last", True, ("fp32", "eager", "ours", "ours_fused"))):
+                          ("channels_last", True, ("fp32", "eager", "ours", "ours_fused", "fp32_graphed",
+                                                   "ours_fused_graphed"))):
         if only and fmt not in only and not (only & set(arms)):
             continue
         res[fmt] = {}
@@ -573,7 +580,8 @@ def run_qat(args, rank, world, device):
             if only and arm not in only and fmt not in only:
                 continue
             try:
-                res[fmt][arm] = _qat_arm(arm, cl, args.qat_batch, args.qat_steps, rank, world, device)
+                res[fmt][arm] = _qat_arm(arm.replace("_graphed", ""), cl, args.qat_batch, args.qat_steps, rank, world,
+                                         device, graphed=arm.endswith("_graphed"))
             except Exception as e:                      # an arm that fails must not take the headline metric down
                 res[fmt][arm] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
@@ -709,6 +717,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")      # NCCL work inside CUDA graphs (graphed arms)
         dist.init_process_group("nccl", device_id=device)
     try:
         if args.qat_only:

@@ -8,15 +8,44 @@ backward + optimizer step can be captured ONCE and replayed: the host then issue
     step = graph_train_step(model, optimizer, criterion, sample_input, sample_target)
     loss = step(x, t)            # copies x, t into the static buffers, replays, returns the (static) loss tensor
 
-Requirements (checked): observers initialised (run one forward first), single device, `capturable` optimizer state
-(torch.optim.SGD is; Adam needs capturable=True).  DistributedDataParallel is not captured here - under DDP the step
-is GPU-bound by the gradient all-reduce long before the host matters."""
+Requirements (checked): observers initialised (run one forward first), single device per process, `capturable`
+optimizer state (torch.optim.SGD is; Adam needs capturable=True).
+
+DistributedDataParallel: the DDP step is host-bound too (the GPU idles ~7 ms of a 33 ms ResNet-50 step at 2 GPUs while
+the NCCL kernels take < 1 ms: profiles/r02_ddp_gpu_busy_n2.jsonl), so the step is captured INCLUDING DDP's bucketed
+gradient all-reduces.  PyTorch's rules for that: the DDP wrapper is constructed on a side stream (`wrap_ddp`), at least
+11 eager iterations run before capture (bucket rebuild, the reducer's first-iteration logic - `graph_train_step` warms
+up 12 when it sees a DDP model) and NCCL's async error watchdog is off (`TORCH_NCCL_ASYNC_ERROR_HANDLING=0`, set before
+`init_process_group`).
+
+    model = wrap_ddp(model, device_ids=[local_rank])
+    optimizer = torch.optim.SGD(model.parameters(), ...)
+    step = graph_train_step(model, optimizer, criterion, x, t)"""
+import os
+
 import torch
 
-__all__ = ["graph_train_step"]
+__all__ = ["graph_train_step", "wrap_ddp"]
+
+_DDP_WARMUP = 12
 
 
-def graph_train_step(model, optimizer, criterion, sample_input, sample_target, warmup=3):
+def wrap_ddp(model, **ddp_kwargs):
+    """DistributedDataParallel(model, **ddp_kwargs) constructed on a side stream, as whole-step capture requires."""
+    if os.environ.get("TORCH_NCCL_ASYNC_ERROR_HANDLING", "") not in ("0",):
+        raise RuntimeError("wrap_ddp: set TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group - NCCL work "
+                           "captured in a CUDA graph cannot be watched by the async error handler")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ddp = torch.nn.parallel.DistributedDataParallel(model, **ddp_kwargs)
+    torch.cuda.current_stream().wait_stream(side)
+    return ddp
+
+
+def graph_train_step(model, optimizer, criterion, sample_input, sample_target, warmup=None):
+    if warmup is None:
+        warmup = _DDP_WARMUP if isinstance(model, torch.nn.parallel.DistributedDataParallel) else 3
     from .scalar.modules.base import QBase
     for m in model.modules():
         if isinstance(m, QBase):

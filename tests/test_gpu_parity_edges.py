@@ -135,3 +135,132 @@ def test_two_ranks_reproduce_the_single_gpu_result():
         mp.spawn(_worker, args=(2, port, results), nprocs=2, join=True)
         got = dict(results)
     assert got == {"stats": True, "minmax": True, "rows_sharded": True, "percentile": True, "scale_grad": True}, got
+
+
+# ---------------------------------------------------------------------------------------------------------------
+_GRAPH_CFG = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}},
+              "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 4, "signed": False}},
+              "exclude_layers": [], "override_options": [], "momentum": 0.1}
+
+
+def _small_qat_net(dev):
+    import copy
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.fuse import fuse_bn_act_quant
+    from dlmc_quant_b200.quantize import group_weight_quantizers
+    torch.manual_seed(2333)
+    nn = torch.nn
+    net = nn.Sequential(nn.Conv2d(3, 16, 3, padding=1, bias=False), nn.BatchNorm2d(16), nn.ReLU(),
+                        nn.Conv2d(16, 16, 3, padding=1, bias=False), nn.BatchNorm2d(16), nn.ReLU(),
+                        nn.Conv2d(16, 8, 1), nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(8, 5)).to(dev)
+    quantize_model(net, copy.deepcopy(_GRAPH_CFG), None)
+    net = net.to(memory_format=torch.channels_last).train()
+    gen = torch.Generator().manual_seed(5)
+    xs = torch.rand(6, 8, 3, 12, 12, generator=gen).to(dev).contiguous(memory_format=torch.channels_last)
+    ts = torch.randint(0, 5, (6, 8), generator=gen).to(dev)
+    with torch.no_grad():
+        net(xs[0])                                          # lazy observer initialisation
+    group_weight_quantizers(net)
+    fuse_bn_act_quant(net)
+    return net, xs, ts
+
+
+def _train(net, opt, crit, xs, ts, order, stepper=None):
+    losses = []
+    for i in order:
+        if stepper is not None:
+            losses.append(stepper(xs[i], ts[i]).detach().clone())
+            continue
+        opt.zero_grad(set_to_none=True)
+        loss = crit(net(xs[i]), ts[i])
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach().clone())
+    return torch.stack(losses)
+
+
+def test_whole_step_cuda_graph_equals_the_eager_steps():
+    """graph.py: forward + backward + SGD captured once and replayed (one cudaGraphLaunch per step) walks the same
+    trajectory as the eager step on fresh batches: same losses, same parameters, same BN running statistics - through
+    the fused BN->ReLU->quant ops and the grouped weight quantizer."""
+    import copy
+    from dlmc_quant_b200.graph import graph_train_step
+    dev = torch.device("cuda")
+    net, xs, ts = _small_qat_net(dev)
+    ref = copy.deepcopy(net)
+    crit = torch.nn.CrossEntropyLoss()
+    mk = lambda m: torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=5e-4)  # noqa: E731
+    opt, opt_ref = mk(net), mk(ref)
+    step = graph_train_step(net, opt, crit, xs[0], ts[0], warmup=3)       # 3 eager steps on batch 0, then capture
+    order = [1, 2, 3, 4, 5, 1, 2]
+    got = _train(net, opt, crit, xs, ts, order, stepper=step)
+    want = _train(ref, opt_ref, crit, xs, ts, [0, 0, 0] + order)[3:]
+    assert torch.isfinite(got).all()
+    assert torch.allclose(got, want, rtol=2e-4, atol=1e-5), (got, want)
+    sd, sd_ref = net.state_dict(), ref.state_dict()
+    assert sd.keys() == sd_ref.keys()
+    for k in sd:
+        a, b = sd[k].float(), sd_ref[k].float()
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-4), (k, (a - b).abs().max())
+    # a model whose observers have not run cannot be captured: loud error, not a silent sync inside the capture
+    from dlmc_quant_b200 import quantize_model
+    cold = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Flatten(), torch.nn.LazyLinear(5)).to(dev)
+    quantize_model(cold, copy.deepcopy(_GRAPH_CFG), None)
+    with pytest.raises(RuntimeError, match="run one forward first"):
+        graph_train_step(cold, torch.optim.SGD(cold.parameters(), lr=0.1), crit, xs[0], ts[0])
+
+
+def _ddp_graph_worker(rank, world, port, results):
+    import copy
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dlmc_quant_b200.graph import graph_train_step, wrap_ddp
+        dev = torch.device("cuda", rank)
+        net, xs, ts = _small_qat_net(dev)
+        xs = [x[rank * 4:(rank + 1) * 4].contiguous(memory_format=torch.channels_last) for x in xs]   # this rank's shard
+        ts = [t[rank * 4:(rank + 1) * 4].contiguous() for t in ts]
+        ref = copy.deepcopy(net)
+        crit = torch.nn.CrossEntropyLoss()
+        mk = lambda m: torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)  # noqa: E731
+        ddp, ddp_ref = wrap_ddp(net, device_ids=[rank]), torch.nn.parallel.DistributedDataParallel(ref, device_ids=[rank])
+        opt, opt_ref = mk(ddp), mk(ddp_ref)
+        step = graph_train_step(ddp, opt, crit, xs[0], ts[0])          # 12 eager warm-up steps (DDP), then capture
+        order = [1, 2, 3, 4, 5]
+        got = _train(ddp, opt, crit, xs, ts, order, stepper=step)
+        want = _train(ddp_ref, opt_ref, crit, xs, ts, [0] * 12 + order)[12:]
+        ok = bool(torch.isfinite(got).all() and torch.allclose(got, want, rtol=1e-3, atol=1e-4))
+        worst = 0.0
+        for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
+            worst = max(worst, float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-3)))
+        # every rank holds the same parameters after the replayed all-reduces
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        other = flat.clone()
+        dist.broadcast(other, src=0)
+        same = bool(torch.equal(flat, other))
+        res = torch.tensor([float(ok), float(same), worst], device=dev)
+        dist.all_reduce(res, op=dist.ReduceOp.MAX)
+        okmin = torch.tensor([float(ok), float(same)], device=dev)
+        dist.all_reduce(okmin, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            results.update({"losses": bool(okmin[0]), "ranks_agree": bool(okmin[1]), "worst_rel": float(res[2])})
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (profiles/run_multi.sh runs it on a 2-GPU box)")
+def test_two_ranks_whole_step_graph_under_ddp():
+    """The captured step includes DDP's bucketed gradient all-reduces: replayed on 2 ranks it follows the eager DDP
+    trajectory and leaves identical parameters on both ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        results = mgr.dict()
+        port = 29800 + os.getpid() % 200
+        mp.spawn(_ddp_graph_worker, args=(2, port, results), nprocs=2, join=True)
+        got = dict(results)
+    assert got.get("losses") and got.get("ranks_agree") and got["worst_rel"] < 5e-3, got
