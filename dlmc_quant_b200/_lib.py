@@ -113,6 +113,8 @@ SIGNATURES = {
     "dlmcq_rootq_prepare_many": (_I, [_P, _I, _P]),
     "dlmcq_rootq_wt_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
     "dlmcq_rootq_wt_backward_grouped": (_I, [_P, _P, _I, _L, _I, _P, _P]),
+    "dlmcq_rootq_act_forward_grouped": (_I, [_P, _P, _I, _L, _I, _P]),
+    "dlmcq_rootq_act_backward_grouped": (_I, [_P, _P, _I, _L, _I, _P, _P]),
     "dlmcq_obs_stats": (_I, [_P, _P, _LP, _I, _P, _Z, _P]),
     "dlmcq_obs_minmax_finalize": (_I, [_P, _P, _P, _L, _I, _I, _I, _P]),
     "dlmcq_obs_minmax_finalize_mode": (_I, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
@@ -124,6 +126,7 @@ SIGNATURES = {
     "dlmcq_obs_kth_values": (_I, [_P, _P, _P]),
     "dlmcq_obs_kth_fast_workspace_bytes": (_Z, [_L]),
     "dlmcq_obs_kth_fast": (_I, [_P, _L, _I, _I, _L, _L, _P, _P, _P, _Z, _P]),
+    "dlmcq_obs_kth_auto": (_I, [_P, _L, _I, _I, _L, _L, _P, _P, _P, _P, _Z, _P]),
     "dlmcq_obs_sweep_tensor_sse": (_I, [_P, _L, _I, _P, _I, _I, _P, _P, _Z, _P]),
     "dlmcq_obs_sweep_tensor_finalize": (_I, [_P, _P, _D, _I, _I, _P, _P, _P, _P]),
     "dlmcq_obs_sweep_channel": (_I, [_P, _L, _L, _I, _I, _I, _P, _P, _P]),

@@ -36,6 +36,14 @@ int64_t cmaj_max_inner() {
   return v;
 }
 
+bool slab_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DLMCQ_NO_SLAB");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("DLMCQ_NO_PDL");

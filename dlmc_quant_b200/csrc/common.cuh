@@ -246,6 +246,56 @@ inline bool cmaj_vec_ok(int64_t inner, const void* a, const void* b, const void*
   return inner % Vec<T>::N == 0 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d);
 }
 
+// Slab geometry: per-channel ACTIVATIONS [B, C, inner] whose short rows are NOT whole 128-bit vectors (7x7, 5x5, 3x3
+// planes, inner == 1).  G = VEC / gcd(inner, VEC) adjacent channels form a contiguous, 16-byte-aligned run of
+// W = G * inner / VEC vectors per batch index.  Thread (r, v) of a CTA owns vector v of one run for the batch indices
+// r, r + R, ...: the channel of each of its VEC elements is the same for the whole kernel, so the per-channel constants
+// are resolved once into registers, every access is a coalesced 128-bit one, and no lane idles on a row remainder
+// (the scalar channel-major kernels spend 22 - 41 instructions per element on 7x7 planes and are issue-bound).
+struct SlabGeom {
+  int64_t outer, channels, inner;
+  int64_t plane_vecs;   // C * inner / VEC: vectors between consecutive batch indices
+  int32_t G, W, R;      // channels per group, vectors per group row, batch rows per CTA pass (R * W <= kThreads)
+  int32_t bc, chunks;   // batch indices per CTA, CTAs per channel group
+  int32_t groups;       // C / G
+};
+constexpr int kSlabUnroll = 4;
+bool slab_enabled();    // DLMCQ_NO_SLAB=1 falls back to the scalar channel-major kernels (A/B aid)
+template <typename T>
+inline bool slab_ok(int64_t outer, int64_t channels, int64_t inner, const void* a, const void* b, const void* c,
+                    const void* d) {
+  constexpr int VEC = Vec<T>::N;
+  if (!slab_enabled() || !cmaj_ok(outer, channels, inner) || inner % VEC == 0) return false;
+  int g = 1;
+  while ((inner * g) % VEC != 0) g <<= 1;                  // VEC / gcd(inner, VEC): a power of two <= VEC
+  return channels % g == 0 && aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d) &&
+         channels / g * outer < (int64_t(1) << 31);      // grid = groups * chunks, chunks <= outer
+}
+template <typename T>
+inline SlabGeom make_slab(int64_t outer, int64_t channels, int64_t inner) {
+  constexpr int VEC = Vec<T>::N;
+  SlabGeom s;
+  s.outer = outer; s.channels = channels; s.inner = inner;
+  int g = 1;
+  while ((inner * g) % VEC != 0) g <<= 1;
+  s.G = g;
+  s.W = static_cast<int32_t>(inner * g / VEC);
+  s.R = kThreads / s.W;
+  s.groups = static_cast<int32_t>(channels / g);
+  s.plane_vecs = channels * inner / VEC;
+  // CTAs live long (the per-thread constants and the CTA fold are paid once per CTA): as few batch chunks as still
+  // give ~8 CTAs per SM, each a whole number of (R * unroll)-row passes
+  const int64_t pass_rows = static_cast<int64_t>(s.R) * kSlabUnroll * 2;
+  int64_t chunks = (148 * 8 + s.groups - 1) / s.groups;
+  if (chunks < 1) chunks = 1;
+  int64_t bc = (outer + chunks - 1) / chunks;
+  bc = (bc + pass_rows - 1) / pass_rows * pass_rows;
+  if (bc > outer) bc = outer;
+  s.bc = static_cast<int32_t>(bc);
+  s.chunks = static_cast<int32_t>((outer + bc - 1) / bc);
+  return s;
+}
+
 // Programmatic dependent launch: consecutive kernels of one stream (the per-layer quantizer launches of a
 // training step) hide their launch latency behind the predecessor's tail.  Every kernel launched this way
 // executes pdl_wait() before its first global-memory access - it then sees all of the predecessor's

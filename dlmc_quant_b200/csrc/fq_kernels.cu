@@ -353,6 +353,55 @@ fq_cmaj_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// slab kernel (forward): per-channel activations whose short rows are not whole 128-bit vectors (SlabGeom,
+// common.cuh).  The backward of these layouts stays on fq_cmaj_kernel: its scalar accesses already reach 0.86 of the
+// copy rate on 7x7 planes (the backward moves 12 B per element for the same index arithmetic), and a slab backward
+// measured slower (per-slot accumulators + a CTA fold per channel).
+// ---------------------------------------------------------------------------------------
+template <int FORM, typename T>
+__global__ void __launch_bounds__(kThreads, 3)
+fq_slab_kernel(const T* __restrict__ x, T* __restrict__ out, T* __restrict__ codes, SlabGeom gm,
+               const float* __restrict__ scale, const float* __restrict__ offset, float g, float lo, float hi) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  constexpr int U = kSlabUnroll;
+  const int tid = threadIdx.x;
+  const int r = tid / gm.W, v = tid - r * gm.W;
+  if (r >= gm.R) return;
+  // adjacent CTAs own adjacent channel groups of the same batch chunk: adjacent memory
+  const int64_t j = blockIdx.x / gm.groups, grp = blockIdx.x - j * gm.groups;
+  const int64_t b0 = j * gm.bc;
+  const int64_t b1 = (gm.outer - b0) < gm.bc ? gm.outer : b0 + gm.bc;
+  const int64_t col = grp * gm.W + v;                       // vector index inside one batch plane
+  const raw* xv = reinterpret_cast<const raw*>(x) + col;
+  raw* ov = out ? reinterpret_cast<raw*>(out) + col : nullptr;
+  raw* cv = codes ? reinterpret_cast<raw*>(codes) + col : nullptr;
+  ChanParams p[V::N];
+#pragma unroll
+  for (int k = 0; k < V::N; ++k)
+    p[k] = make_params<FORM>(scale, offset, grp * gm.G + (V::N * v + k) / static_cast<int>(gm.inner), g, lo, hi);
+  for (int64_t b = b0 + r; b < b1; b += static_cast<int64_t>(gm.R) * U) {
+    raw rx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t bb = b + static_cast<int64_t>(u) * gm.R;
+      if (bb < b1) rx[u] = ld_stream(xv + bb * gm.plane_vecs);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t bb = b + static_cast<int64_t>(u) * gm.R;
+      if (bb >= b1) break;
+      float f[V::N], o1[V::N], o2[V::N];
+      V::unpack(rx[u], f);
+#pragma unroll
+      for (int k = 0; k < V::N; ++k) fq_elem<FORM>(f[k], p[k], lo, hi, o2[k], o1[k]);
+      if (ov) st_stream(ov + bb * gm.plane_vecs, V::pack(o1));
+      if (cv) st_stream(cv + bb * gm.plane_vecs, V::pack(o2));
+    }
+  }
+}
+
 // one CTA per channel: fixed-order sum (in double) of that channel's `per` partials, WIDTH floats each, at
 // part[WIDTH * ((k / inner_n) * stride_o + ch * inner_n + k % inner_n)]  (rows: k = (b, seg), inner_n = segs,
 // stride_o = C * segs; channel-major: inner_n = chunks, stride_o = 0)
@@ -581,6 +630,10 @@ static int launch_fwd(const void* x, void* y, void* codes, const dlmcq_layout* l
     fq_tiled_chan_kernel<FORM, T, false><<<static_cast<unsigned>(tiles), kThreads, 0, st>>>(
         static_cast<const T*>(x), nullptr, static_cast<T*>(y), static_cast<T*>(codes), tg, qp->scale, qp->offset,
         qp->g, lo, hi, nullptr);
+  } else if (slab_ok<T>(l->outer, l->channels, l->inner, x, y, codes, nullptr)) {
+    const SlabGeom sg = make_slab<T>(l->outer, l->channels, l->inner);
+    fq_slab_kernel<FORM, T><<<static_cast<unsigned>(sg.groups) * sg.chunks, kThreads, 0, st>>>(
+        static_cast<const T*>(x), static_cast<T*>(y), static_cast<T*>(codes), sg, qp->scale, qp->offset, qp->g, lo, hi);
   } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
     const bool vec = cmaj_vec_ok<T>(l->inner, x, y, codes, nullptr);
     const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);

@@ -238,6 +238,62 @@ stats_cmaj_kernel(const T* __restrict__ x, CmajGeom gm, Stat4* __restrict__ part
   if (lane == 0) part[c * gm.chunks + jc] = s;
 }
 
+// slab statistics (SlabGeom, common.cuh): short rows that are not whole 128-bit vectors, read as vectors anyway;
+// one Stat4 per element slot of the thread's vector, folded per channel in a fixed order; partial [channel][chunk].
+template <typename T, bool ABS>
+__global__ void __launch_bounds__(kThreads, 2)
+stats_slab_kernel(const T* __restrict__ x, SlabGeom gm, Stat4* __restrict__ part) {
+  using V = Vec<T>;
+  using raw = typename V::raw;
+  constexpr int U = 2 * kSlabUnroll;
+  __shared__ Stat4 sh[V::N * kThreads];
+  const int tid = threadIdx.x;
+  const int r = tid / gm.W, v = tid - r * gm.W;
+  const bool active = r < gm.R;
+  const int64_t j = blockIdx.x / gm.groups, grp = blockIdx.x - j * gm.groups;
+  const int64_t b0 = j * gm.bc;
+  const int64_t b1 = (gm.outer - b0) < gm.bc ? gm.outer : b0 + gm.bc;
+  const raw* xv = reinterpret_cast<const raw*>(x) + grp * gm.W + v;
+  Stat4 s[V::N];
+#pragma unroll
+  for (int k = 0; k < V::N; ++k) stat_init(s[k]);
+  if (active) {
+    for (int64_t b = b0 + r; b < b1; b += static_cast<int64_t>(gm.R) * U) {
+      raw rx[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t bb = b + static_cast<int64_t>(u) * gm.R;
+        if (bb < b1) rx[u] = ld_stream(xv + bb * gm.plane_vecs);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (b + static_cast<int64_t>(u) * gm.R >= b1) break;
+        float f[V::N];
+        V::unpack(rx[u], f);
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) stat_add<ABS>(s[k], f[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V::N; ++k) sh[k * kThreads + tid] = s[k];
+  __syncthreads();
+  // channel q of the group owns the flat elements [q * inner, (q + 1) * inner) of every row: warp w folds channels
+  // w, w + 8, ... in a fixed order (row-major over its entries, then the shuffle tree)
+  const int warp = tid >> 5, lane = tid & 31;
+  const int inner = static_cast<int>(gm.inner);
+  for (int q = warp; q < gm.G; q += kThreads / 32) {
+    Stat4 t;
+    stat_init(t);
+    for (int i = lane; i < gm.R * inner; i += 32) {
+      const int rr = i / inner, e = q * inner + (i - rr * inner);
+      stat_merge(t, sh[(e % V::N) * kThreads + rr * gm.W + e / V::N]);
+    }
+    t = stat_warp(t);
+    if (lane == 0) part[(grp * gm.G + q) * gm.chunks + j] = t;
+  }
+}
+
 // one CTA per channel: merge that channel's `per` partials at part[(k / inner_n) * stride_o + ch * inner_n +
 // (k % inner_n)] (rows: k = (b, seg), stride_o = C * segs, inner_n = segs; channel-major: stride_o = 0).
 __global__ void __launch_bounds__(128)
@@ -1039,6 +1095,12 @@ static int stats_launch(const T* x, float* stats, const dlmcq_layout* l, void* w
   if (l->channels == 1) {
     const int64_t tiles = (n / Vec<T>::N + kThreads * 4 - 1) / (kThreads * 4);
     stats_flat_kernel<T, ABS><<<stream_grid(tiles, 8), kThreads, 0, st>>>(x, n, stats, ws);
+  } else if (slab_ok<T>(l->outer, l->channels, l->inner, x, nullptr, nullptr, nullptr)) {
+    const SlabGeom sg = make_slab<T>(l->outer, l->channels, l->inner);
+    Stat4* part = reinterpret_cast<Stat4*>(ws_partials(ws));
+    stats_slab_kernel<T, ABS><<<static_cast<unsigned>(sg.groups) * sg.chunks, kThreads, 0, st>>>(x, sg, part);
+    DLMCQ_LAUNCH_CHECK();
+    stats_finalize_kernel<<<static_cast<unsigned>(sg.channels), 128, 0, st>>>(part, sg.chunks, sg.chunks, 0, stats);
   } else if (cmaj_ok(l->outer, l->channels, l->inner)) {
     const bool vec = cmaj_vec_ok<T>(l->inner, x, nullptr, nullptr, nullptr);
     const CmajGeom cg = make_cmaj(l->outer, l->channels, l->inner, vec ? Vec<T>::N : 1);

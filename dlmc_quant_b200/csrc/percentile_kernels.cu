@@ -15,6 +15,7 @@
 // Roofline: HBM (three streaming reads); the shared-memory histogram is the cost: real activations put half of
 // their elements into one bin (post-ReLU zeros, counted in registers) and the rest into a few dozen bins.
 #include "common.cuh"
+#include "fq_math.cuh"
 
 namespace dlmcq {
 
@@ -313,50 +314,60 @@ struct KthRank {
   float flo, fhi;            // their float images
   unsigned int below, el, eh;
 };
+// Candidates (keys strictly inside the bracket: a fraction of a percent of the tensor) are appended to a per-CTA
+// shared-memory list with a shared-memory atomic - no warp-wide step, so a lane that finds one does not drag its warp
+// through a scan and a global atomic's round trip (with a 0.3 % bracket a third of all 128-element warp visits hold
+// at least one) - and the list is flushed once, coalesced, when the CTA is done.  Order is irrelevant: the resolve step
+// histograms the keys.
+constexpr unsigned int kCandSmem = 3072;            // keys per rank per CTA before appends go to global memory directly
+// Appending one candidate - the rare case (a fraction of a percent of the elements), kept out of line so that the
+// streaming loop stays small (it was missing the instruction cache) and takes its operand in a register.
+template <bool ABS>
+__device__ __noinline__ void kth_append(float v, unsigned int lo, unsigned int hi, unsigned int* s_cnt,
+                                        unsigned int* s_buf, unsigned int* __restrict__ n_cand,
+                                        unsigned int* __restrict__ cand, unsigned int cap,
+                                        unsigned int* __restrict__ overflow) {
+  const unsigned int key = radix_key(v, ABS);
+  if (key > lo && key < hi) {
+    const unsigned int pos = atomicAdd(s_cnt, 1u);
+    if (pos < kCandSmem) {
+      s_buf[pos] = key;
+    } else {
+      const unsigned int gp = atomicAdd(n_cand, 1u);
+      if (gp < cap) cand[gp] = key; else *overflow = 1u;
+    }
+  }
+}
+// One vector against one bracket.  The common cases are decided from the vector's minimum and maximum: everything
+// above the bracket (nothing to count) or everything below it (one add).  fminf ignores a NaN (a NaN sorts last:
+// "above" is right for it); the maximum propagates it, so a vector holding one is never taken for "all below".
+// Otherwise four compares per element give below / equal-lo / equal-hi (mass points such as post-ReLU zeros sit on
+// a bracket end and are only counted), and only a vector with something strictly inside calls kth_append.
 template <int N, bool ABS>
-__device__ __forceinline__ void kth_visit_vec(const float (&f)[N], bool ok, KthRank& r, unsigned int* __restrict__ n_cand,
-                                              unsigned int* __restrict__ cand, unsigned int cap,
-                                              unsigned int* __restrict__ overflow, int lane) {
-  unsigned int nb = 0, ne = 0, nh = 0, na = 0;
+__device__ __forceinline__ void kth_visit_vec(const float (&f)[N], float vmin, float vmax, KthRank& r,
+                                              unsigned int* s_cnt, unsigned int* s_buf,
+                                              unsigned int* __restrict__ n_cand, unsigned int* __restrict__ cand,
+                                              unsigned int cap, unsigned int* __restrict__ overflow) {
+  if (vmin > r.fhi) return;
+  if (vmax < r.flo) { r.below += N; return; }
+  unsigned int nb = 0, nle = 0, nlh = 0, nleh = 0;
 #pragma unroll
   for (int e = 0; e < N; ++e) {
     const float v = ABS ? fabsf(f[e]) : f[e];
     nb += v < r.flo ? 1u : 0u;
-    ne += v == r.flo ? 1u : 0u;
-    nh += v == r.fhi ? 1u : 0u;
-    na += v > r.fhi ? 1u : 0u;
+    nle += v <= r.flo ? 1u : 0u;
+    nlh += v < r.fhi ? 1u : 0u;
+    nleh += v <= r.fhi ? 1u : 0u;
   }
-  if (r.hi == r.lo) nh = 0;                       // a degenerate bracket: equality is counted once
-  if (ok) { r.below += nb; r.el += ne; r.eh += nh; }
-  const bool maybe_inside = ok && (nb + ne + nh + na != N);      // something strictly inside, or a NaN
-  if (__any_sync(0xffffffffu, maybe_inside)) {
-    unsigned int keys[N], cnt = 0;
-    bool in[N];
+  r.below += nb;
+  r.el += nle - nb;
+  if (r.hi != r.lo) r.eh += nleh - nlh;          // a degenerate bracket: equality is counted once
+  if (nlh > nle || r.fhi != r.fhi) {             // something strictly inside (or a NaN bracket end: decide by key)
 #pragma unroll
     for (int e = 0; e < N; ++e) {
-      keys[e] = radix_key(f[e], ABS);
-      in[e] = ok && keys[e] > r.lo && keys[e] < r.hi;
-      cnt += in[e] ? 1u : 0u;
-    }
-    unsigned int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total) {
-      unsigned int base = 0;
-      if (lane == 0) base = atomicAdd(n_cand, total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      unsigned int pos = base + incl - cnt;
-#pragma unroll
-      for (int e = 0; e < N; ++e) {
-        if (in[e]) {
-          if (pos < cap) cand[pos] = keys[e]; else *overflow = 1u;
-          ++pos;
-        }
-      }
+      const float v = ABS ? fabsf(f[e]) : f[e];
+      if (!(v <= r.flo) && !(v >= r.fhi))          // NaN ends / NaN values pass: kth_append decides by key
+        kth_append<ABS>(f[e], r.lo, r.hi, s_cnt, s_buf, n_cand, cand, cap, overflow);
     }
   }
 }
@@ -368,12 +379,25 @@ kth_collect_kernel(const T* __restrict__ x, int64_t n, KthFastState* __restrict_
   using V = Vec<T>;
   using raw = typename V::raw;
   const int lane = threadIdx.x & 31;
+  __shared__ unsigned int s_cnt[2], s_base[2];
+  __shared__ unsigned int s_buf[TWO ? 2 : 1][kCandSmem];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
   KthRank r0{st->lo_key[0], st->hi_key[0], radix_unkey(st->lo_key[0]), radix_unkey(st->hi_key[0]), 0u, 0u, 0u};
   KthRank r1{0u, 0u, 0.f, 0.f, 0u, 0u, 0u};
   if (TWO) r1 = KthRank{st->lo_key[1], st->hi_key[1], radix_unkey(st->lo_key[1]), radix_unkey(st->hi_key[1]), 0u, 0u, 0u};
   auto visit = [&](const float (&f)[V::N], bool ok) {
-    kth_visit_vec<V::N, ABS>(f, ok, r0, &st->n_cand[0], cand, cap, &st->overflow, lane);
-    if (TWO) kth_visit_vec<V::N, ABS>(f, ok, r1, &st->n_cand[1], cand + cap, cap, &st->overflow, lane);
+    if (!ok) return;
+    float vmin = ABS ? fabsf(f[0]) : f[0], vmax = vmin;
+#pragma unroll
+    for (int e = 1; e < V::N; ++e) {
+      const float v = ABS ? fabsf(f[e]) : f[e];
+      vmin = fminf(vmin, v);
+      vmax = max_nan(vmax, v);
+    }
+    kth_visit_vec<V::N, ABS>(f, vmin, vmax, r0, &s_cnt[0], s_buf[0], &st->n_cand[0], cand, cap, &st->overflow);
+    if (TWO) kth_visit_vec<V::N, ABS>(f, vmin, vmax, r1, &s_cnt[1], s_buf[TWO ? 1 : 0], &st->n_cand[1], cand + cap, cap,
+                                      &st->overflow);
   };
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -383,6 +407,8 @@ kth_collect_kernel(const T* __restrict__ x, int64_t n, KthFastState* __restrict_
   constexpr int U = 4;
   const int64_t full = nvec / (U * stride) * (U * stride);       // whole warps take part in every shuffle
   for (; i < full; i += U * stride) {
+    __syncwarp();            // lanes that took the rare paths rejoin here: without it the warp stays split into
+                             // sub-warps that run the rest of the loop separately (measured: 8 active lanes on average)
     raw r[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) r[k] = ld_stream(xv + i + k * stride);
@@ -391,10 +417,12 @@ kth_collect_kernel(const T* __restrict__ x, int64_t n, KthFastState* __restrict_
       float f[V::N];
       V::unpack(r[k], f);
       visit(f, true);
+      __syncwarp();
     }
   }
   const int64_t tail_iters = (nvec - full + stride - 1) / stride;
   for (int64_t t = 0; t < tail_iters; ++t, i += stride) {
+    __syncwarp();
     const bool ok = i < nvec;
     float f[V::N];
 #pragma unroll
@@ -417,6 +445,21 @@ kth_collect_kernel(const T* __restrict__ x, int64_t n, KthFastState* __restrict_
     // count only slot 0: temporarily classify the padded vector, then undo nothing (NaN pads add to no counter)
     visit(f, ok);
   }
+  // flush the CTA's candidate lists: one global atomic per rank, coalesced copies
+  __syncthreads();
+  if (threadIdx.x < (TWO ? 2 : 1)) {
+    const unsigned int c = s_cnt[threadIdx.x] < kCandSmem ? s_cnt[threadIdx.x] : kCandSmem;
+    s_cnt[threadIdx.x] = c;
+    s_base[threadIdx.x] = c ? atomicAdd(&st->n_cand[threadIdx.x], c) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < (TWO ? 2 : 1); ++q) {
+    const unsigned int c = s_cnt[q], base = s_base[q];
+    for (unsigned int t = threadIdx.x; t < c; t += blockDim.x) {
+      if (base + t < cap) cand[static_cast<size_t>(q) * cap + base + t] = s_buf[q][t]; else st->overflow = 1u;
+    }
+  }
   unsigned long long c[6] = {r0.below, r1.below, r0.el, r1.el, r0.eh, r1.eh};
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -433,59 +476,85 @@ kth_collect_kernel(const T* __restrict__ x, int64_t n, KthFastState* __restrict_
   }
 }
 
-// Resolve, cooperatively: every CTA histograms its slice of the candidate keys (shared memory, then the non-empty
-// bins into a global histogram), a grid barrier, and every CTA finds the same digit from the same global histogram -
-// three digits per rank, six barriers at most, whatever the candidate count (a single CTA needed ~100 us per pass for
-// the ~0.3 % of a 2^28-element tensor a tail bracket collects).
+// Resolve, cooperatively: every CTA histograms its slice of the keys (shared memory, then the non-empty bins into a
+// global histogram), a grid barrier, and every CTA finds the same digit from the same global histogram - three digits
+// per rank, six barriers at most, whatever the key count (a single CTA needed ~100 us per pass for the ~0.3 % of a
+// 2^28-element tensor a tail bracket collects).  The keys are the collected candidates when the bracket held; when it
+// missed (adversarially ordered data, a candidate overflow) the SAME three-digit select runs over the whole tensor
+// inside this launch - the values are exact either way and no second launch sequence or host read is needed; the
+// status word only reports which of the two happened.
+template <typename KeyAt>
+__device__ unsigned int grid_radix_select(KeyAt key_at, unsigned long long count, unsigned long long r,
+                                          unsigned int* __restrict__ gh3 /* [3][2048], zeroed */,
+                                          unsigned int* hist, unsigned long long* s_rank, unsigned int* counter,
+                                          unsigned int& barrier_no) {
+  unsigned int prefix = 0;
+  if (threadIdx.x == 0) *s_rank = r;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = radix_shift(pass);
+    const unsigned int mask = radix_mask(pass);
+    const int up = pass == 0 ? 32 : radix_shift(pass - 1);
+    unsigned int* gh = gh3 + static_cast<size_t>(pass) * kRadixBins;
+    for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
+    unsigned int zeros = 0;                                // the one value real data repeats: counted in a register
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+      const unsigned int kk = key_at(i);
+      if (pass == 0 || (kk >> up) == prefix) {
+        if (kk == kZeroKey) ++zeros;
+        else atomicAdd(hist + ((kk >> shift) & mask), 1u);
+      }
+    }
+    if (zeros) atomicAdd(hist + ((kZeroKey >> shift) & mask), zeros);
+    __syncthreads();
+    for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x)
+      if (hist[b]) atomicAdd(gh + b, hist[b]);
+    barrier_no += 1;
+    grid_barrier(counter, barrier_no * gridDim.x);
+    for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[b] = __ldcg(gh + b);
+    __syncthreads();
+    prefix = cta_scan_select(hist, s_rank, prefix, pass);
+  }
+  return prefix;
+}
+
+template <typename T, bool ABS>
 __global__ void __launch_bounds__(kKthCtaThreads, 1)
 kth_resolve_kernel(const KthFastState* __restrict__ st, const unsigned int* __restrict__ cand, unsigned int cap,
                    unsigned int* __restrict__ ghist /* [2 ranks][3 passes][2048], zeroed */,
-                   unsigned int* __restrict__ counter /* zeroed */, float* __restrict__ values,
-                   int32_t* __restrict__ status) {
+                   unsigned int* __restrict__ counter /* zeroed */, const T* __restrict__ x, int64_t n,
+                   float* __restrict__ values, int32_t* __restrict__ status) {
   __shared__ unsigned int hist[kRadixBins];
   __shared__ unsigned long long s_rank;
-  bool ok = st->overflow == 0u;
+  const bool no_overflow = st->overflow == 0u;
+  bool all_held = true;
   const unsigned int nr = st->n_ranks;
   unsigned int barrier_no = 0;
-  for (unsigned int j = 0; j < nr; ++j) {
+  for (unsigned int j = 0; j < nr; ++j) {                  // every branch below is uniform across the grid
     const unsigned long long k = st->rank[j], below = st->below[j], el = st->eq_lo[j], eh = st->eq_hi[j];
     const unsigned int nc = st->n_cand[j];
-    if (!ok || nc > cap || k <= below || k > below + el + nc + eh) { ok = false; continue; }   // the bracket missed
-    const unsigned long long r = k - below;
+    unsigned int* gh3 = ghist + static_cast<size_t>(j) * 3 * kRadixBins;
     unsigned int key;
-    if (r <= el) {
-      key = st->lo_key[j];
-    } else if (r > el + nc) {
-      key = st->hi_key[j];
-    } else {                                   // uniform across the grid: every CTA takes the same branch
-      const unsigned int* keys = cand + static_cast<size_t>(j) * cap;
-      unsigned int prefix = 0;
-      if (threadIdx.x == 0) s_rank = r - el;
-      for (int pass = 0; pass < 3; ++pass) {
-        const int shift = radix_shift(pass);
-        const unsigned int mask = radix_mask(pass);
-        const int up = pass == 0 ? 32 : radix_shift(pass - 1);
-        unsigned int* gh = ghist + (static_cast<size_t>(j) * 3 + pass) * kRadixBins;
-        for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[b] = 0u;
-        __syncthreads();
-        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
-          const unsigned int kk = __ldcg(keys + i);
-          if (pass == 0 || (kk >> up) == prefix) atomicAdd(hist + ((kk >> shift) & mask), 1u);
-        }
-        __syncthreads();
-        for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x)
-          if (hist[b]) atomicAdd(gh + b, hist[b]);
-        barrier_no += 1;
-        grid_barrier(counter, barrier_no * gridDim.x);
-        for (int b = threadIdx.x; b < kRadixBins; b += blockDim.x) hist[b] = __ldcg(gh + b);
-        __syncthreads();
-        prefix = cta_scan_select(hist, &s_rank, prefix, pass);
+    if (!no_overflow || nc > cap || k <= below || k > below + el + nc + eh) {   // the bracket missed
+      all_held = false;
+      key = grid_radix_select([&](unsigned long long i) { return radix_key(to_f32<T>(x[i]), ABS); },
+                              static_cast<unsigned long long>(n), k, gh3, hist, &s_rank, counter, barrier_no);
+    } else {
+      const unsigned long long r = k - below;
+      if (r <= el) {
+        key = st->lo_key[j];
+      } else if (r > el + nc) {
+        key = st->hi_key[j];
+      } else {
+        const unsigned int* keys = cand + static_cast<size_t>(j) * cap;
+        key = grid_radix_select([&](unsigned long long i) { return __ldcg(keys + i); }, nc, r - el, gh3, hist, &s_rank,
+                                counter, barrier_no);
       }
-      key = prefix;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) values[j] = radix_unkey(key);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = ok ? 1 : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = all_held ? 1 : 0;
 }
 
 }  // namespace dlmcq
@@ -611,9 +680,33 @@ extern "C" int dlmcq_obs_kth_fast(const void* x, int64_t numel, int dtype, int f
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kth_resolve_kernel, static_cast<const KthFastState*>(st),
-                         static_cast<const unsigned int*>(cand), cap, ghist, counter, values, status);
+#define DLMCQ_KTH_RESOLVE(T, ABS)                                                                              \
+  cudaLaunchKernelEx(&cfg, kth_resolve_kernel<T, ABS>, static_cast<const KthFastState*>(st),                   \
+                     static_cast<const unsigned int*>(cand), cap, ghist, counter, static_cast<const T*>(x), numel, \
+                     values, status)
+  if (dtype == DLMCQ_F32) e = abs_input ? DLMCQ_KTH_RESOLVE(float, true) : DLMCQ_KTH_RESOLVE(float, false);
+  else e = abs_input ? DLMCQ_KTH_RESOLVE(__nv_bfloat16, true) : DLMCQ_KTH_RESOLVE(__nv_bfloat16, false);
+#undef DLMCQ_KTH_RESOLVE
   if (e != cudaSuccess) return set_cuda_error(e);
   return DLMCQ_OK;
 }
 
+// One call for the whole observer: the one-read path (tensors of >= 65536 elements; exact whether or not its bracket
+// held) or, for small tensors, the three-pass select.  No host read anywhere.
+extern "C" int dlmcq_obs_kth_auto(const void* x, int64_t numel, int dtype, int flags, int64_t rank0, int64_t rank1,
+                                  float* values, int32_t* status, void* state, void* scratch, size_t scratch_bytes,
+                                  void* stream) {
+  if (!x || !values || !status || !state) return DLMCQ_EINVAL;
+  int rc = DLMCQ_EUNSUPPORTED;
+  if (scratch && numel >= 4 * kKthSample)
+    rc = dlmcq_obs_kth_fast(x, numel, dtype, flags, rank0, rank1, values, status, scratch, scratch_bytes, stream);
+  if (rc != DLMCQ_EUNSUPPORTED) return rc;
+  cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_cuda_error(e);
+  if ((rc = dlmcq_obs_kth_begin(state, rank0, rank1, stream)) != DLMCQ_OK) return rc;
+  for (int pass = 0; pass < 3; ++pass) {
+    if ((rc = dlmcq_obs_kth_hist(x, numel, dtype, flags, pass, state, stream)) != DLMCQ_OK) return rc;
+    if ((rc = dlmcq_obs_kth_select(pass, state, stream)) != DLMCQ_OK) return rc;
+  }
+  return dlmcq_obs_kth_values(state, values, stream);
+}

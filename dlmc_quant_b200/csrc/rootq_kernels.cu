@@ -419,12 +419,13 @@ __device__ __forceinline__ int rq_find(const int64_t* __restrict__ prefix, int n
   return lo;
 }
 
-template <typename T, bool BWD>
+template <typename T, bool WEIGHT, bool BWD>
 __global__ void __launch_bounds__(kRowWarps * 32)
-rootq_wt_grouped_kernel(const dlmcq_rootq_item* __restrict__ items, const int64_t* __restrict__ prefix, int n_items,
-                        int64_t total_units, float* __restrict__ partials) {
+rootq_grouped_kernel(const dlmcq_rootq_item* __restrict__ items, const int64_t* __restrict__ prefix, int n_items,
+                     int64_t total_units, float* __restrict__ partials) {
   using V = Vec<T>;
   using raw = typename V::raw;
+  constexpr int U = WEIGHT ? 2 : 4;                        // 128-bit loads per tensor in flight per lane
   const int lane = threadIdx.x & 31;
   const int64_t unit = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (unit >= total_units) return;
@@ -432,7 +433,11 @@ rootq_wt_grouped_kernel(const dlmcq_rootq_item* __restrict__ items, const int64_
   const dlmcq_rootq_item it = items[k];
   const int64_t beg = (unit - __ldg(prefix + k)) * DLMCQ_ROOTQ_UNIT;
   const int64_t len = (it.numel - beg) < DLMCQ_ROOTQ_UNIT ? (it.numel - beg) : DLMCQ_ROOTQ_UNIT;
-  const RqW pw = load_rqw(it.state);
+  RqW pw = {};
+  float rs = 0.f, up = 0.f, qa = 0.f;
+  FastDiv fd = {};
+  if constexpr (WEIGHT) pw = load_rqw(it.state);
+  else { rs = it.state[RA_SCALE]; up = it.state[RA_UPPER]; qa = it.state[RA_Q]; fd = make_fastdiv(rs); }
   const T* xr = static_cast<const T*>(it.x) + beg;
   const T* gr = BWD ? static_cast<const T*>(it.dy) + beg : nullptr;
   T* yr = static_cast<T*>(it.y) + beg;
@@ -445,20 +450,29 @@ rootq_wt_grouped_kernel(const dlmcq_rootq_item* __restrict__ items, const int64_
     const raw* xv = reinterpret_cast<const raw*>(xr);
     const raw* gv = reinterpret_cast<const raw*>(gr);
     raw* yv = reinterpret_cast<raw*>(yr);
-    for (int64_t j = lane; j < nvec; j += 64) {           // two 128-bit loads per tensor in flight
-      const bool two = j + 32 < nvec;
-      raw x0 = ld_stream(xv + j), x1 = x0, g0 = x0, g1 = x0;
-      if (two) x1 = ld_stream(xv + j + 32);
-      if (BWD) { g0 = ld_stream(gv + j); if (two) g1 = ld_stream(gv + j + 32); }
+    for (int64_t j = lane; j < nvec; j += 32 * U) {
+      raw xs[U], gs[U];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && !two) break;
+      for (int h = 0; h < U; ++h) {
+        const bool in = j + 32 * h < nvec;
+        xs[h] = ld_stream(xv + (in ? j + 32 * h : j));
+        if (BWD) gs[h] = ld_stream(gv + (in ? j + 32 * h : j));
+      }
+#pragma unroll
+      for (int h = 0; h < U; ++h) {
+        if (j + 32 * h >= nvec) break;
         float a[V::N], b[V::N], o[V::N];
-        V::unpack(h ? x1 : x0, a);
-        if (BWD) V::unpack(h ? g1 : g0, b);
+        V::unpack(xs[h], a);
+        if (BWD) V::unpack(gs[h], b);
+        if constexpr (WEIGHT) {
 #pragma unroll
-        for (int e = 0; e < V::N; ++e)
-          o[e] = BWD ? rq_wt_bwd(a[e], b[e], pw, acc[0], acc[1], acc[2]) : rq_wt_fwd(a[e], pw);
+          for (int e = 0; e < V::N; ++e)
+            o[e] = BWD ? rq_wt_bwd(a[e], b[e], pw, acc[0], acc[1], acc[2]) : rq_wt_fwd(a[e], pw);
+        } else if constexpr (BWD) {
+          rq_act_bwd_vec<V::N>(a, b, rs, up, qa, fd, o, acc[0]);
+        } else {
+          rq_act_fwd_vec<V::N>(a, rs, up, fd, o);
+        }
         st_stream(yv + j + 32 * h, V::pack(o));
       }
     }
@@ -466,23 +480,30 @@ rootq_wt_grouped_kernel(const dlmcq_rootq_item* __restrict__ items, const int64_
   }
   for (int64_t j = done + lane; j < len; j += 32) {
     const float a = to_f32<T>(xr[j]);
-    yr[j] = from_f32<T>(BWD ? rq_wt_bwd(a, to_f32<T>(gr[j]), pw, acc[0], acc[1], acc[2]) : rq_wt_fwd(a, pw));
+    float o;
+    if constexpr (WEIGHT) o = BWD ? rq_wt_bwd(a, to_f32<T>(gr[j]), pw, acc[0], acc[1], acc[2]) : rq_wt_fwd(a, pw);
+    else o = BWD ? rq_act_bwd(a, to_f32<T>(gr[j]), rs, up, qa, acc[0]) : rq_act_fwd(a, rs, up);
+    yr[j] = from_f32<T>(o);
   }
   if (BWD) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) acc[q] = warp_sum(acc[q]);
+    for (int q = 0; q < (WEIGHT ? 3 : 1); ++q) acc[q] = warp_sum(acc[q]);
     if (lane == 0) {
       partials[3 * unit] = acc[0];
-      partials[3 * unit + 1] = acc[1];
-      partials[3 * unit + 2] = acc[2];
+      if (WEIGHT) {
+        partials[3 * unit + 1] = acc[1];
+        partials[3 * unit + 2] = acc[2];
+      }
     }
   }
 }
 
-// one warp per tensor: fixed-order sum (double) of its units' partials, then the chain of base.py:137-139
+// one warp per tensor: fixed-order sum (double) of its units' partials, then the chain of base.py:137-139 (weights)
+// or base.py:95,97 (activations)
+template <bool WEIGHT>
 __global__ void __launch_bounds__(kRowWarps * 32)
-rootq_wt_grouped_finalize(const dlmcq_rootq_item* __restrict__ items, const int64_t* __restrict__ prefix, int n_items,
-                          const float* __restrict__ partials) {
+rootq_grouped_finalize(const dlmcq_rootq_item* __restrict__ items, const int64_t* __restrict__ prefix, int n_items,
+                       const float* __restrict__ partials) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (k >= n_items) return;
@@ -490,15 +511,21 @@ rootq_wt_grouped_finalize(const dlmcq_rootq_item* __restrict__ items, const int6
   const int64_t u0 = prefix[k], u1 = prefix[k + 1];
   double t[3] = {0.0, 0.0, 0.0};
   for (int64_t u = u0 + lane; u < u1; u += 32) {
-    t[0] += partials[3 * u]; t[1] += partials[3 * u + 1]; t[2] += partials[3 * u + 2];
+    t[0] += partials[3 * u];
+    if (WEIGHT) { t[1] += partials[3 * u + 1]; t[2] += partials[3 * u + 2]; }
   }
 #pragma unroll
-  for (int q = 0; q < 3; ++q) t[q] = warp_sum(t[q]);
+  for (int q = 0; q < (WEIGHT ? 3 : 1); ++q) t[q] = warp_sum(t[q]);
   if (lane == 0) {
-    const float g = it.state[RW_G], m = it.state[RW_M];
-    it.grads[0] = m * (g * static_cast<float>(t[0]));
-    it.grads[1] = m * (g * static_cast<float>(t[1]));
-    it.grads[2] = it.state[RW_AMASK] * static_cast<float>(t[2]);
+    if (WEIGHT) {
+      const float g = it.state[RW_G], m = it.state[RW_M];
+      it.grads[0] = m * (g * static_cast<float>(t[0]));
+      it.grads[1] = m * (g * static_cast<float>(t[1]));
+      it.grads[2] = it.state[RW_AMASK] * static_cast<float>(t[2]);
+    } else {
+      const float g = it.state[RA_G], m = it.state[RA_M];
+      it.grads[0] = m * (g * static_cast<float>(t[0]));      // d in_scale
+    }
   }
 }
 
@@ -600,43 +627,47 @@ extern "C" int dlmcq_rootq_prepare_many(const dlmcq_rootq_prep* items, int n_ite
   return DLMCQ_OK;
 }
 
-extern "C" int dlmcq_rootq_wt_forward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
-                                              int64_t total_units, int dtype, void* stream) {
-  if (!items || !unit_prefix || n_items < 1 || total_units < 0) return DLMCQ_EINVAL;
+template <bool WEIGHT, bool BWD>
+static int rootq_grouped_launch(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                int64_t total_units, int dtype, float* partials, void* stream) {
+  if (!items || !unit_prefix || (BWD && !partials) || n_items < 1 || total_units < 0) return DLMCQ_EINVAL;
   if (total_units == 0) return DLMCQ_OK;
   const int64_t blocks = (total_units + kRowWarps - 1) / kRowWarps;
   if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == DLMCQ_F32)
-    rootq_wt_grouped_kernel<float, false><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
-        items, unit_prefix, n_items, total_units, nullptr);
+    rootq_grouped_kernel<float, WEIGHT, BWD><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, total_units, partials);
   else if (dtype == DLMCQ_BF16)
-    rootq_wt_grouped_kernel<__nv_bfloat16, false><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
-        items, unit_prefix, n_items, total_units, nullptr);
+    rootq_grouped_kernel<__nv_bfloat16, WEIGHT, BWD><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, total_units, partials);
   else
     return DLMCQ_EINVAL;
   DLMCQ_LAUNCH_CHECK();
+  if (BWD) {
+    rootq_grouped_finalize<WEIGHT><<<(n_items + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(
+        items, unit_prefix, n_items, partials);
+    DLMCQ_LAUNCH_CHECK();
+  }
   return DLMCQ_OK;
+}
+
+extern "C" int dlmcq_rootq_wt_forward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                              int64_t total_units, int dtype, void* stream) {
+  return rootq_grouped_launch<true, false>(items, unit_prefix, n_items, total_units, dtype, nullptr, stream);
 }
 
 extern "C" int dlmcq_rootq_wt_backward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
                                                int64_t total_units, int dtype, float* partials, void* stream) {
-  if (!items || !unit_prefix || !partials || n_items < 1 || total_units < 0) return DLMCQ_EINVAL;
-  if (total_units == 0) return DLMCQ_OK;
-  const int64_t blocks = (total_units + kRowWarps - 1) / kRowWarps;
-  if (blocks > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == DLMCQ_F32)
-    rootq_wt_grouped_kernel<float, true><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
-        items, unit_prefix, n_items, total_units, partials);
-  else if (dtype == DLMCQ_BF16)
-    rootq_wt_grouped_kernel<__nv_bfloat16, true><<<static_cast<unsigned>(blocks), kRowWarps * 32, 0, st>>>(
-        items, unit_prefix, n_items, total_units, partials);
-  else
-    return DLMCQ_EINVAL;
-  DLMCQ_LAUNCH_CHECK();
-  rootq_wt_grouped_finalize<<<(n_items + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, st>>>(items, unit_prefix,
-                                                                                               n_items, partials);
-  DLMCQ_LAUNCH_CHECK();
-  return DLMCQ_OK;
+  return rootq_grouped_launch<true, true>(items, unit_prefix, n_items, total_units, dtype, partials, stream);
+}
+
+extern "C" int dlmcq_rootq_act_forward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                               int64_t total_units, int dtype, void* stream) {
+  return rootq_grouped_launch<false, false>(items, unit_prefix, n_items, total_units, dtype, nullptr, stream);
+}
+
+extern "C" int dlmcq_rootq_act_backward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                                int64_t total_units, int dtype, float* partials, void* stream) {
+  return rootq_grouped_launch<false, true>(items, unit_prefix, n_items, total_units, dtype, partials, stream);
 }

@@ -319,17 +319,18 @@ def kth_values(x, ranks, abs_input=False, reduce_hist=None, fast=True):
     values = torch.empty(2, dtype=torch.float32, device=x.device)
     flags = 1 if abs_input else 0
     if reduce_hist is None and fast and x.numel() >= 65536:
-        # single GPU: one full read (sample bracket -> count + collect -> exact select among the candidates); the
-        # status word (one host read, calibration time only) says whether the bracket held - else the 3-pass select
-        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        # single GPU: one full read (sample bracket -> count + collect -> exact select among the candidates).  The
+        # status word stays on the device: it arms the 3-pass select, whose kernels return at once when the bracket
+        # held (no host read; the whole call is stream-ordered and graph-capturable) - all from ONE library call
+        state = torch.empty(h.dlmcq_obs_kth_state_bytes() + 8, dtype=torch.uint8, device=x.device)
+        status = state[-8:].view(torch.int32)
         with torch.cuda.device(x.device):
             nws = h.dlmcq_obs_kth_fast_workspace_bytes(x.numel())
             ws = _scratch(x.device, nws)          # NOT the shared zero-contract workspace: this call scribbles on all of it
-            _lib.check(h.dlmcq_obs_kth_fast(_ptr(x), x.numel(), _dtype_code(x), flags, ranks[0],
+            _lib.check(h.dlmcq_obs_kth_auto(_ptr(x), x.numel(), _dtype_code(x), flags, ranks[0],
                                             ranks[1] if len(ranks) > 1 else 0, _ptr(values),
-                                            C.c_void_p(status.data_ptr()), _ptr(ws), nws, _stream_ptr()))
-        if int(status.item()) == 1:
-            return values[:len(ranks)]
+                                            C.c_void_p(status.data_ptr()), _ptr(state), _ptr(ws), nws, _stream_ptr()))
+        return values[:len(ranks)]
     state = torch.zeros(h.dlmcq_obs_kth_state_bytes(), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         st = _stream_ptr()
@@ -691,8 +692,8 @@ class GroupedRootQ:
     def __init__(self, device):
         self.device = torch.device(device)
         self._prep_key = self._prep_tab = self.states = None
-        self._wt = {False: [None, None, None, 0], True: [None, None, None, 0]}   # key, items, prefix, units
-        self._partials = None
+        self._wt = {(w, b): [None, None, None, 0] for w in ("wt", "act") for b in (False, True)}   # key, items, prefix, units
+        self._partials = {"wt": None, "act": None}
 
     def prepare(self, quantizers):
         """quantizers: dicts with kind 'act' (in_scale, run_scale) or 'wt' (upper, lower, alpha, run_upper,
@@ -720,8 +721,8 @@ class GroupedRootQ:
             _lib.check(_lib.lib().dlmcq_rootq_prepare_many(_ptr(self._prep_tab), len(quantizers), _stream_ptr()))
         return [self.states[i] for i in range(len(quantizers))]
 
-    def _table(self, entries, backward):
-        slot = self._wt[backward]
+    def _table(self, entries, backward, kind="wt"):
+        slot = self._wt[(kind, backward)]
         key = tuple((e["w"].data_ptr(), e["out"].data_ptr(), e["dy"].data_ptr() if backward else 0,
                      e["state"].data_ptr(), e["grads"].data_ptr() if backward else 0, e["w"].numel()) for e in entries)
         if key == slot[0]:
@@ -738,8 +739,8 @@ class GroupedRootQ:
         slot[1] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
         slot[2] = torch.tensor(units, dtype=torch.int64).to(self.device)
         slot[3] = units[-1]
-        if self._partials is None or self._partials.numel() < 3 * units[-1]:
-            self._partials = torch.empty(max(3 * units[-1], 1), dtype=torch.float32, device=self.device)
+        if self._partials[kind] is None or self._partials[kind].numel() < 3 * units[-1]:
+            self._partials[kind] = torch.empty(max(3 * units[-1], 1), dtype=torch.float32, device=self.device)
         return slot
 
     def wt_forward(self, entries, dtype=torch.float32):
@@ -755,7 +756,24 @@ class GroupedRootQ:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().dlmcq_rootq_wt_backward_grouped(_ptr(items), _ptr(prefix), len(entries), units,
                                                                   F32 if dtype == torch.float32 else BF16,
-                                                                  _ptr(self._partials), _stream_ptr()))
+                                                                  _ptr(self._partials["wt"]), _stream_ptr()))
+
+    def act_forward(self, entries, dtype=torch.float32):
+        """Several ACTIVATION tensors in one launch.  entries: dicts with w (the activation), out (receives x_q), state
+        (the block `prepare` / rootq_act_prepare wrote) - contiguous tensors resident at the same time: a block input
+        that feeds two quantised convolutions, cached calibration activations, a quantizer-set measurement."""
+        _, items, prefix, units = self._table(entries, False, "act")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_rootq_act_forward_grouped(_ptr(items), _ptr(prefix), len(entries), units,
+                                                                  F32 if dtype == torch.float32 else BF16, _stream_ptr()))
+
+    def act_backward(self, entries, dtype=torch.float32):
+        """entries additionally carry dy and grads [1] (d in_scale); out receives dx."""
+        _, items, prefix, units = self._table(entries, True, "act")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dlmcq_rootq_act_backward_grouped(_ptr(items), _ptr(prefix), len(entries), units,
+                                                                   F32 if dtype == torch.float32 else BF16,
+                                                                   _ptr(self._partials["act"]), _stream_ptr()))
 
 
 class HostFakeQuant:

@@ -220,6 +220,15 @@ int dlmcq_rootq_wt_forward_grouped(const dlmcq_rootq_item* items, const int64_t*
                                    int64_t total_units, int dtype, void* stream);
 int dlmcq_rootq_wt_backward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
                                     int64_t total_units, int dtype, float* partials, void* stream);
+/* The same launches for ACTIVATION quantizers (RootQ/base.py:92-111): several activation tensors that are resident at
+ * the same time - the tensor a residual block feeds to both its first convolution and its shortcut convolution
+ * (two quantizers, two in_scales), cached calibration activations, the quantizer set of BASELINE configs[0] - go
+ * through one launch per direction.  item: x, y = x_q (forward) or dx (backward), dy, state = the block written by
+ * dlmcq_rootq_act_prepare / _prepare_many, grads[1] = d in_scale.  partials: 3*total_units floats. */
+int dlmcq_rootq_act_forward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                    int64_t total_units, int dtype, void* stream);
+int dlmcq_rootq_act_backward_grouped(const dlmcq_rootq_item* items, const int64_t* unit_prefix, int n_items,
+                                     int64_t total_units, int dtype, float* partials, void* stream);
 
 /* ---- observers (dlmc/quantization/scalar/ops.py) --------------------------------------
  * Statistics pass: one read of the tensor -> stats[channels][4] = {min, max, max|x|, sum|x|}
@@ -266,13 +275,20 @@ int dlmcq_obs_kth_values(const void* state, float* values, void* stream);
 
 /* The same order statistics in ONE full read (single GPU): the k-th element is bracketed from 16 384 pseudo-randomly
  * placed samples, the read counts what lies below the bracket and collects the few elements inside it, and an exact
- * radix select over those candidates gives the answer.  *status (device) = 1: values[] hold the exact result;
- * 0: the bracket missed or the candidate buffer overflowed (probability ~1e-9 per call; also any
- * adversarial input) - run the three-pass select above.  Returns DLMCQ_EUNSUPPORTED for numel < 65 536 (use the
- * three-pass form).  Never approximate: the sample only decides the speed. */
+ * radix select over those candidates gives the answer.  values[] are exact in every case: if the bracket missed or
+ * the candidate buffer overflowed (probability ~1e-9 per call on ordinary data; any adversarially ordered input)
+ * the same cooperative launch runs the three-digit select over the whole tensor instead.  *status (device) only
+ * reports which happened: 1 = the bracket held (one read), 0 = the in-kernel full select ran (four reads).  Returns
+ * DLMCQ_EUNSUPPORTED for numel < 65 536 (use the three-pass form).  The sample decides the speed, never the value. */
 size_t dlmcq_obs_kth_fast_workspace_bytes(int64_t numel);
 int dlmcq_obs_kth_fast(const void* x, int64_t numel, int dtype, int flags, int64_t rank0, int64_t rank1, float* values,
                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+/* One entry for the observer: dlmcq_obs_kth_fast for numel >= 65536 (exact whether or not its bracket held), the
+ * three-pass select below that.  state: dlmcq_obs_kth_state_bytes() bytes; scratch: dlmcq_obs_kth_fast_workspace_bytes
+ * (numel) bytes (may be NULL / 0 for numel < 65536).  Stream-ordered, no host read; *status ends as 1 when the one-read
+ * path's bracket held. */
+int dlmcq_obs_kth_auto(const void* x, int64_t numel, int dtype, int flags, int64_t rank0, int64_t rank1, float* values,
+                       int32_t* status, void* state, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ops.py:36-68 quantize_l2loss_tensor (unsigned branch): 80-candidate clip-ratio sweep.
  * Pass 1 (dlmcq_obs_stats) gives min/max; this pass accumulates the 80 squared-error sums

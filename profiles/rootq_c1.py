@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--cpu-passes", type=int, default=3)
     ap.add_argument("--per-layer", action="store_true", help="six launches per layer instead of the grouped launches")
+    ap.add_argument("--act-per-layer", action="store_true",
+                    help="grouped prepare / weights, but one activation launch per layer and direction (round 1)")
     args = ap.parse_args()
     from dlmc_quant_b200 import functional as F
     from oracle import restate as R
@@ -96,8 +98,22 @@ def main():
         grp.wt_backward([dict(w=d["w"], dy=d["dyw"], out=d["dw"], state=states[2 * i + 1], grads=d["gw"])
                          for i, d in enumerate(dev)])
 
-    step = step_per_layer if args.per_layer else step_grouped
-    launches = 21 * 6 if args.per_layer else 21 * 2 + 4
+    for d in dev:
+        d["y"], d["dx"], d["ds"] = torch.empty_like(d["x"]), torch.empty_like(d["x"]), torch.empty(1, device="cuda")
+
+    def step_all_grouped():
+        # the quantizer set has every tensor resident at once: the 21 activation tensors go through ONE launch per
+        # direction as well (dlmcq_rootq_act_forward_grouped / _backward_grouped) - 8 launches for the whole step
+        states = grp.prepare(quantizers)
+        grp.wt_forward([dict(w=d["w"], out=d["wq"], state=states[2 * i + 1]) for i, d in enumerate(dev)])
+        grp.act_forward([dict(w=d["x"], out=d["y"], state=states[2 * i]) for i, d in enumerate(dev)])
+        grp.act_backward([dict(w=d["x"], dy=d["dyx"], out=d["dx"], state=states[2 * i], grads=d["ds"])
+                          for i, d in enumerate(dev)])
+        grp.wt_backward([dict(w=d["w"], dy=d["dyw"], out=d["dw"], state=states[2 * i + 1], grads=d["gw"])
+                         for i, d in enumerate(dev)])
+
+    step = step_per_layer if args.per_layer else (step_grouped if args.act_per_layer else step_all_grouped)
+    launches = 21 * 6 if args.per_layer else (21 * 2 + 4 if args.act_per_layer else 8)
 
     for _ in range(3):
         step()

@@ -156,8 +156,8 @@ def _small_qat_net(dev):
     quantize_model(net, copy.deepcopy(_GRAPH_CFG), None)
     net = net.to(memory_format=torch.channels_last).train()
     gen = torch.Generator().manual_seed(5)
-    xs = torch.rand(6, 8, 3, 12, 12, generator=gen).to(dev).contiguous(memory_format=torch.channels_last)
-    ts = torch.randint(0, 5, (6, 8), generator=gen).to(dev)
+    xs = [x.to(dev).contiguous(memory_format=torch.channels_last) for x in torch.rand(6, 8, 3, 12, 12, generator=gen)]
+    ts = list(torch.randint(0, 5, (6, 8), generator=gen).to(dev))
     with torch.no_grad():
         net(xs[0])                                          # lazy observer initialisation
     group_weight_quantizers(net)
@@ -204,7 +204,8 @@ def test_whole_step_cuda_graph_equals_the_eager_steps():
         assert torch.allclose(a, b, rtol=2e-3, atol=2e-4), (k, (a - b).abs().max())
     # a model whose observers have not run cannot be captured: loud error, not a silent sync inside the capture
     from dlmc_quant_b200 import quantize_model
-    cold = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Flatten(), torch.nn.LazyLinear(5)).to(dev)
+    cold = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                               torch.nn.Linear(4, 5)).to(dev)
     quantize_model(cold, copy.deepcopy(_GRAPH_CFG), None)
     with pytest.raises(RuntimeError, match="run one forward first"):
         graph_train_step(cold, torch.optim.SGD(cold.parameters(), lr=0.1), crit, xs[0], ts[0])

@@ -399,6 +399,67 @@ def test_channel_major_kernels_with_several_batch_chunks(shape):
     red_close(ds, ds_ref.reshape(-1), abs_sum=dy.abs().sum(dim=(0, 2, 3)) * 15 * g)
 
 
+@pytest.mark.parametrize("shape,dtype", [
+    ((400, 8, 7, 7), torch.float32),        # G = 4 channels per 49-vector run, several batch chunks
+    ((300, 12, 5, 5), torch.float32),       # 25-vector runs
+    ((257, 16, 3, 3), torch.float32),       # 9-vector runs, ragged last pass
+    ((1000, 64, 1, 1), torch.float32),      # inner == 1: a vector is four channels
+    ((90, 6, 5, 10), torch.float32),        # inner % 4 == 2: G = 2
+    ((3, 2048, 7, 7), torch.float32),       # fewer batch indices than rows per pass
+    ((200, 16, 7, 7), torch.bfloat16),      # VEC = 8: G = 8, one channel per warp in the CTA fold
+    ((130, 8, 3, 5), torch.bfloat16),       # inner = 15, G = 8, 15-vector runs
+])
+def test_slab_kernels_for_rows_that_are_not_whole_vectors(shape, dtype):
+    """stats_slab_kernel / fq_slab_kernel (per-channel activations with short, unaligned rows read as 128-bit vectors
+    across G adjacent channels): statistics, forward (AFFINE and ZP forms, codes too), backward and the NaN rule equal
+    the oracle exactly as the scalar channel-major kernels did; a channel count that is not a multiple of G still takes
+    the scalar kernels and gives the same bits."""
+    gen = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = (torch.relu(torch.randn(shape, generator=gen)) * 1.5 - 0.1).to(dtype)
+    dy = torch.randn(x.shape, generator=gen).to(dtype)
+    xf, dyf = x.float(), dy.float()
+    C = shape[1]
+    st = F().obs_stats(dev(x), ch_axis=1).cpu()
+    rows = xf.transpose(0, 1).reshape(C, -1)
+    assert torch.equal(st[:, 0], rows.min(1)[0]) and torch.equal(st[:, 1], rows.max(1)[0])
+    assert torch.equal(st[:, 2], rows.abs().max(1)[0]) and torch.allclose(st[:, 3], rows.abs().sum(1), rtol=1e-5)
+    xn = x.clone()
+    xn[shape[0] - 1, C - 3, shape[2] - 1, shape[3] - 1] = float("nan")
+    stn = F().obs_stats(dev(xn), ch_axis=1).cpu()
+    others = [c for c in range(C) if c != C - 3]
+    assert torch.isnan(stn[C - 3]).all() and not torch.isnan(stn[others]).any()
+    scale, off = R.obs_minmax_channel(xf, 4, False, ch_axis=1)
+    g = R.lsq_g(x.numel(), 15)
+    xs, ss = xf.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+    y_ref = R.fq_affine(xs, ss, off, 0, 15, g)
+    dx_ref, ds_ref = torch.autograd.grad(y_ref, (xs, ss), dyf)
+    y = F().fq_forward(dev(x), dev(scale), dev(off), 0, 15, 1, g=g, ch_axis=1)
+    exact(y.float(), y_ref.detach().to(dtype).float(), "y")
+    dx, ds = F().fq_backward(dev(x), dev(dy), dev(scale), dev(off), 0, 15, 1, g=g, ch_axis=1)
+    # the reference's dx is (dy * s') / s' where in range: up to 1 ulp off dy (the kernels return dy itself)
+    assert torch.equal(dx.float().cpu() == 0, dx_ref == 0) and torch.allclose(dx.float().cpu(), dx_ref, rtol=1e-6 if dtype is torch.float32 else 4e-3, atol=0)
+    red_close(ds, ds_ref.reshape(-1), abs_sum=dyf.abs().sum(dim=(0, 2, 3)) * 15 * g)
+    # zero-point form, with codes
+    zp = torch.arange(C, dtype=torch.float32).reshape(1, C, 1, 1) % 5
+    s2 = (scale.reshape(1, C, 1, 1) * 0.7 + 0.01)
+    y2_ref, dx2_ref, ds2_ref = R.fq_zp_fwd_bwd(xf, s2, zp, 0, 15, dyf)[:3]
+    y2 = F().fq_forward(dev(x), dev(s2.reshape(-1)), dev(zp.reshape(-1)), 0, 15, 2, ch_axis=1)
+    exact(y2.float(), y2_ref.to(dtype).float(), "y zp")
+    dx2, ds2 = F().fq_backward(dev(x), dev(dy), dev(s2.reshape(-1)), dev(zp.reshape(-1)), 0, 15, 2, ch_axis=1)
+    assert torch.equal(dx2.float().cpu() == 0, dx2_ref == 0) and torch.allclose(dx2.float().cpu(), dx2_ref, rtol=1e-6 if dtype is torch.float32 else 4e-3, atol=0)
+    red_close(ds2, ds2_ref.reshape(-1), abs_sum=dyf.abs().sum(dim=(0, 2, 3)) * 16)
+    # odd channel count: the scalar channel-major kernels, same bits on the shared channels
+    if C > 4:
+        xo, dyo = x[:, :C - 1].contiguous(), dy[:, :C - 1].contiguous()
+        so, oo = scale.reshape(-1)[:C - 1].contiguous(), off.reshape(-1)[:C - 1].contiguous()
+        yo = F().fq_forward(dev(xo), dev(so), dev(oo), 0, 15, 1, g=g, ch_axis=1)
+        exact(yo, y[:, :C - 1], "slab vs scalar channel-major forward")
+        dxo, dso = F().fq_backward(dev(xo), dev(dyo), dev(so), dev(oo), 0, 15, 1, g=g, ch_axis=1)
+        exact(dxo, dx[:, :C - 1], "slab vs scalar channel-major backward")
+        red_close(dso, ds[:C - 1], abs_sum=dyf[:, :C - 1].abs().sum(dim=(0, 2, 3)) * 15 * g)
+        assert torch.equal(F().obs_stats(dev(xo), ch_axis=1).cpu()[:, :3], st[:C - 1, :3])
+
+
 def test_l2norm_per_channel_multi_cta_finalise():
     """More than 256 channels: the new scales, the global stopping rule and the done flag are produced by
     several finalising CTAs plus a last-ticket combination."""
@@ -512,6 +573,47 @@ def test_grouped_rootq_matches_per_layer_launches():
         assert bits_equal(ent[i]["out"].cpu(), r["wq"].cpu()), i
         assert bits_equal(bent[i]["out"].cpu(), r["dw"].cpu()), i
         assert torch.allclose(bent[i]["grads"], r["gw"], rtol=1e-5, atol=1e-6), (i, bent[i]["grads"], r["gw"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grouped_rootq_activations_match_per_tensor_launches(dtype):
+    """dlmcq_rootq_act_forward_grouped / _backward_grouped: several activation tensors (ragged sizes, a misaligned
+    view, an empty tensor, one that spans many work units, two quantizers reading the SAME tensor as a residual
+    block's main and shortcut convolutions do) in one launch per direction give the per-tensor entries' x_q and dx
+    bit for bit and d in_scale to 1e-5."""
+    from dlmc_quant_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(77)
+    lo, hi, mom = 0, 15, 0.1
+    base = torch.randn(70_001, generator=gen)
+    xs = [torch.relu(torch.randn(8, 16, 12, 12, generator=gen)) * 2, torch.randn(3, 5, generator=gen) * 4,
+          torch.randn(1_000_003, generator=gen) * 3, base[1:], torch.empty(0), torch.randn(2048 * 3, generator=gen)]
+    xs = [x.to(dtype).cuda() for x in xs]
+    xs[3] = base.to(dtype).cuda()[1:]                       # not 16-byte aligned: scalar path
+    xs.append(xs[0])                                        # second quantizer on the first tensor
+    G = Fn.GroupedRootQ("cuda")
+    qs, ref = [], []
+    for i, x in enumerate(xs):
+        in_scale = torch.tensor([0.05 + 0.07 * i], device="cuda")
+        g = 1 / math.sqrt(max(x.numel(), 1) * hi)
+        run = in_scale.clone() * 0.8
+        sa = Fn.rootq_act_prepare(in_scale, run.clone(), mom, g, lo, hi, True)
+        dy = torch.randn(x.shape, generator=gen).to(dtype).cuda()
+        y = Fn.rootq_act_forward(x, sa) if x.numel() else x.clone()
+        dx, ds = Fn.rootq_act_backward(x, dy, sa) if x.numel() else (x.clone(), torch.zeros(1, device="cuda"))
+        ref.append(dict(y=y, dx=dx, ds=ds, dy=dy))
+        qs.append(dict(kind="act", in_scale=in_scale, run_scale=run, momentum=mom, g=g, lo=lo, hi=hi, training=True))
+    states = G.prepare(qs)
+    fwd = [dict(w=x, out=torch.full_like(x, float("nan")), state=states[i]) for i, x in enumerate(xs)]
+    G.act_forward(fwd, dtype)
+    bwd = [dict(w=x, dy=ref[i]["dy"], out=torch.full_like(x, float("nan")), state=states[i],
+                grads=torch.full((1,), float("nan"), device="cuda")) for i, x in enumerate(xs)]
+    G.act_backward(bwd, dtype)
+    for i, r in enumerate(ref):
+        assert bits_equal(fwd[i]["out"].float().cpu(), r["y"].float().cpu()), i
+        assert bits_equal(bwd[i]["out"].float().cpu(), r["dx"].float().cpu()), i
+        want = r["ds"].reshape(-1)[:1]
+        floor = 4e-7 * float(r["dy"].float().abs().sum()) * hi * float(states[i][2]) * float(states[i][3]) if xs[i].numel() else 0
+        assert torch.allclose(bwd[i]["grads"], want, rtol=1e-5, atol=max(floor, 1e-9)), (i, bwd[i]["grads"], want)
 
 
 # --------------------------------------------------------------------------------------
@@ -773,11 +875,44 @@ def test_resident_l2norm_matches_the_stepwise_loop_and_the_oracle():
     assert it == 2 and not done
 
 
+def test_one_read_kth_value_survives_a_missed_bracket():
+    """The sample positions are a fixed hash of the index: plant values there that misplace the bracket for the rank
+    asked (all samples huge, the tensor otherwise small): status must report the miss and the values must still equal
+    torch.kthvalue - for one rank, two ranks, |x| and bf16."""
+    import ctypes as C
+    from dlmc_quant_b200 import _lib
+    n = 1_500_001
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(n, generator=gen)
+    i = torch.arange(16384, dtype=torch.int64)
+    hsh = (i * 2654435761 + 0x9e3779b9) & 0xffffffff
+    idx = (hsh * n) >> 32
+    x[idx] = 1000.0 + torch.arange(16384, dtype=torch.float32)           # every sample lies above the true quantiles
+    h = _lib.lib()
+    for dtype in (torch.float32, torch.bfloat16):
+        xd = x.to(dtype).cuda()
+        srt = xd.float().cpu().sort()[0]
+        asrt = xd.float().cpu().abs().sort()[0]
+        nws = h.dlmcq_obs_kth_fast_workspace_bytes(n)
+        ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+        for ranks, flags, ref in (((n // 2, 0), 0, srt), ((n // 4, 3 * n // 4), 0, srt), ((n // 2, n - 20000), 1, asrt)):
+            vals = torch.zeros(2, device="cuda")
+            status = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+            _lib.check(h.dlmcq_obs_kth_fast(C.c_void_p(xd.data_ptr()), n, 0 if dtype is torch.float32 else 1, flags,
+                                            ranks[0], ranks[1], C.c_void_p(vals.data_ptr()),
+                                            C.c_void_p(status.data_ptr()), C.c_void_p(ws.data_ptr()), nws, None))
+            torch.cuda.synchronize()
+            assert int(status) == 0, (dtype, ranks)
+            for j, k in enumerate(ranks):
+                if k:
+                    assert vals[j].cpu() == ref[k - 1], (dtype, ranks, j, vals, ref[k - 1])
+
+
 @pytest.mark.parametrize("kind", ["randn", "relu", "relu6", "const", "sorted", "periodic", "heavy_tail"])
 def test_one_read_kth_value_is_exact(kind):
     """dlmcq_obs_kth_fast (sample bracket -> one counting / collecting read -> exact select among the candidates) equals
-    torch.kthvalue on every rank asked, and says so itself (status 1) on ordinary data; where the bracket cannot hold
-    (adversarially ordered data) the wrapper's three-pass fallback still returns the exact value."""
+    torch.kthvalue on every rank asked, and reports status 1 on ordinary data; where the bracket cannot hold the same
+    launch runs the full three-digit select in-kernel (status 0) and the value is exact all the same."""
     n = 3_000_017
     gen = torch.Generator().manual_seed(11)
     x = torch.randn(n, generator=gen) * 2
@@ -816,8 +951,7 @@ def test_one_read_kth_value_is_exact(kind):
     _lib.check(h.dlmcq_obs_kth_fast(C.c_void_p(xd.data_ptr()), n, 0, 0, k, 0, C.c_void_p(vals.data_ptr()),
                                     C.c_void_p(status.data_ptr()), C.c_void_p(ws.data_ptr()), nws, None))
     torch.cuda.synchronize()
-    if int(status) == 1:
-        assert vals[0].cpu() == srt[k - 1], kind
+    assert vals[0].cpu() == srt[k - 1], kind          # exact whether the bracket held (1) or the in-kernel full select ran (0)
     assert int(status) == 1 or kind in ("sorted",), kind          # pseudo-random sample positions: only exotic orders miss
     bf = x[:1_000_003].bfloat16()
     assert F().kth_values(bf.cuda(), [999_000]).cpu()[0] == bf.float().sort()[0][999_000 - 1]
