@@ -15,14 +15,13 @@ DistributedDataParallel: the DDP step is host-bound too (the GPU idles ~7 ms of 
 the NCCL kernels take < 1 ms: profiles/r02_ddp_gpu_busy_n2.jsonl), so the step is captured INCLUDING DDP's bucketed
 gradient all-reduces.  PyTorch's rules for that: the DDP wrapper is constructed on a side stream (`wrap_ddp`), at least
 11 eager iterations run before capture (bucket rebuild, the reducer's first-iteration logic - `graph_train_step` warms
-up 12 when it sees a DDP model) and NCCL's async error watchdog is off (`TORCH_NCCL_ASYNC_ERROR_HANDLING=0`, set before
-`init_process_group`).
+up 12 when it sees a DDP model).  NCCL >= 2.9.6 captures its collectives as they are (measured here under torchrun,
+which sets TORCH_NCCL_ASYNC_ERROR_HANDLING=1: profiles/r02_ddp_graph_probe_n{2,8}.jsonl); older NCCL needs that variable
+set to 0 before `init_process_group`.
 
     model = wrap_ddp(model, device_ids=[local_rank])
     optimizer = torch.optim.SGD(model.parameters(), ...)
     step = graph_train_step(model, optimizer, criterion, x, t)"""
-import os
-
 import torch
 
 __all__ = ["graph_train_step", "wrap_ddp"]
@@ -32,9 +31,6 @@ _DDP_WARMUP = 12
 
 def wrap_ddp(model, **ddp_kwargs):
     """DistributedDataParallel(model, **ddp_kwargs) constructed on a side stream, as whole-step capture requires."""
-    if os.environ.get("TORCH_NCCL_ASYNC_ERROR_HANDLING", "") not in ("0",):
-        raise RuntimeError("wrap_ddp: set TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group - NCCL work "
-                           "captured in a CUDA graph cannot be watched by the async error handler")
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):

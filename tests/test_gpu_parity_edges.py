@@ -229,10 +229,16 @@ def _ddp_graph_worker(rank, world, port, results):
         mk = lambda m: torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)  # noqa: E731
         ddp, ddp_ref = wrap_ddp(net, device_ids=[rank]), torch.nn.parallel.DistributedDataParallel(ref, device_ids=[rank])
         opt, opt_ref = mk(ddp), mk(ddp_ref)
+        print(f"[rank {rank}] models built", flush=True)
         step = graph_train_step(ddp, opt, crit, xs[0], ts[0])          # 12 eager warm-up steps (DDP), then capture
+        print(f"[rank {rank}] captured", flush=True)
         order = [1, 2, 3, 4, 5]
         got = _train(ddp, opt, crit, xs, ts, order, stepper=step)
+        torch.cuda.synchronize()
+        print(f"[rank {rank}] replayed", flush=True)
         want = _train(ddp_ref, opt_ref, crit, xs, ts, [0] * 12 + order)[12:]
+        torch.cuda.synchronize()
+        print(f"[rank {rank}] eager reference done", flush=True)
         ok = bool(torch.isfinite(got).all() and torch.allclose(got, want, rtol=1e-3, atol=1e-4))
         worst = 0.0
         for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
@@ -249,6 +255,9 @@ def _ddp_graph_worker(rank, world, port, results):
         if rank == 0:
             results.update({"losses": bool(okmin[0]), "ranks_agree": bool(okmin[1]), "worst_rel": float(res[2])})
         dist.barrier()
+        # the captured graph holds NCCL kernels: release it before the communicator goes away
+        del step, got, want
+        torch.cuda.synchronize()
     finally:
         dist.destroy_process_group()
 
@@ -257,11 +266,18 @@ def _ddp_graph_worker(rank, world, port, results):
 def test_two_ranks_whole_step_graph_under_ddp():
     """The captured step includes DDP's bucketed gradient all-reduces: replayed on 2 ranks it follows the eager DDP
     trajectory and leaves identical parameters on both ranks."""
+    import time
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         results = mgr.dict()
         port = 29800 + os.getpid() % 200
-        mp.spawn(_ddp_graph_worker, args=(2, port, results), nprocs=2, join=True)
+        procs = mp.spawn(_ddp_graph_worker, args=(2, port, results), nprocs=2, join=False)
+        deadline = time.time() + 240                       # a wedged collective must fail the test, not hang the suite
+        while not procs.join(timeout=5):
+            if time.time() > deadline:
+                for p in procs.processes:
+                    p.kill()
+                pytest.fail("2-rank whole-step graph workers did not finish in 240 s")
         got = dict(results)
     assert got.get("losses") and got.get("ranks_agree") and got["worst_rel"] < 5e-3, got
