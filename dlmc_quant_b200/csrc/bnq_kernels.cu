@@ -206,29 +206,46 @@ bnq_stats_kernel(const T* __restrict__ x, BnqGeom gm, float* __restrict__ part) 
   bnq_store_partials<VN>(s1, s2, sm, gm, tx, ty, col, active, part);
 }
 
-// one WARP per channel: the lanes stride over the nbx per-CTA partials (independent loads, all in flight at once),
-// accumulate in double and fold with a fixed shuffle tree - a few microseconds whatever the partial count (a thread
-// per channel walking the partials serially took 25-50 us, more than the statistics pass itself)
+// Column sums of the per-CTA partials [nbx][2][C] for 32 adjacent channels, in a fixed order: thread (warp w, lane l)
+// adds rows w, w + W, ... of channel c0 + l - every warp load is one coalesced 128-byte row segment (a warp per channel
+// striding over the rows touched one 32-byte sector per 4 useful bytes and took 13 - 14 us on 592 x 256 partials) -
+// and warp 0 folds the W warp sums in warp order.  Valid in warp 0 (lane = channel - c0) on return.
+constexpr int kBnqFoldWarps = 16;
+__device__ __forceinline__ void bnq_fold_partials(const float* __restrict__ part, int nbx, int C, int c0,
+                                                  double (*sh)[2][32], double& s0, double& s1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = c0 + lane;
+  const size_t stride = 2 * static_cast<size_t>(C);
+  double t0 = 0.0, t1 = 0.0;
+  if (c < C) {
+#pragma unroll 8
+    for (int b = warp; b < nbx; b += kBnqFoldWarps) {
+      t0 += static_cast<double>(__ldcg(part + b * stride + c));
+      t1 += static_cast<double>(__ldcg(part + b * stride + C + c));
+    }
+  }
+  sh[warp][0][lane] = t0;
+  sh[warp][1][lane] = t1;
+  __syncthreads();
+  s0 = 0.0; s1 = 0.0;
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 0; w < kBnqFoldWarps; ++w) { s0 += sh[w][0][lane]; s1 += sh[w][1][lane]; }
+  }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBnqFoldWarps * 32)
 bnq_stats_finalize_kernel(const T* __restrict__ x, const float* __restrict__ part, BnqGeom gm, float eps, float momentum,
                           float* __restrict__ running_mean, float* __restrict__ running_var,
                           float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  __shared__ double sh[kBnqFoldWarps][2][32];
   pdl_wait();          // the partials come from the statistics kernel launched just before
   pdl_trigger();
-  if (c >= gm.C) return;
-  double t1 = 0.0, t2 = 0.0;
-  const size_t stride = 2 * static_cast<size_t>(gm.C);
-#pragma unroll 4
-  for (int b = lane; b < gm.nbx; b += 32) {
-    t1 += static_cast<double>(__ldcg(part + b * stride + c));
-    t2 += static_cast<double>(__ldcg(part + b * stride + gm.C + c));
-  }
-  t1 = warp_sum(t1);
-  t2 = warp_sum(t2);
-  if (lane == 0) {
+  double t1, t2;
+  bnq_fold_partials(part, gm.nbx, gm.C, blockIdx.x * 32, sh, t1, t2);
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  if (threadIdx.x < 32 && c < gm.C) {
     const double n = static_cast<double>(gm.rows);
     const double k = static_cast<double>(to_f32<T>(x[c]));
     const double m1 = t1 / n;
@@ -786,13 +803,13 @@ bnq_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ a_saved, co
   }
 }
 
-// per-channel d gamma / d beta and the coefficients of the dx pass (one warp per channel, as above); the last CTA
-// reduces the scale gradient
-__global__ void __launch_bounds__(256)
+// per-channel d gamma / d beta and the coefficients of the dx pass (32 channels per CTA, folded as above); the last
+// CTA reduces the scale gradient
+__global__ void __launch_bounds__(kBnqFoldWarps * 32)
 bnq_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ part_s, BnqGeom gm, int n_part_s,
                         int training, float g, float* __restrict__ dgamma, float* __restrict__ dbeta,
                         float* __restrict__ coef, float* __restrict__ dscale) {
-  __shared__ double sh[8];
+  __shared__ double sh[kBnqFoldWarps][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_wait();
   pdl_trigger();
@@ -800,27 +817,19 @@ bnq_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict_
     double s = 0.0;
     for (int i = threadIdx.x; i < n_part_s; i += blockDim.x) s += static_cast<double>(__ldcg(part_s + i));
     s = warp_sum(s);
-    if (lane == 0) sh[warp] = s;
+    if (lane == 0) sh[warp][0][0] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.0;
-      for (int r = 0; r < 8; ++r) t += sh[r];
+      for (int r = 0; r < kBnqFoldWarps; ++r) t += sh[r][0][0];
       if (dscale) dscale[0] = static_cast<float>(t) * g;     // chain through grad_scale (utils.py:24-27)
     }
     return;
   }
-  const int c = blockIdx.x * 8 + warp;
-  if (c >= gm.C) return;
-  double db = 0.0, dg = 0.0;
-  const size_t stride = 2 * static_cast<size_t>(gm.C);
-#pragma unroll 4
-  for (int b = lane; b < gm.nbx; b += 32) {
-    db += static_cast<double>(__ldcg(part + b * stride + c));
-    dg += static_cast<double>(__ldcg(part + b * stride + gm.C + c));
-  }
-  db = warp_sum(db);
-  dg = warp_sum(dg);
-  if (lane == 0) {
+  double db, dg;
+  bnq_fold_partials(part, gm.nbx, gm.C, blockIdx.x * 32, sh, db, dg);
+  const int c = blockIdx.x * 32 + lane;
+  if (warp == 0 && c < gm.C) {
     if (dbeta) dbeta[c] = static_cast<float>(db);
     if (dgamma) dgamma[c] = static_cast<float>(dg);
     const double n = static_cast<double>(gm.rows);
@@ -1152,7 +1161,7 @@ static int bnq_forward_t(const void* x, const void* idn, const float* gamma, con
     cudaError_t e = launch_pdl(bnq_stats_kernel<T>, dim3(g.nbx, g.gy), dim3(kBnqThreads), bnq_smem<VN>(g), st, xt, g,
                                w.part);
     if (e != cudaSuccess) return set_cuda_error(e);
-    e = launch_pdl(bnq_stats_finalize_kernel<T>, dim3((g.C + 7) / 8), dim3(256), 0, st, xt,
+    e = launch_pdl(bnq_stats_finalize_kernel<T>, dim3((g.C + 31) / 32), dim3(kBnqFoldWarps * 32), 0, st, xt,
                    static_cast<const float*>(w.part), g, d->eps, d->momentum, rmean, rvar, smean, sinv);
     if (e != cudaSuccess) return set_cuda_error(e);
   } else {
@@ -1211,7 +1220,7 @@ static int bnq_backward_t(const void* x, const void* a_saved, const void* d_a, c
     if (e != cudaSuccess) return set_cuda_error(e);
   }
   {
-    cudaError_t e = launch_pdl(bnq_bwd_finalize_kernel, dim3((g.C + 7) / 8 + 1), dim3(256), 0, st,
+    cudaError_t e = launch_pdl(bnq_bwd_finalize_kernel, dim3((g.C + 31) / 32 + 1), dim3(kBnqFoldWarps * 32), 0, st,
                                static_cast<const float*>(w.part), static_cast<const float*>(w.part_s), g,
                                quant ? g.nbx * g.gy : 0, training, gq, dgamma, dbeta, w.coef,
                                quant ? dscale : static_cast<float*>(nullptr));

@@ -6,6 +6,7 @@ R=${1:-r02}
 O=gpurun_out
 mkdir -p $O
 NCU="ncu --clock-control none"
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/${R}_smoke.log 2>&1
 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $O/${R}_gpu_tests_full.log
 python bench.py > $O/${R}_bench_n1.json 2> $O/${R}_bench_n1.err && echo bench ok
 python bench.py --impl reference > $O/${R}_bench_reference_n1.json 2>> $O/${R}_bench_n1.err
@@ -25,6 +26,13 @@ python profiles/ncu_summary.py /tmp/${R}_bnq.ncu-rep > $O/${R}_ncu_full_bnq.txt 
 # the .ncu-rep files stay on the box unless small (gpurun_out/ is capped at 64 MiB): the summaries above are what is judged
 for f in /tmp/${R}_fq_flat.ncu-rep /tmp/${R}_bnq.ncu-rep; do [ -f $f ] && [ $(stat -c %s $f) -lt 25000000 ] && cp $f $O/; done
 $NCU --metrics gpu__time_duration.sum,smsp__inst_executed.sum --csv --log-file $O/${R}_launches_bnq.csv python profiles/prof_bnq.py --one > /dev/null 2>&1
+# this round's observer kernels: one-read k-th value, slab kernels (7x7 planes), grouped RootQ launches
+$NCU --set full -k regex:"kth_" -c 3 -o /tmp/${R}_kth python profiles/prof_kth.py > /dev/null 2>&1
+python profiles/ncu_summary.py /tmp/${R}_kth.ncu-rep > $O/${R}_ncu_full_kth.txt 2>&1
+$NCU --set full -k regex:"slab|cmaj|l2norm_resident|sweep_channel_grouped" -c 8 -o /tmp/${R}_obs python profiles/prof_obs.py 1 > /dev/null 2>&1
+python profiles/ncu_summary.py /tmp/${R}_obs.ncu-rep > $O/${R}_ncu_full_observers.txt 2>&1
+$NCU --set full -k regex:"rootq_grouped" -c 4 -o /tmp/${R}_rootq python profiles/rootq_c1.py --cpu-passes 1 > /dev/null 2>&1
+python profiles/ncu_summary.py /tmp/${R}_rootq.ncu-rep > $O/${R}_ncu_full_rootq_grouped.txt 2>&1
 # plain drivers
 python profiles/prof_obs.py 5 > $O/${R}_prof_obs_plain.log 2>&1
 python profiles/prof_kth.py > $O/${R}_prof_kth.log 2>&1
