@@ -14,6 +14,7 @@ STATS_PER_CHANNEL = 4
 DIV_IEEE, DIV_CUDA_EAGER = 0, 1
 SWEEP_CANDIDATES = 80
 ROOTQ_STATE_FLOATS = 8
+QGEMM_I8, QGEMM_E4M3 = 0, 1
 
 
 class Layout(C.Structure):
@@ -147,6 +148,9 @@ SIGNATURES = {
     "dlmcq_host_ctx_synchronize": (_I, [_P]),
     "dlmcq_host_ctx_fq_forward_backward": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F]),
     "dlmcq_host_ctx_fq_codes": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _I]),
+    "dlmcq_codes_forward": (_I, [_P, _P, _LP, _QP, _I, _P]),
+    "dlmcq_qgemm_prepare": (_I, [_P, _L, _L, _I, _QP, _QP, _L, _P, _P, _P, _P]),
+    "dlmcq_qgemm": (_I, [_P, _P, _P, _P, _P, _L, _L, _L, _I, _I, _I, _I, _P]),
 }
 
 

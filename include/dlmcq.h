@@ -482,6 +482,40 @@ int dlmcq_host_ctx_fq_codes(dlmcq_host_ctx* ctx, const void* x_host, const void*
                             void* keep_host, float* dscale_host, int64_t numel, int dtype, int form, int lo, int hi,
                             float g, float scale, float offset, int pack4);
 
+/* ---- the layer's matrix product on the integer codes (consumer side of the activation quantizer) ----------------
+ * Replaces `_forward_func(q_input, q_weight)` = F.linear / a 1x1 F.conv2d on the two FAKE-QUANTISED fp32 tensors
+ * (modules/linear.py, modules/conv.py, entered from modules/base.py:140; FSPTQuant/base.py:111-113) for a per-tensor
+ * activation quantizer and a per-output-channel or per-tensor weight quantizer without an additive weight term:
+ *     sum_k y_a[m,k] * y_w[n,k] = alpha[n] * (sum_k ca[m,k] * cw[n,k]) + beta[n]
+ * with the exact integer dot product of the codes on the tcgen05 tensor cores (TMA-staged one-byte operands, TMEM
+ * accumulators).  Activations are read at ONE byte per element instead of four.
+ *   encoding DLMCQ_QGEMM_I8    one byte per code, uint8 (lo >= 0) or two's complement; tcgen05.mma kind::i8, s32
+ *                              accumulators: exact for every range dlmcq_export_codes accepts (weights: hi <= 127)
+ *   encoding DLMCQ_QGEMM_E4M3  the code as an e4m3 byte, kind::f8f6f4, fp32 accumulators: |code| <= 16 only
+ *
+ * dlmcq_codes_forward   x -> codes, one byte each; the same arithmetic (and therefore the same codes) as
+ *                       dlmcq_fq_forward / dlmcq_export_codes for every form and layout; NaN -> 0.
+ * dlmcq_qgemm_prepare   per output channel n, from DEVICE-resident qparams (no host sync; AFFINE scales go through
+ *                       the grad_scale value like the fake-quant kernels):
+ *                         alpha[n] = m_a * m_w[n]
+ *                         beta[n]  = ((o_a - z_a*m_a) * m_w[n]) * float(sum_k cw[n,k])  (+ bias[n] if bias != NULL)
+ *                       m: dequantisation multiplier, o_a: A1 / AFFINE offset, z_a: ZP zero-point.  wt_qp->offset
+ *                       must be NULL and wt_qp->form != ZP (DLMCQ_EUNSUPPORTED otherwise: the product would not
+ *                       factor); wt_channels = n (per output channel) or 1.  w_codes: [n, k] bytes, row-major.
+ * dlmcq_qgemm           out[m,n] = RN(RN(float(acc[m,n]) * alpha[n]) + beta[n]), optionally max(., 0);
+ *                       a_codes [m, k], w_codes [n, k] bytes row-major, 16-byte aligned, k % 16 == 0
+ *                       (DLMCQ_EUNSUPPORTED otherwise); out [m, n] row-major fp32 / bf16 (a channels-last activation
+ *                       [B,H,W,C] is exactly such a matrix with m = B*H*W).  a_signed: activation codes are int8. */
+#define DLMCQ_QGEMM_I8 0
+#define DLMCQ_QGEMM_E4M3 1
+int dlmcq_codes_forward(const void* x, void* codes, const dlmcq_layout* layout, const dlmcq_qparams* qp, int encoding,
+                        void* stream);
+int dlmcq_qgemm_prepare(const void* w_codes, int64_t n, int64_t k, int encoding, const dlmcq_qparams* act_qp,
+                        const dlmcq_qparams* wt_qp, int64_t wt_channels, const float* bias, float* alpha, float* beta,
+                        void* stream);
+int dlmcq_qgemm(const void* a_codes, const void* w_codes, const float* alpha, const float* beta, void* out, int64_t m,
+                int64_t n, int64_t k, int encoding, int a_signed, int relu, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,38 @@ def fq_sym_fwd_bwd(w, scale, lo, hi, dy):
     return y.detach(), dw, ds
 
 
+# --------------------------------------------------------------------------- #
+# the layer product on the two fake-quantised tensors (consumer side of row f2)
+# --------------------------------------------------------------------------- #
+def layer_product_reference(q_input, q_weight, bias=None, dtype=torch.float64):
+    """modules/linear.py / conv.py `_forward_func(q_input, q_weight)` for a Linear / 1x1 convolution, written as the
+    matrix product it is: q_input [m, k] (fake-quantised activations), q_weight [n, k].  Evaluated in `dtype`
+    (float64 = the exact value of the reference expression up to 1e-16; float32 = what the reference's library call
+    computes up to its own summation order)."""
+    y = q_input.to(dtype) @ q_weight.to(dtype).t()
+    return y if bias is None else y + bias.to(dtype)
+
+
+def code_gemm(a_codes, w_codes, m_a, o_a, z_a, m_w, bias=None, relu=False):
+    """The factored form of the same product that dlmcq_qgemm evaluates (include/dlmcq.h), every fp32 rounding where
+    the kernels round:  acc = exact integer dot product;  alpha[n] = m_a*m_w[n];
+    beta[n] = ((o_a - z_a*m_a) * m_w[n]) * float(sum_k cw[n,k]) (+ bias[n]);  out = (float(acc) * alpha) + beta.
+    a_codes [m,k], w_codes [n,k]: integer-valued tensors; m_a, o_a, z_a: fp32 scalars; m_w: fp32 [n] or [1]."""
+    f32 = torch.float32
+    ca, cw = a_codes.to(torch.int64), w_codes.to(torch.int64)
+    acc = ca @ cw.t()
+    wsum = cw.sum(dim=1)
+    m_a, o_a, z_a = (torch.as_tensor(v, dtype=f32).reshape(()) for v in (m_a, o_a, z_a))
+    m_w = torch.as_tensor(m_w, dtype=f32).reshape(-1).expand(cw.shape[0])
+    alpha = m_a * m_w
+    t = o_a - z_a * m_a
+    beta = (t * m_w) * wsum.to(f32)
+    if bias is not None:
+        beta = beta + bias.to(f32)
+    out = acc.to(f32) * alpha + beta
+    return torch.relu(out) if relu else out
+
+
 ADAROUND_GAMMA, ADAROUND_ZETA = -0.1, 1.1   # FSPTQuant/base.py:62
 
 
