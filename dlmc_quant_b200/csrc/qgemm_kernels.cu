@@ -11,17 +11,17 @@
 //
 // acc is an exact integer dot product of the codes.  It runs on the 5th-generation tensor cores:
 //   * operands: one BYTE per code (1/4 of the fp32 activation traffic the fake-quantised tensor costs cuDNN),
-//     K-major, staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 3-stage mbarrier pipeline;
+//     K-major, staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) through a 4-stage mbarrier pipeline;
 //   * tcgen05.mma cta_group::1 issued by ONE thread, M=128 x N=128 x K=32 per instruction, accumulators in TMEM
 //     (128 lanes x 128 columns); kind::i8 (u8|s8 x s8 -> s32, exact for every code width up to 8 bits; sm_100a has
 //     it) or kind::f8f6f4 on codes stored as e4m3 bytes (exact for |code| <= 16, fp32 accumulators);
 //   * epilogue: tcgen05.ld (32x32b.x32) -> registers -> a padded smem transpose -> coalesced 128-byte row stores of
 //     out = RN(RN(acc * alpha[n]) + beta[n]) (+ ReLU), fp32 or bf16.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-5 = epilogue
-// (warp w may only touch TMEM lanes 32*(w%4) .. +31, so the four epilogue warps cover the four lane quarters).
-// One 128x128 output tile per CTA; two CTAs are co-resident per SM (97 KB of smem, 128 TMEM columns each), so one
-// CTA's epilogue overlaps the other's main loop.  This path is bound by the bytes it moves (codes in, y out), not
-// by the tensor pipe - the point of doing the product on codes is the 4x smaller operand.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-9 = epilogue
+// (warp w may only touch TMEM lanes 32*(w%4) .. +31: two warps per lane quarter, 64 of the tile's 128 columns each).
+// Persistent, one CTA per SM (169 KB of smem, 256 TMEM columns = two accumulator buffers): the epilogue of one tile
+// overlaps the loads and MMAs of the next.  This path is bound by the bytes it moves (codes in, y out), not by the
+// tensor pipe - the point of doing the product on codes is the 4x smaller operand.
 //
 // Also here: dlmcq_codes_forward (x -> one byte per code, the same arithmetic as dlmcq_fq_forward, streaming) and
 // dlmcq_qgemm_prepare (alpha / beta from the DEVICE-resident qparams: no host sync, learnable scales stay put).
@@ -34,13 +34,16 @@ namespace dlmcq {
 namespace {
 
 constexpr int kBM = 128, kBN = 128, kBK = 128;                // tile; kBK bytes = codes (one byte each)
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK, kBBytes = kBN * kBK, kStageBytes = kABytes + kBBytes;
 constexpr int kUmmaK = 32;                                    // codes one tcgen05.mma of an 8-bit kind consumes
-constexpr int kGemmThreads = 192;
-constexpr int kTmemCols = kBN;                                // one 32-bit accumulator column per output column
+constexpr int kEpiWarps = 8;                                  // two per TMEM lane quarter (64 columns each)
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kTmemCols = 2 * kBN;                            // double-buffered accumulator, one 32-bit column per output column
+constexpr int kStgPitch = 36;                                 // floats per row of the epilogue's transpose buffer
+constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;
 constexpr int kBarBytes = 128;
-constexpr size_t kGemmSmem = 1024 + static_cast<size_t>(kStages) * kStageBytes + kBarBytes;
+constexpr size_t kGemmSmem = 1024 + static_cast<size_t>(kStages) * kStageBytes + kStgBytes + kBarBytes;
 constexpr long long kWatchdogCycles = 4000000000LL;           // ~2 s: a wedged pipeline traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -120,22 +123,117 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // out[m, n] = RN(RN(float(sum_k A[m,k] * B[n,k]) * alpha[n]) + beta[n])   (optionally max(., 0))
+//
+// Persistent: one CTA per SM walks the 128x128 output tiles (N tiles fastest, so the CTAs that share an A tile run
+// at the same time and the second read comes from L2).  Three decoupled pipelines:
+//   TMA producer  --full[s]/empty[s]-->  MMA thread  --acc_full[b]/acc_empty[b]-->  8 epilogue warps
+// The accumulator is double-buffered in TMEM (2 x 128 columns), so the epilogue of tile i overlaps the loads and
+// MMAs of tile i+1, and the operand ring keeps running across tile boundaries.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool IS_INT>
+__device__ __forceinline__ float acc_value(uint32_t v) {
+  return IS_INT ? static_cast<float>(static_cast<int>(v)) : __uint_as_float(v);
+}
+
+// One 32-row x 32-column piece of the tile: this lane holds row `lane` (32 accumulators); the piece is transposed
+// through a padded smem buffer (pitch 36 floats: 128-bit writes and reads are both conflict-free) so that global
+// stores are whole 128-byte lines.  MODE 0: scalar stores (any N, any alignment); 1: fp32, 16-byte stores
+// (N % 4 == 0); 2: bf16, 16-byte stores of 8 values (N % 8 == 0).
+template <bool IS_INT, int MODE>
+__device__ __forceinline__ void epilogue_piece(const uint32_t (&v)[32], float* stg, int lane, int row0, int col0, int M,
+                                               int N, const float* __restrict__ alpha, const float* __restrict__ beta,
+                                               void* __restrict__ out, int relu, int out_bf16) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * j) =
+        make_float4(acc_value<IS_INT>(v[4 * j]), acc_value<IS_INT>(v[4 * j + 1]), acc_value<IS_INT>(v[4 * j + 2]),
+                    acc_value<IS_INT>(v[4 * j + 3]));
+  __syncwarp();
+  if (MODE == 1) {
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4, col = col0 + c4;
+    if (col < N) {
+      float al[4], be[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { al[e] = __ldg(alpha + col + e); be[e] = __ldg(beta + col + e); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        if (row0 + r < M) {
+          const float4 t = *reinterpret_cast<const float4*>(stg + r * kStgPitch + c4);
+          float o[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[e] = __fadd_rn(__fmul_rn(o[e], al[e]), be[e]);
+            if (relu) o[e] = relu_ref(o[e]);
+          }
+          *reinterpret_cast<float4*>(static_cast<float*>(out) + static_cast<size_t>(row0 + r) * N + col) =
+              make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  } else if (MODE == 2) {
+    const int rsub = lane >> 2, c8 = (lane & 3) * 8, col = col0 + c8;
+    if (col < N) {
+      float al[8], be[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { al[e] = __ldg(alpha + col + e); be[e] = __ldg(beta + col + e); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + rsub;
+        if (row0 + r < M) {
+          const float4 t0 = *reinterpret_cast<const float4*>(stg + r * kStgPitch + c8);
+          const float4 t1 = *reinterpret_cast<const float4*>(stg + r * kStgPitch + c8 + 4);
+          float o[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            o[e] = __fadd_rn(__fmul_rn(o[e], al[e]), be[e]);
+            if (relu) o[e] = relu_ref(o[e]);
+          }
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(row0 + r) * N + col) =
+              Vec<__nv_bfloat16>::pack(o);
+        }
+      }
+    }
+  } else {
+    const int col = col0 + lane;
+    if (col < N) {
+      const float al = __ldg(alpha + col), be = __ldg(beta + col);
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        if (row0 + r >= M) break;
+        float o = __fadd_rn(__fmul_rn(stg[r * kStgPitch + lane], al), be);
+        if (relu) o = relu_ref(o);
+        const size_t idx = static_cast<size_t>(row0 + r) * static_cast<size_t>(N) + static_cast<size_t>(col);
+        if (out_bf16) static_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(o);
+        else static_cast<float*>(out)[idx] = o;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int KIND>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 qgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              const float* __restrict__ alpha, const float* __restrict__ beta, void* __restrict__ out, int M, int N,
-             int K, uint32_t idesc, int relu, int out_bf16) {
+             int K, uint32_t idesc, int relu, int out_bf16, int vec_ok) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // the swizzle atoms need 1024-byte alignment
   uint8_t* const tiles = smem_raw + (base - raw);
-  const uint32_t bars = base + kStages * kStageBytes;           // full[s] | empty[s] | accumulator-ready | TMEM slot
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tiles + kStages * kStageBytes + 8 * (2 * kStages + 1));
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_acc = bars + 16 * kStages;
+  float* const stg_all = reinterpret_cast<float*>(tiles + kStages * kStageBytes);
+  const uint32_t bars = base + kStages * kStageBytes + kStgBytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_acc_full = bars + 16 * kStages,
+                 bar_acc_empty = bar_acc_full + 16;
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(tiles + kStages * kStageBytes + kStgBytes + 16 * kStages + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;       // N tiles fastest: CTAs sharing an A tile run together
+  const int tiles_n = (N + kBN - 1) / kBN, tiles_m = (M + kBM - 1) / kBM;
+  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + kBK - 1) / kBK;
 
   if (threadIdx.x == 0) {
@@ -143,7 +241,10 @@ qgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_init(bar_full + 8 * s, 1);                           // one arrive.expect_tx by the producer
       mbar_init(bar_empty + 8 * s, 1);                          // one tcgen05.commit by the MMA thread
     }
-    mbar_init(bar_acc, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc_full + 8 * b, 1);                       // one tcgen05.commit per tile
+      mbar_init(bar_acc_empty + 8 * b, kEpiWarps * 32);         // every epilogue thread, once its TMEM reads are done
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -161,65 +262,74 @@ qgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);                   // slot free (passes at once in the first round)
-        mbar_expect_tx(bar_full + 8 * s, kStageBytes);          // a box always delivers its full byte count (OOB = 0)
-        const uint32_t dst = base + s * kStageBytes;
-        tma_load_2d(dst, &map_a, bar_full + 8 * s, kb * kBK, m0);
-        tma_load_2d(dst + kABytes, &map_b, bar_full + 8 * s, kb * kBK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);                 // slot free (passes at once in the first round)
+          mbar_expect_tx(bar_full + 8 * s, kStageBytes);        // a box always delivers its full byte count (OOB = 0)
+          const uint32_t dst = base + s * kStageBytes;
+          tma_load_2d(dst, &map_a, bar_full + 8 * s, kb * kBK, m0);
+          tma_load_2d(dst + kABytes, &map_b, bar_full + 8 * s, kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer: one thread drives the tensor core for the whole CTA =====
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t ab = ti & 1, aph = (ti >> 1) & 1;
+        mbar_wait(bar_acc_empty + 8 * ab, aph ^ 1);             // the epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a = base + s * kStageBytes, b = a + kABytes;
-        const int left = K - kb * kBK;                          // bytes of K beyond this block are zero-filled: skip them
-        const int steps = left >= kBK ? kBK / kUmmaK : (left + kUmmaK - 1) / kUmmaK;
-        for (int k = 0; k < steps; ++k)
-          umma<KIND>(tmem, umma_desc(a + k * kUmmaK), umma_desc(b + k * kUmmaK), idesc, (kb | k) != 0 ? 1u : 0u);
-        tc_commit(bar_empty + 8 * s);                           // the slot returns to the producer when these complete
+        const uint32_t d = tmem + ab * kBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a = base + s * kStageBytes, b = a + kABytes;
+          const int left = K - kb * kBK;                        // bytes of K beyond this block are zero-filled: skip them
+          const int steps = left >= kBK ? kBK / kUmmaK : (left + kUmmaK - 1) / kUmmaK;
+          for (int k = 0; k < steps; ++k)
+            umma<KIND>(d, umma_desc(a + k * kUmmaK), umma_desc(b + k * kUmmaK), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(bar_empty + 8 * s);                         // the slot returns to the producer when these complete
+        }
+        tc_commit(bar_acc_full + 8 * ab);                       // ... and this tile's accumulators are final
       }
-      tc_commit(bar_acc);                                       // ... and the accumulators are final
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced stores =====
+    // ===== epilogue: TMEM -> registers -> smem transpose -> 128-byte line stores =====
+    constexpr bool IS_INT = KIND == DLMCQ_QGEMM_I8;
+    const int ew = warp - 2;
     const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    // every operand stage has been consumed by now: stage 0 doubles as the transpose buffer (4 warps x 32 x 33 floats)
-    float* const stg = reinterpret_cast<float*>(tiles) + (warp - 2) * (32 * 33);
-    const int row0 = m0 + q * 32;
-    for (int c = 0; c < kBN / 32; ++c) {
-      const int col = n0 + c * 32 + lane;
-      if (n0 + c * 32 >= N) break;                              // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        stg[lane * 33 + j] = KIND == DLMCQ_QGEMM_I8 ? static_cast<float>(static_cast<int>(v[j])) : __uint_as_float(v[j]);
-      __syncwarp();
-      const bool col_ok = col < N;
-      const float al = col_ok ? __ldg(alpha + col) : 0.f;
-      const float be = col_ok ? __ldg(beta + col) : 0.f;
-      if (col_ok) {
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          if (row0 + r >= M) break;
-          float o = __fadd_rn(__fmul_rn(stg[r * 33 + lane], al), be);
-          if (relu) o = relu_ref(o);
-          const size_t idx = static_cast<size_t>(row0 + r) * static_cast<size_t>(N) + static_cast<size_t>(col);
-          if (out_bf16) static_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(o);
-          else static_cast<float*>(out)[idx] = o;
-        }
+    const int half = ew >> 2;                                   // which 64 of the tile's 128 columns
+    float* const stg = stg_all + ew * (32 * kStgPitch);
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+      const uint32_t ab = ti & 1, aph = (ti >> 1) & 1;
+      mbar_wait(bar_acc_full + 8 * ab, aph);
+      tc_fence_after();
+      const uint32_t t0 = tmem + ab * kBN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * 64);
+      const int col0 = n0 + half * 64;
+      const bool want0 = col0 < N, want1 = col0 + 32 < N;       // warp-uniform
+      uint32_t v0[32], v1[32];
+      if (want0) tmem_ld32(t0, v0);
+      if (want1) tmem_ld32(t0 + 32, v1);
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * ab);                      // registers hold the tile: the MMA thread may reuse it
+      const int row0 = m0 + q * 32;
+      if (vec_ok && !out_bf16) {
+        if (want0) epilogue_piece<IS_INT, 1>(v0, stg, lane, row0, col0, M, N, alpha, beta, out, relu, out_bf16);
+        if (want1) epilogue_piece<IS_INT, 1>(v1, stg, lane, row0, col0 + 32, M, N, alpha, beta, out, relu, out_bf16);
+      } else if (vec_ok) {
+        if (want0) epilogue_piece<IS_INT, 2>(v0, stg, lane, row0, col0, M, N, alpha, beta, out, relu, out_bf16);
+        if (want1) epilogue_piece<IS_INT, 2>(v1, stg, lane, row0, col0 + 32, M, N, alpha, beta, out, relu, out_bf16);
+      } else {
+        if (want0) epilogue_piece<IS_INT, 0>(v0, stg, lane, row0, col0, M, N, alpha, beta, out, relu, out_bf16);
+        if (want1) epilogue_piece<IS_INT, 0>(v1, stg, lane, row0, col0 + 32, M, N, alpha, beta, out, relu, out_bf16);
       }
-      __syncwarp();
     }
   }
   tc_fence_before();
@@ -447,9 +557,13 @@ int gemm_launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* alpha
     if (e != cudaSuccess) return set_cuda_error(e);
     if (dev >= 0 && dev < 64) opted_in[dev] = true;
   }
-  const dim3 grid(static_cast<unsigned>((n + kBN - 1) / kBN), static_cast<unsigned>((m + kBM - 1) / kBM));
+  const int64_t tiles = static_cast<int64_t>((n + kBN - 1) / kBN) * ((m + kBM - 1) / kBM);
+  const int sms = num_sms();
+  const unsigned grid = static_cast<unsigned>(tiles < sms ? tiles : sms);      // persistent: one CTA per SM
+  // 16-byte row stores need every row start aligned: N a multiple of 4 (fp32) / 8 (bf16) and an aligned base
+  const int vec_ok = aligned16(out) && (n % (out_bf16 ? 8 : 4) == 0);
   qgemm_kernel<KIND><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, alpha, beta, out, m, n, k,
-                                                            make_idesc(KIND, a_signed), relu, out_bf16);
+                                                            make_idesc(KIND, a_signed), relu, out_bf16, vec_ok);
   DLMCQ_LAUNCH_CHECK();
   return DLMCQ_OK;
 }
@@ -506,7 +620,7 @@ extern "C" int dlmcq_qgemm(const void* a_codes, const void* w_codes, const float
   // TMA: 16-byte aligned base addresses and row pitch; 32-bit tile coordinates
   if (!aligned16(a_codes) || !aligned16(w_codes)) return DLMCQ_EALIGN;
   if ((k & 15) != 0 || m > 0x7fffff00LL || n > 0x7fffff00LL || k > 0x7fffff00LL) return DLMCQ_EUNSUPPORTED;
-  if ((m + kBM - 1) / kBM > 65535) return DLMCQ_EUNSUPPORTED;
+  if (((m + kBM - 1) / kBM) * ((n + kBN - 1) / kBN) > 0x7fffffffLL) return DLMCQ_EUNSUPPORTED;
   CUtensorMap ma, mb;
   if (!make_map(&ma, a_codes, m, k, kBM) || !make_map(&mb, w_codes, n, k, kBN)) return DLMCQ_EUNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -234,7 +234,9 @@ def case_errors():
 def build_cases():
     cases = []
     raw_shapes = [(128, 128, 128), (256, 128, 512), (128, 256, 128), (100, 72, 64), (300, 200, 208), (1, 16, 16),
-                  (401, 1000, 2048), (4096, 64, 256), (129, 129, 144), (512, 512, 4096)]
+                  (401, 1000, 2048), (4096, 64, 256), (129, 129, 144), (512, 512, 4096),
+                  (128 * 150 + 7, 384, 96),          # 453 tiles: every persistent CTA walks several, both TMEM buffers reused
+                  (128 * 148 * 2, 128, 640)]         # exactly two tiles per CTA, the operand ring wraps inside a tile
     for enc in (I8, E4M3):
         tag = "i8" if enc == I8 else "e4m3"
         for (m, n, k) in raw_shapes:
@@ -242,6 +244,8 @@ def build_cases():
         cases.append((f"raw_{tag}_signed", case_raw_gemm, dict(m=200, n=136, k=320, encoding=enc, a_signed=True, a_hi=7)))
         cases.append((f"raw_{tag}_relu_bf16", case_raw_gemm, dict(m=257, n=96, k=128, encoding=enc, a_signed=False,
                                                                     relu=True, bf16=True)))
+        cases.append((f"raw_{tag}_bf16_scalar_stores", case_raw_gemm, dict(m=300, n=100, k=160, encoding=enc, a_signed=False,
+                                                                            bf16=True)))
         cases.append((f"raw_{tag}_relu", case_raw_gemm, dict(m=130, n=130, k=256, encoding=enc, a_signed=False, relu=True)))
     # 8-bit codes need the integer kind; K = 8192 keeps |acc| far beyond 2^24 so the s32 -> f32 rounding is exercised
     cases.append(("raw_i8_8bit", case_raw_gemm, dict(m=256, n=128, k=8192, encoding=I8, a_signed=False, a_hi=255, w_hi=127)))
