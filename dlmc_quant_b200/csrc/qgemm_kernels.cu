@@ -17,10 +17,11 @@
 //     it) or kind::f8f6f4 on codes stored as e4m3 bytes (exact for |code| <= 16, fp32 accumulators);
 //   * epilogue: tcgen05.ld (32x32b.x32) -> registers -> a padded smem transpose -> coalesced 128-byte row stores of
 //     out = RN(RN(acc * alpha[n]) + beta[n]) (+ ReLU), fp32 or bf16.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-9 = epilogue
-// (warp w may only touch TMEM lanes 32*(w%4) .. +31: two warps per lane quarter, 64 of the tile's 128 columns each).
-// Persistent, one CTA per SM (169 KB of smem, 256 TMEM columns = two accumulator buffers): the epilogue of one tile
-// overlaps the loads and MMAs of the next.  This path is bound by the bytes it moves (codes in, y out), not by the
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue, warps 2-17 = epilogue in
+// two groups of 8 (warp w may only touch TMEM lanes 32*(w%4) .. +31: two warps per lane quarter and group, 64 of the
+// tile's 128 columns each).  Persistent, one CTA per SM (206 KB of smem, 256 TMEM columns = two accumulator
+// buffers, one per epilogue group): while one group streams its tile out, the other reads the next accumulator and
+// the loads and MMAs of the tiles after that are already running.  This path is bound by the bytes it moves (codes in, y out), not by the
 // tensor pipe - the point of doing the product on codes is the 4x smaller operand.
 //
 // Also here: dlmcq_codes_forward (x -> one byte per code, the same arithmetic as dlmcq_fq_forward, streaming) and
@@ -37,7 +38,8 @@ constexpr int kBM = 128, kBN = 128, kBK = 128;                // tile; kBK bytes
 constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK, kBBytes = kBN * kBK, kStageBytes = kABytes + kBBytes;
 constexpr int kUmmaK = 32;                                    // codes one tcgen05.mma of an 8-bit kind consumes
-constexpr int kEpiWarps = 8;                                  // two per TMEM lane quarter (64 columns each)
+constexpr int kEpiWarps = 16;                                 // two groups of 8 (two per TMEM lane quarter, 64 columns each)
+constexpr int kEpiGroupWarps = kEpiWarps / 2;                 // group g drains accumulator buffer g: even / odd tiles
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 2 * kBN;                            // double-buffered accumulator, one 32-bit column per output column
 constexpr int kStgPitch = 36;                                 // floats per row of the epilogue's transpose buffer
@@ -139,85 +141,144 @@ __device__ __forceinline__ float acc_value(uint32_t v) {
   return IS_INT ? static_cast<float>(static_cast<int>(v)) : __uint_as_float(v);
 }
 
+// Per-column epilogue constants of one 32-column piece, fetched BEFORE the warp waits for the accumulator (their
+// latency hides behind the wait).  MODE 0: one column per lane; 1: four (fp32 line stores); 2: eight (bf16).
+template <int MODE>
+struct EpiConst {
+  static constexpr int W = MODE == 0 ? 1 : (MODE == 1 ? 4 : 8);
+  float al[W], be[W];
+  __device__ __forceinline__ void load(const float* __restrict__ alpha, const float* __restrict__ beta, int col0, int lane,
+                                       int N) {
+    const int col = col0 + (MODE == 0 ? lane : (MODE == 1 ? (lane & 7) * 4 : (lane & 3) * 8));
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const bool ok = col + e < N;
+      al[e] = ok ? __ldg(alpha + col + e) : 0.f;
+      be[e] = ok ? __ldg(beta + col + e) : 0.f;
+    }
+  }
+};
+
 // One 32-row x 32-column piece of the tile: this lane holds row `lane` (32 accumulators); the piece is transposed
 // through a padded smem buffer (pitch 36 floats: 128-bit writes and reads are both conflict-free) so that global
 // stores are whole 128-byte lines.  MODE 0: scalar stores (any N, any alignment); 1: fp32, 16-byte stores
-// (N % 4 == 0); 2: bf16, 16-byte stores of 8 values (N % 8 == 0).
+// (N % 4 == 0); 2: bf16, 16-byte stores of 8 values (N % 8 == 0).  All smem reads are issued before the first
+// store; `floor` is 0 for a fused ReLU and -inf otherwise (max.NaN: NaN propagates, -0 -> +0, like torch.relu).
 template <bool IS_INT, int MODE>
 __device__ __forceinline__ void epilogue_piece(const uint32_t (&v)[32], float* stg, int lane, int row0, int col0, int M,
-                                               int N, const float* __restrict__ alpha, const float* __restrict__ beta,
-                                               void* __restrict__ out, int relu, int out_bf16) {
+                                               int N, const EpiConst<MODE>& k, void* __restrict__ out, float floor,
+                                               int out_bf16) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(stg + lane * kStgPitch + 4 * j) =
         make_float4(acc_value<IS_INT>(v[4 * j]), acc_value<IS_INT>(v[4 * j + 1]), acc_value<IS_INT>(v[4 * j + 2]),
                     acc_value<IS_INT>(v[4 * j + 3]));
   __syncwarp();
+  const int rows = M - row0;                                    // >= 1; the common case is a full piece (>= 32)
   if (MODE == 1) {
     const int rsub = lane >> 3, c4 = (lane & 7) * 4, col = col0 + c4;
     if (col < N) {
-      float al[4], be[4];
+      float* p = static_cast<float*>(out) + static_cast<size_t>(row0 + rsub) * N + col;
+      const size_t step = static_cast<size_t>(4) * N;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { al[e] = __ldg(alpha + col + e); be[e] = __ldg(beta + col + e); }
+      for (int h = 0; h < 2; ++h) {                             // two batches of four rows: 4 smem reads in flight, 16 live registers
+        float4 t[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + rsub;
-        if (row0 + r < M) {
-          const float4 t = *reinterpret_cast<const float4*>(stg + r * kStgPitch + c4);
-          float o[4] = {t.x, t.y, t.z, t.w};
+        for (int i = 0; i < 4; ++i) t[i] = *reinterpret_cast<const float4*>(stg + ((h * 4 + i) * 4 + rsub) * kStgPitch + c4);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            o[e] = __fadd_rn(__fmul_rn(o[e], al[e]), be[e]);
-            if (relu) o[e] = relu_ref(o[e]);
-          }
-          *reinterpret_cast<float4*>(static_cast<float*>(out) + static_cast<size_t>(row0 + r) * N + col) =
-              make_float4(o[0], o[1], o[2], o[3]);
+        for (int i = 0; i < 4; ++i) {
+          float4 o;
+          o.x = max_nan(__fadd_rn(__fmul_rn(t[i].x, k.al[0]), k.be[0]), floor);
+          o.y = max_nan(__fadd_rn(__fmul_rn(t[i].y, k.al[1]), k.be[1]), floor);
+          o.z = max_nan(__fadd_rn(__fmul_rn(t[i].z, k.al[2]), k.be[2]), floor);
+          o.w = max_nan(__fadd_rn(__fmul_rn(t[i].w, k.al[3]), k.be[3]), floor);
+          if ((h * 4 + i) * 4 + rsub < rows) *reinterpret_cast<float4*>(p + (h * 4 + i) * step) = o;
         }
       }
     }
+    __syncwarp();
   } else if (MODE == 2) {
     const int rsub = lane >> 2, c8 = (lane & 3) * 8, col = col0 + c8;
     if (col < N) {
-      float al[8], be[8];
+      __nv_bfloat16* p = static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(row0 + rsub) * N + col;
+      const size_t step = static_cast<size_t>(8) * N;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { al[e] = __ldg(alpha + col + e); be[e] = __ldg(beta + col + e); }
+      for (int h = 0; h < 2; ++h) {
+        float4 t[2][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = i * 8 + rsub;
-        if (row0 + r < M) {
-          const float4 t0 = *reinterpret_cast<const float4*>(stg + r * kStgPitch + c8);
-          const float4 t1 = *reinterpret_cast<const float4*>(stg + r * kStgPitch + c8 + 4);
-          float o[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        for (int i = 0; i < 2; ++i) {
+          t[i][0] = *reinterpret_cast<const float4*>(stg + ((h * 2 + i) * 8 + rsub) * kStgPitch + c8);
+          t[i][1] = *reinterpret_cast<const float4*>(stg + ((h * 2 + i) * 8 + rsub) * kStgPitch + c8 + 4);
+        }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            o[e] = __fadd_rn(__fmul_rn(o[e], al[e]), be[e]);
-            if (relu) o[e] = relu_ref(o[e]);
-          }
-          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + static_cast<size_t>(row0 + r) * N + col) =
-              Vec<__nv_bfloat16>::pack(o);
+        for (int i = 0; i < 2; ++i) {
+          float o[8] = {t[i][0].x, t[i][0].y, t[i][0].z, t[i][0].w, t[i][1].x, t[i][1].y, t[i][1].z, t[i][1].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = max_nan(__fadd_rn(__fmul_rn(o[e], k.al[e]), k.be[e]), floor);
+          if ((h * 2 + i) * 8 + rsub < rows) *reinterpret_cast<uint4*>(p + (h * 2 + i) * step) = Vec<__nv_bfloat16>::pack(o);
         }
       }
     }
+    __syncwarp();
   } else {
     const int col = col0 + lane;
     if (col < N) {
-      const float al = __ldg(alpha + col), be = __ldg(beta + col);
-#pragma unroll 4
-      for (int r = 0; r < 32; ++r) {
-        if (row0 + r >= M) break;
-        float o = __fadd_rn(__fmul_rn(stg[r * kStgPitch + lane], al), be);
-        if (relu) o = relu_ref(o);
+      const int nr = rows < 32 ? rows : 32;
+      for (int r = 0; r < nr; ++r) {
+        const float o = max_nan(__fadd_rn(__fmul_rn(stg[r * kStgPitch + lane], k.al[0]), k.be[0]), floor);
         const size_t idx = static_cast<size_t>(row0 + r) * static_cast<size_t>(N) + static_cast<size_t>(col);
         if (out_bf16) static_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(o);
         else static_cast<float*>(out)[idx] = o;
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
+}
+
+// The tile loop of one epilogue warp.  The 16 epilogue warps form two groups: group g owns accumulator buffer g,
+// i.e. the CTA's even / odd tiles, so while one group streams its tile to global memory the other one is already
+// waiting for / reading the next accumulator - the store pipe never idles behind a barrier round trip (timeline:
+// profiles/r02_qgemm_timeline_probe.log).  Inside a group a warp owns TMEM lane quarter q and 64 columns (two
+// 32-column pieces, read one at a time: 32 live accumulator registers).  The buffer is handed back to the MMA thread
+// by ONE arrival per warp, right after the warp's last TMEM read.
+template <bool IS_INT, int MODE>
+__device__ __forceinline__ void epilogue_loop(uint32_t tmem, uint32_t bar_acc_full, uint32_t bar_acc_empty, float* stg,
+                                              int lane, int q, int grp, int chalf, int num_tiles, int tiles_n, int M,
+                                              int N, const float* __restrict__ alpha, const float* __restrict__ beta,
+                                              void* __restrict__ out, float floor, int out_bf16) {
+  const uint32_t full = bar_acc_full + 8 * grp, empty = bar_acc_empty + 8 * grp;
+  const uint32_t tbase = tmem + grp * kBN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(chalf * 64);
+  uint32_t ti = grp;
+  for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, ti += 2) {
+    const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
+    const int col0 = n0 + chalf * 64, row0 = m0 + q * 32;
+    const bool has0 = col0 < N, has1 = col0 + 32 < N;            // warp-uniform
+    EpiConst<MODE> k0;
+    k0.load(alpha, beta, col0, lane, N);
+    mbar_wait(full, (ti >> 1) & 1);
+    tc_fence_after();
+    uint32_t v[32];
+    if (has0) tmem_ld32(tbase, v);
+    if (!has1) {                                                // nothing more to read from this buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty);
+    }
+    if (has0 && row0 < M) epilogue_piece<IS_INT, MODE>(v, stg, lane, row0, col0, M, N, k0, out, floor, out_bf16);
+    if (has1) {
+      EpiConst<MODE> k1;                                        // L1-resident by now; fetched here to keep registers free
+      k1.load(alpha, beta, col0 + 32, lane, N);
+      tmem_ld32(tbase + 32, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty);
+      if (row0 < M) epilogue_piece<IS_INT, MODE>(v, stg, lane, row0, col0 + 32, M, N, k1, out, floor, out_bf16);
+    }
+  }
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)   // 576 threads: ptxas caps the kernel at 96 registers
 qgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              const float* __restrict__ alpha, const float* __restrict__ beta, void* __restrict__ out, int M, int N,
              int K, uint32_t idesc, int relu, int out_bf16, int vec_ok) {
@@ -243,7 +304,7 @@ qgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full + 8 * b, 1);                       // one tcgen05.commit per tile
-      mbar_init(bar_acc_empty + 8 * b, kEpiWarps * 32);         // every epilogue thread, once its TMEM reads are done
+      mbar_init(bar_acc_empty + 8 * b, kEpiGroupWarps);         // one arrival per warp of the group that drains buffer b
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -303,34 +364,19 @@ qgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     constexpr bool IS_INT = KIND == DLMCQ_QGEMM_I8;
     const int ew = warp - 2;
     const int q = warp & 3;                                     // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                                   // which 64 of the tile's 128 columns
+    const int grp = ew >> 3;                                    // accumulator buffer / tile parity this warp serves
+    const int chalf = (ew >> 2) & 1;                            // which 64 of the tile's 128 columns
     float* const stg = stg_all + ew * (32 * kStgPitch);
-    uint32_t ti = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * kBN;
-      const uint32_t ab = ti & 1, aph = (ti >> 1) & 1;
-      mbar_wait(bar_acc_full + 8 * ab, aph);
-      tc_fence_after();
-      const uint32_t t0 = tmem + ab * kBN + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * 64);
-      const int col0 = n0 + half * 64;
-      const bool want0 = col0 < N, want1 = col0 + 32 < N;       // warp-uniform
-      uint32_t v0[32], v1[32];
-      if (want0) tmem_ld32(t0, v0);
-      if (want1) tmem_ld32(t0 + 32, v1);
-      tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * ab);                      // registers hold the tile: the MMA thread may reuse it
-      const int row0 = m0 + q * 32;
-      if (vec_ok && !out_bf16) {
-        if (want0) epilogue_piece<IS_INT, 1>(v0, stg, lane, row0, col0, M, N, alpha, beta, out, relu, out_bf16);
-        if (want1) epilogue_piece<IS_INT, 1>(v1, stg, lane, row0, col0 + 32, M, N, alpha, beta, out, relu, out_bf16);
-      } else if (vec_ok) {
-        if (want0) epilogue_piece<IS_INT, 2>(v0, stg, lane, row0, col0, M, N, alpha, beta, out, relu, out_bf16);
-        if (want1) epilogue_piece<IS_INT, 2>(v1, stg, lane, row0, col0 + 32, M, N, alpha, beta, out, relu, out_bf16);
-      } else {
-        if (want0) epilogue_piece<IS_INT, 0>(v0, stg, lane, row0, col0, M, N, alpha, beta, out, relu, out_bf16);
-        if (want1) epilogue_piece<IS_INT, 0>(v1, stg, lane, row0, col0 + 32, M, N, alpha, beta, out, relu, out_bf16);
-      }
-    }
+    const float floor = relu ? 0.f : __int_as_float(0xff800000);
+    if (vec_ok && !out_bf16)
+      epilogue_loop<IS_INT, 1>(tmem, bar_acc_full, bar_acc_empty, stg, lane, q, grp, chalf, num_tiles, tiles_n, M, N,
+                               alpha, beta, out, floor, out_bf16);
+    else if (vec_ok)
+      epilogue_loop<IS_INT, 2>(tmem, bar_acc_full, bar_acc_empty, stg, lane, q, grp, chalf, num_tiles, tiles_n, M, N,
+                               alpha, beta, out, floor, out_bf16);
+    else
+      epilogue_loop<IS_INT, 0>(tmem, bar_acc_full, bar_acc_empty, stg, lane, q, grp, chalf, num_tiles, tiles_n, M, N,
+                               alpha, beta, out, floor, out_bf16);
   }
   tc_fence_before();
   __syncthreads();

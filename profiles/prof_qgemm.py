@@ -94,6 +94,19 @@ def run(batch, hw, cin, cout, encoding, check):
 def main():
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     encs = [Q.QGEMM_I8] + ([Q.QGEMM_E4M3] if "--e4m3" in sys.argv else [])
+    if "--shape" in sys.argv:                       # one shape only, few calls: the command profiled under ncu
+        hw, cin, cout = SHAPES[int(sys.argv[sys.argv.index("--shape") + 1])]
+        dev = torch.device("cuda")
+        m = batch * hw * hw
+        a = torch.randint(0, 16, (m, cin), device=dev, dtype=torch.uint8)
+        w = torch.randint(-7, 8, (cout, cin), device=dev, dtype=torch.int8).view(torch.uint8)
+        al, be = torch.full((cout,), 1e-3, device=dev), torch.zeros(cout, device=dev)
+        out = torch.empty(m, cout, device=dev)
+        for _ in range(3):
+            Q.qgemm(a, w, al, be, out=out)
+        torch.cuda.synchronize()
+        print(json.dumps({"shape": [m, cin, cout], "us": timeit(lambda: Q.qgemm(a, w, al, be, out=out), 10, 2)}))
+        return
     print(json.dumps({"device": torch.cuda.get_device_name(0), "copy_peak_gbs": PEAK, "batch": batch}))
     for enc in encs:
         for hw, cin, cout in SHAPES:
