@@ -286,6 +286,7 @@ def run_ours(args, rank, world, device):
     del wl
     torch.cuda.empty_cache()
     qat = run_qat(args, rank, world, device)
+    code_gemm = run_code_gemm(args, device) if (rank == 0 and world == 1) else None
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -298,7 +299,7 @@ def run_ours(args, rank, world, device):
            "elements_per_s": round(total_elems / (ms * 1e-3), 1),
            "images_per_s_quantizer_path": round(args.batch * world * args.steps / (ms * 1e-3), 1),
            "gpu_launches": launches_total, "roofline": roofline, "clocks": clocks, "e2e": e2e,
-           "qat_images_per_s": qat}
+           "qat_images_per_s": qat, "code_gemm": code_gemm}
     if rank == 0:
         out["cpu_baseline"] = cpu_reference(sample_batch=1, passes=3) if world == 1 else None
         print(json.dumps(out), flush=True)
@@ -548,6 +549,83 @@ def _qat_arm(arm, channels_last, batch, steps, rank, world, device, graphed=Fals
     del model, opt
     torch.cuda.empty_cache()
     return out
+
+
+# torchvision ResNet-50's stride-1 1x1 convolutions: (H = W, Cin, Cout, how many layers have this shape)
+R50_POINTWISE = [(56, 64, 64, 1), (56, 64, 256, 4), (56, 256, 64, 2), (56, 256, 128, 1), (28, 128, 512, 4),
+                 (28, 512, 128, 3), (28, 512, 256, 1), (14, 256, 1024, 6), (14, 1024, 256, 5), (14, 1024, 512, 1),
+                 (7, 512, 2048, 3), (7, 2048, 512, 2)]
+
+
+def _event_us(fn, iters=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / iters * 1e3
+
+
+def run_code_gemm(args, device):
+    """Consumer side of row f2 (dlmc_quant_b200.qgemm, csrc/qgemm_kernels.cu): the 1x1 convolutions of ResNet-50 as
+    integer-code GEMMs on the tcgen05 tensor cores (W4A4 codes, one byte each, channels-last) beside the reference's
+    path for the same layers - cuDNN convolution of the fake-quantised fp32 tensor (TF32, torch's default).
+    Per shape: CUDA-event time of 20 calls after 5 warm-ups; totals weight each shape by its layer count."""
+    if args.no_qat:
+        return None
+    from dlmc_quant_b200 import qgemm as Q
+    res = {"workload": "torchvision resnet50 stride-1 1x1 convolutions, batch %d, channels_last, W4A4 codes" % args.batch,
+           "kernel": "TMA -> tcgen05.mma kind::f8f6f4 on e4m3-encoded codes (bit-identical to kind::i8) -> TMEM -> "
+                     "alpha[n]*acc + beta[n] epilogue", "shapes": [], "timing": "CUDA events, 20 calls after 5 warm-ups"}
+    tot = {"ours_f32_us": 0.0, "ours_bf16_us": 0.0, "cudnn_tf32_us": 0.0, "ours_bytes_f32": 0, "cudnn_bytes": 0}
+    worst = 0.0
+    try:
+        for hw, cin, cout, count in R50_POINTWISE:
+            m, k, n = args.batch * hw * hw, cin, cout
+            g = torch.Generator(device="cuda").manual_seed(hw * 1000 + cin)
+            ca = torch.randint(0, 16, (m, k), device=device, generator=g, dtype=torch.uint8)
+            cw = torch.randint(-7, 8, (n, k), device=device, generator=g, dtype=torch.int8)
+            a_b = ca.float().to(torch.float8_e4m3fn).view(torch.uint8)
+            w_b = cw.float().to(torch.float8_e4m3fn).view(torch.uint8)
+            s_a, s_w = 0.11, torch.rand(n, device=device, generator=g) * 0.01 + 0.002
+            alpha, beta = (s_a * s_w).float(), torch.zeros(n, device=device)
+            o32 = torch.empty(m, n, device=device)
+            o16 = torch.empty(m, n, device=device, dtype=torch.bfloat16)
+            x = (ca.float() * s_a).view(args.batch, hw, hw, k).permute(0, 3, 1, 2)     # NCHW view, channels-last storage
+            w = (cw.float() * s_w[:, None]).view(n, k, 1, 1).contiguous(memory_format=torch.channels_last)
+            t32 = _event_us(lambda: Q.qgemm(a_b, w_b, alpha, beta, encoding=Q.QGEMM_E4M3, out=o32))
+            t16 = _event_us(lambda: Q.qgemm(a_b, w_b, alpha, beta, encoding=Q.QGEMM_E4M3, out=o16,
+                                            out_dtype=torch.bfloat16))
+            torch.backends.cudnn.allow_tf32 = True
+            tc = _event_us(lambda: torch.nn.functional.conv2d(x, w))
+            torch.backends.cudnn.allow_tf32 = False
+            ref = torch.nn.functional.conv2d(x, w).permute(0, 2, 3, 1).reshape(m, n)
+            torch.backends.cudnn.allow_tf32 = True
+            err = float(((o32 - ref).abs() / ((15 * s_a) * (7 * s_w) * k)).max())
+            worst = max(worst, err)
+            by = m * k + n * k + m * n * 4
+            res["shapes"].append({"m": m, "k": k, "n": n, "layers": count, "ours_f32_us": round(t32, 2),
+                                  "ours_bf16_us": round(t16, 2), "cudnn_tf32_us": round(tc, 2),
+                                  "ours_f32_gbs": round(by / t32 * 1e-3, 1)})
+            tot["ours_f32_us"] += count * t32
+            tot["ours_bf16_us"] += count * t16
+            tot["cudnn_tf32_us"] += count * tc
+            tot["ours_bytes_f32"] += count * by
+            tot["cudnn_bytes"] += count * (m * k * 4 + n * k * 4 + m * n * 4)
+            del ca, cw, a_b, w_b, o32, o16, x, w, ref
+            torch.cuda.empty_cache()
+        res["total"] = {k_: (round(v, 1) if isinstance(v, float) else v) for k_, v in tot.items()}
+        res["speedup_vs_cudnn_tf32"] = {"f32_out": round(tot["cudnn_tf32_us"] / tot["ours_f32_us"], 3),
+                                        "bf16_out": round(tot["cudnn_tf32_us"] / tot["ours_bf16_us"], 3)}
+        res["max_err_vs_strict_fp32_cudnn_over_sum_abs_bound"] = worst
+        res["parity_ok"] = worst <= 1e-5
+    except Exception as e:                              # must not take the headline metric down
+        res["error"] = f"{type(e).__name__}: {e}"[:300]
+    return res
 
 
 def run_qat(args, rank, world, device):

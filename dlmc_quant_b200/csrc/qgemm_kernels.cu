@@ -192,7 +192,7 @@ __device__ __forceinline__ void epilogue_piece(const uint32_t (&v)[32], float* s
           o.y = max_nan(__fadd_rn(__fmul_rn(t[i].y, k.al[1]), k.be[1]), floor);
           o.z = max_nan(__fadd_rn(__fmul_rn(t[i].z, k.al[2]), k.be[2]), floor);
           o.w = max_nan(__fadd_rn(__fmul_rn(t[i].w, k.al[3]), k.be[3]), floor);
-          if ((h * 4 + i) * 4 + rsub < rows) *reinterpret_cast<float4*>(p + (h * 4 + i) * step) = o;
+          if ((h * 4 + i) * 4 + rsub < rows) st_stream(reinterpret_cast<float4*>(p + (h * 4 + i) * step), o);
         }
       }
     }
@@ -215,7 +215,7 @@ __device__ __forceinline__ void epilogue_piece(const uint32_t (&v)[32], float* s
           float o[8] = {t[i][0].x, t[i][0].y, t[i][0].z, t[i][0].w, t[i][1].x, t[i][1].y, t[i][1].z, t[i][1].w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = max_nan(__fadd_rn(__fmul_rn(o[e], k.al[e]), k.be[e]), floor);
-          if ((h * 2 + i) * 8 + rsub < rows) *reinterpret_cast<uint4*>(p + (h * 2 + i) * step) = Vec<__nv_bfloat16>::pack(o);
+          if ((h * 2 + i) * 8 + rsub < rows) st_stream(reinterpret_cast<uint4*>(p + (h * 2 + i) * step), Vec<__nv_bfloat16>::pack(o));
         }
       }
     }

@@ -238,8 +238,17 @@ def _code_forward(self, input):
     return out.view(*input.shape[:-1], n)
 
 
-def enable_code_gemm(model, encoding=QGEMM_I8):
-    """Route every eligible quantised Linear / 1x1 Conv2d of `model` through the integer-code GEMM in eval mode.
+def _auto_encoding(mod):
+    """e4m3 operands (fp32 accumulators: no int -> float conversion in the epilogue) when every code of the layer is
+    exactly representable (|code| <= 16, i.e. up to 4-bit unsigned / 5-bit signed ranges), the integer kind otherwise.
+    Both are bit-identical where both apply (tests/qgemm_cases.py)."""
+    small = mod.wt_min_val >= -16 and mod.wt_max_val <= 16 and mod.in_min_val >= -16 and mod.in_max_val <= 16
+    return QGEMM_E4M3 if small else QGEMM_I8
+
+
+def enable_code_gemm(model, encoding=None):
+    """Route every eligible quantised Linear / 1x1 Conv2d of `model` through the integer-code GEMM in eval mode
+    (`encoding`: QGEMM_I8, QGEMM_E4M3, or None = per layer by code range).
     Returns the list of module names switched.  Eligibility that depends on calibrated state (per-tensor activation
     scale, zero weight offset, ...) is re-checked lazily and a layer that fails it silently keeps its original path."""
     names = []
@@ -247,7 +256,7 @@ def enable_code_gemm(model, encoding=QGEMM_I8):
         forms = _family(mod)
         if forms is None or not _geometry_ok(mod) or '_code_gemm' in mod.__dict__:
             continue
-        mod.__dict__['_code_gemm'] = _CodeGemmState(encoding)
+        mod.__dict__['_code_gemm'] = _CodeGemmState(_auto_encoding(mod) if encoding is None else encoding)
         mod.__dict__['_code_gemm_forms'] = forms
         mod.__dict__['_code_gemm_orig_forward'] = mod.forward
         mod.forward = types.MethodType(_code_forward, mod)

@@ -265,6 +265,7 @@ def build_cases():
         tag = "i8" if enc == I8 else "e4m3"
         cases.append((f"module_{tag}_conv_qbase", case_module, dict(kind="conv", family="qbase", encoding=enc)))
         cases.append((f"module_{tag}_linear_qbase", case_module, dict(kind="linear", family="qbase", encoding=enc)))
+    cases.append(("module_auto_encoding_conv_qbase", case_module, dict(kind="conv", family="qbase", encoding=None)))
     cases.append(("module_i8_conv_fsptq_8bit", case_module, dict(kind="conv", family="fsptq", encoding=I8)))
     cases.append(("module_i8_linear_fsptq_8bit", case_module, dict(kind="linear", family="fsptq", encoding=I8)))
     cases.append(("module_i8_conv_nchw_qbase", case_module, dict(kind="conv", family="qbase", encoding=I8, channels_last=False)))
