@@ -287,6 +287,7 @@ def run_ours(args, rank, world, device):
     torch.cuda.empty_cache()
     qat = run_qat(args, rank, world, device)
     code_gemm = run_code_gemm(args, device) if (rank == 0 and world == 1) else None
+    inference = run_inference(args, device) if (rank == 0 and world == 1) else None
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -299,7 +300,8 @@ def run_ours(args, rank, world, device):
            "elements_per_s": round(total_elems / (ms * 1e-3), 1),
            "images_per_s_quantizer_path": round(args.batch * world * args.steps / (ms * 1e-3), 1),
            "gpu_launches": launches_total, "roofline": roofline, "clocks": clocks, "e2e": e2e,
-           "qat_images_per_s": qat, "code_gemm": code_gemm}
+           "qat_images_per_s": qat, "code_gemm": code_gemm,
+           "inference_images_per_s": inference}
     if rank == 0:
         out["cpu_baseline"] = cpu_reference(sample_batch=1, passes=3) if world == 1 else None
         print(json.dumps(out), flush=True)
@@ -625,6 +627,59 @@ def run_code_gemm(args, device):
         res["parity_ok"] = worst <= 1e-5
     except Exception as e:                              # must not take the headline metric down
         res["error"] = f"{type(e).__name__}: {e}"[:300]
+    return res
+
+
+def run_inference(args, device):
+    """ResNet-50 W4A4 inference (eval, no autograd, channels_last, synthetic batch) through the public module API:
+    un-quantised, quantize_model (fake-quant kernels + cuDNN on fp32), and the same model after
+    qgemm.enable_code_gemm (every stride-1 1x1 convolution and the classifier as an integer-code GEMM)."""
+    if args.no_qat:
+        return None
+    import copy
+    import torchvision
+    res = {"model": "torchvision resnet50 W4A4 (QBase, minmax observers), eval / no_grad, channels_last, batch %d, fp32 "
+                    "tensors (cuDNN TF32 convolutions: torch default)" % args.qat_batch,
+           "timing": "CUDA events, %d forwards after 3 warm-ups" % args.qat_steps}
+    try:
+        x = torch.randn(args.qat_batch, 3, 224, 224, device=device).contiguous(memory_format=torch.channels_last)
+        outs = {}
+        for arm in ("fp32", "ours", "ours_code_gemm"):
+            torch.manual_seed(2333)
+            model = torchvision.models.resnet50().to(device).to(memory_format=torch.channels_last)
+            if arm != "fp32":
+                from dlmc_quant_b200 import quantize_model
+                quantize_model(model, copy.deepcopy(QAT_CFG), None)
+            model.eval()
+            switched = None
+            with torch.no_grad():
+                model(x[:8])                                 # lazy observer initialisation
+                if arm == "ours_code_gemm":
+                    from dlmc_quant_b200.qgemm import enable_code_gemm
+                    switched = len(enable_code_gemm(model))
+                for _ in range(3):
+                    y = model(x)
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(args.qat_steps):
+                    y = model(x)
+                t1.record()
+                torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / args.qat_steps
+            outs[arm] = y.float()
+            res[arm] = {"images_per_s": round(args.qat_batch / ms * 1e3, 1), "ms_per_forward": round(ms, 3)}
+            if switched is not None:
+                res[arm]["layers_on_code_gemm"] = switched
+                used = sum(1 for m_ in model.modules() if getattr(m_.__dict__.get("_code_gemm"), "usable", False))
+                res[arm]["layers_that_used_it"] = used
+            del model
+            torch.cuda.empty_cache()
+        d = (outs["ours_code_gemm"] - outs["ours"]).abs().max() / outs["ours"].abs().max().clamp_min(1e-30)
+        res["logits_max_diff_code_gemm_vs_ours_rel"] = float(d)
+    except Exception as e:                              # must not take the headline metric down
+        res["error"] = f"{type(e).__name__}: {e}"[:300]
+        torch.cuda.empty_cache()
     return res
 
 
