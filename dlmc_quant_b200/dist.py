@@ -3,7 +3,7 @@ torch.distributed collectives (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
 Activations shard by batch and weights are replicated, so the fake-quant kernels themselves need no
 collective.  What must agree across ranks is O(channels) data:
-  * observer statistics  - [C,4] = (min, max, max|x|, sum|x|): MIN / MAX / SUM all-reduces,
+  * observer statistics  - [C,4] = (min, max, max|x|, sum|x|): one all-gather of the blocks, folded locally,
   * sweep partial sums   - 80 squared-error sums per tensor: SUM,
   * scale gradients      - one flat buffer per step: SUM (DDP averages parameter grads itself),
   * per-channel WEIGHT observers (replicated weights, e.g. the 80-candidate sweep): each rank computes the
@@ -31,21 +31,20 @@ def world_size(group=None):
 
 def sync_stats(stats, group=None):
     """stats [C,4] = (min, max, absmax, abssum) -> the statistics of the union of all ranks' tensors.
-    NaN statistics (NaN inputs) stay NaN: MIN/MAX of NaN is handled by reducing a flag with the sum."""
-    if world_size(group) == 1:
+    ONE collective and no host synchronisation: the [C,4] blocks are all-gathered and folded locally (amin / amax /
+    sum over the rank axis, in rank order - deterministic).  NaN statistics (NaN inputs) stay NaN: torch's amin / amax
+    / sum propagate NaN, and a rank that saw a NaN reports NaN in all four columns (the statistics kernels do)."""
+    w = world_size(group)
+    if w == 1:
         return stats
-    s = stats.clone()
-    lo = s[:, 0].contiguous()
-    hi = s[:, 1:3].contiguous()
-    sm = s[:, 3].contiguous()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=group)      # NaN on any rank -> NaN everywhere
-    nan = torch.isnan(sm)
-    out = torch.stack([lo, hi[:, 0], hi[:, 1], sm], dim=1)
-    if bool(nan.any()):
-        out[nan, :3] = float("nan")
-    return out
+    mine = stats.contiguous()
+    parts = [torch.empty_like(mine) for _ in range(w)]
+    dist.all_gather(parts, mine, group=group)
+    allr = torch.stack(parts, dim=0)                              # [world, C, 4]
+    sm = allr[..., 3].sum(dim=0)
+    out = torch.stack([allr[..., 0].amin(dim=0), allr[..., 1].amax(dim=0), allr[..., 2].amax(dim=0), sm], dim=1)
+    # a NaN anywhere in a channel poisons its min / max / absmax too (what one pass over the union would give)
+    return torch.where(torch.isnan(sm).unsqueeze(1), torch.full_like(out, float("nan")), out)
 
 
 def sync_sse(sse, rows, group=None):
