@@ -668,6 +668,12 @@ def run_inference(args, device):
                 torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / args.qat_steps
             outs[arm] = y.float()
+            if arm != "fp32":                                # the same model with strict-fp32 library convolutions
+                torch.backends.cudnn.allow_tf32 = False      # (ours_code_gemm: its 3x3 / strided layers)
+                torch.backends.cuda.matmul.allow_tf32 = False
+                with torch.no_grad():
+                    outs[arm + "_strict_fp32"] = model(x).float()
+                torch.backends.cudnn.allow_tf32 = True
             res[arm] = {"images_per_s": round(args.qat_batch / ms * 1e3, 1), "ms_per_forward": round(ms, 3)}
             if switched is not None:
                 res[arm]["layers_on_code_gemm"] = switched
@@ -675,8 +681,20 @@ def run_inference(args, device):
                 res[arm]["layers_that_used_it"] = used
             del model
             torch.cuda.empty_cache()
-        d = (outs["ours_code_gemm"] - outs["ours"]).abs().max() / outs["ours"].abs().max().clamp_min(1e-30)
-        res["logits_max_diff_code_gemm_vs_ours_rel"] = float(d)
+        # 4-bit activations: a relative error of 1e-3 in a convolution (TF32) flips codes downstream, each flip is 1/15
+        # of a layer's range, and an untrained 50-layer network amplifies that - so the yardstick is the model with
+        # strict-fp32 library convolutions, and how far the TF32 default itself is from it.  Layer-by-layer parity of
+        # the code path (same inputs, 2e-5) is a GPU test: tests/qgemm_cases.py::case_resnet_layers.
+        ref = outs["ours_strict_fp32"]
+        rel = lambda a: float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30))  # noqa: E731
+        top = lambda a: float((a.argmax(1) == ref.argmax(1)).float().mean())             # noqa: E731
+        res["vs_strict_fp32_library_path"] = {
+            "logits_max_diff_rel": {"code_gemm_with_strict_fp32_3x3_layers": rel(outs["ours_code_gemm_strict_fp32"]),
+                                    "code_gemm_with_tf32_3x3_layers": rel(outs["ours_code_gemm"]),
+                                    "library_path_with_tf32": rel(outs["ours"])},
+            "top1_agreement": {"code_gemm_with_strict_fp32_3x3_layers": top(outs["ours_code_gemm_strict_fp32"]),
+                               "code_gemm_with_tf32_3x3_layers": top(outs["ours_code_gemm"]),
+                               "library_path_with_tf32": top(outs["ours"])}}
     except Exception as e:                              # must not take the headline metric down
         res["error"] = f"{type(e).__name__}: {e}"[:300]
         torch.cuda.empty_cache()

@@ -4,7 +4,9 @@ Columns: registers, static shared memory, local (spill) bytes, SASS instruction 
 instructions that show how a kernel moves and computes: 128-bit global loads / stores (LDG.E.128 incl. .NA / .CONSTANT
 variants, STG.E.128), bulk async copies (UBLKCP = cp.async.bulk, the TMA 1-D path) and mbarrier waits (SYNCS), packed
 fp32 math (FFMA2 / FMUL2 / FADD2), reciprocal (MUFU.RCP: the one per-thread reciprocal of the exact fast division),
-shared-memory atomics (ATOMS), warp shuffles."""
+shared-memory atomics (ATOMS), warp shuffles; for the one contraction on the path (the integer-code GEMM) the tensor
+path: UTMALDG (TMA tensor loads), UTC*MMA (tcgen05.mma: UTCIMMA = kind::i8, UTCQMMA = kind::f8f6f4), UTCBAR
+(tcgen05.commit), LDTM (tcgen05.ld from tensor memory)."""
 import collections
 import os
 import re
@@ -44,14 +46,18 @@ for line in sass.splitlines():
             c["STG.128"] += 1
         elif op.startswith("STG"):
             c["STG.other"] += 1
-        for key in ("UBLKCP", "SYNCS", "FFMA2", "FMUL2", "FADD2", "MUFU.RCP", "ATOMS", "SHFL", "UTCHMMA", "UTCQMMA"):
+        for key in ("UBLKCP", "SYNCS", "FFMA2", "FMUL2", "FADD2", "MUFU.RCP", "ATOMS", "SHFL", "UTMALDG", "UTCBAR", "LDTM"):
             if op.startswith(key):
                 c[key] += 1
+        if re.match(r"UTC[A-Z]*MMA", op):
+            c["UTC*MMA"] += 1
 demangle = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=True, text=True).stdout.splitlines()
-pretty = dict(zip(counts, demangle))
-cols = ["LDG.128", "LDG.other", "STG.128", "STG.other", "UBLKCP", "SYNCS", "FFMA2", "FMUL2", "FADD2", "MUFU.RCP", "ATOMS", "SHFL"]
-print("libdlmcq.so: %d kernels (sm_100a); no tensor-core instructions anywhere (nothing on this path is a contraction): "
-      "UTC*MMA count = %d" % (len(counts), sum(c["UTCHMMA"] + c["UTCQMMA"] for c in counts.values())))
+pretty = dict(zip(counts, (d.replace("(anonymous namespace)::", "") for d in demangle)))
+cols = ["LDG.128", "LDG.other", "STG.128", "STG.other", "UBLKCP", "SYNCS", "FFMA2", "FMUL2", "FADD2", "MUFU.RCP", "ATOMS", "SHFL",
+        "UTMALDG", "UTC*MMA", "UTCBAR", "LDTM"]
+tc = [pretty[k] for k in counts if counts[k]["UTC*MMA"]]
+print("libdlmcq.so: %d kernels (sm_100a); tensor-core instructions (tcgen05.mma) only in the %d instantiations of the "
+      "integer-code GEMM: %s" % (len(counts), len(tc), "; ".join(re.sub(r"\(.*", "", t) for t in sorted(tc))))
 print("%-92s %4s %6s %5s %5s " % ("kernel", "REG", "SHARED", "LOCAL", "SASS") + " ".join("%9s" % c for c in cols))
 for k in sorted(counts, key=lambda k: pretty[k]):
     p = re.sub(r"\(.*", "", pretty[k]).replace("dlmcq::", "").replace("void ", "").replace("__nv_bfloat16", "bf16")

@@ -214,6 +214,48 @@ def case_fractional_zp():
     return {}
 
 
+def case_resnet_layers():
+    """Every layer of a quantised torchvision ResNet-50 that enable_code_gemm switches, on the input it sees inside the
+    model (captured on the strict-fp32 library path): code path vs library path, layer by layer, 2e-5 of the layer's
+    output magnitude.  (Whole-model logits are not a parity measure for a 4-bit network: one flipped code is 1/15 of a
+    layer's range and 50 untrained layers amplify it - bench.py reports them beside the TF32 path for scale.)"""
+    import copy
+    import torchvision
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.qgemm import enable_code_gemm
+    torch.manual_seed(11)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 4, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+    net = torchvision.models.resnet50().cuda().to(memory_format=torch.channels_last)
+    quantize_model(net, copy.deepcopy(cfg), None)
+    net.eval()
+    x = torch.randn(3, 3, 96, 96).cuda().contiguous(memory_format=torch.channels_last)
+    seen = {}
+    with torch.no_grad():
+        net(x)                                              # observers
+        hooks = [m.register_forward_hook(lambda mod, inp, out, n=n: seen.__setitem__(n, (mod, inp[0].clone(), out.clone())))
+                 for n, m in net.named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))]
+        net(x)
+        for h in hooks:
+            h.remove()
+        names = enable_code_gemm(net)
+        assert len(names) >= 34, names
+        worst, worst_name = 0.0, None
+        for n in names:
+            mod, inp, want = seen[n]
+            got = mod(inp)
+            assert mod.__dict__["_code_gemm"].usable, f"{n} fell back to the library path"
+            assert got.shape == want.shape
+            err = float((got.float() - want.float()).abs().max() / want.abs().max().clamp_min(1e-30))
+            if err > worst:
+                worst, worst_name = err, n
+        assert worst <= 2e-5, f"{worst_name}: {worst:.3e} of the layer's output magnitude"
+    return {"layers": len(names), "worst_layer": worst_name, "worst_err_over_output_scale": worst}
+
+
 def case_errors():
     from dlmc_quant_b200 import qgemm as Q
     from dlmc_quant_b200._lib import DlmcqError
@@ -270,6 +312,7 @@ def build_cases():
     cases.append(("module_i8_linear_fsptq_8bit", case_module, dict(kind="linear", family="fsptq", encoding=I8)))
     cases.append(("module_i8_conv_nchw_qbase", case_module, dict(kind="conv", family="qbase", encoding=I8, channels_last=False)))
     cases.append(("module_fsptq_fractional_zero_point_keeps_reference_path", case_fractional_zp, {}))
+    cases.append(("module_resnet50_every_switched_layer", case_resnet_layers, {}))
     cases.append(("errors", case_errors, {}))
     return cases
 
