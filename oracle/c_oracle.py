@@ -145,3 +145,16 @@ def kth_value(x, k, abs_input=False):
     fn = lib().orc_kth_value
     fn.restype = C.c_float
     return fn(_p(x), C.c_int64(x.size), C.c_int64(int(k)), C.c_int(int(abs_input)))
+
+
+def code_gemm(a_codes, w_codes, m_a, o_a, z_a, m_w, bias=None, relu=False):
+    a, w = _f(a_codes), _f(w_codes)
+    m, k = a.shape
+    n = w.shape[0]
+    mw = _f(m_w).reshape(-1)
+    b = None if bias is None else _f(bias).reshape(-1)
+    out = np.empty((m, n), dtype=np.float32)
+    lib().orc_code_gemm(_p(a), _p(w), C.c_int64(m), C.c_int64(n), C.c_int64(k), C.c_float(float(m_a)),
+                        C.c_float(float(o_a)), C.c_float(float(z_a)), _p(mw), C.c_int64(mw.size), _p(b),
+                        C.c_int(int(relu)), _p(out))
+    return out

@@ -317,3 +317,32 @@ float orc_kth_value(const float* x, int64_t n, int64_t k, int abs_input) {
   free(t);
   return v;
 }
+
+/* ---- the layer product on the integer codes (oracle/restate.py::code_gemm in plain C) ------------------------------
+ * Reference expression: modules/base.py:140 -> modules/linear.py / conv.py `_forward_func(q_input, q_weight)` with
+ * y_a = (ca - z_a)*m_a + o_a and y_w = cw*m_w[n]; factored as alpha[n]*acc + beta[n] (include/dlmcq.h, dlmcq_qgemm):
+ * exact integer dot product, then alpha[n] = m_a*m_w[n], beta[n] = ((o_a - z_a*m_a)*m_w[n])*float(sum_k cw) (+ bias),
+ * out = float(acc)*alpha + beta - every fp32 rounding where the kernels round.  a_codes [m,k], w_codes [n,k] hold
+ * integer-valued floats (as orc_fq_forward writes them); m_w has n or 1 entries. */
+void orc_code_gemm(const float* a_codes, const float* w_codes, int64_t m, int64_t n, int64_t k, float m_a, float o_a,
+                   float z_a, const float* m_w, int64_t m_w_count, const float* bias, int relu, float* out) {
+  for (int64_t j = 0; j < n; ++j) {
+    long long wsum = 0;
+    for (int64_t t = 0; t < k; ++t) wsum += (long long)w_codes[j * k + t];
+    const float mw = m_w[m_w_count == 1 ? 0 : j];
+    const float alpha = m_a * mw;
+    const float zm = z_a * m_a;
+    const float tt = o_a - zm;
+    const float tw = tt * mw;
+    float beta = tw * (float)wsum;
+    if (bias) beta = beta + bias[j];
+    for (int64_t i = 0; i < m; ++i) {
+      long long acc = 0;
+      for (int64_t t = 0; t < k; ++t) acc += (long long)a_codes[i * k + t] * (long long)w_codes[j * k + t];
+      const float prod = (float)acc * alpha;
+      float o = prod + beta;
+      if (relu) o = reluf(o);
+      out[i * n + j] = o;
+    }
+  }
+}

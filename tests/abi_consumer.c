@@ -20,6 +20,9 @@ void orc_fq_forward(const float* x, float* y, float* codes, int64_t n, int64_t c
 void orc_fq_backward(const float* x, const float* dy, float* dx, double* dscale, int64_t n, int64_t channels,
                      int64_t inner, const float* scale, const float* offset, int form, float lo, float hi, float g);
 void orc_minmax(const float* x, int64_t channels, int64_t inner, int n_bits, int is_signed, float* scale, float* offset);
+float orc_grad_scale_value(float s, float g);
+void orc_code_gemm(const float* a_codes, const float* w_codes, int64_t m, int64_t n, int64_t k, float m_a, float o_a,
+                   float z_a, const float* m_w, int64_t m_w_count, const float* bias, int relu, float* out);
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -134,6 +137,41 @@ static void observer_case(void) {
   free(w); free(s); free(o); free(sr); free(orf);
 }
 
+/* the quantised layer's product on the integer codes: x [m,k] (QBase A4, float offset) and w [n,k] (W4 symmetric per
+ * output channel) -> one byte per code -> alpha / beta from the device-resident qparams -> TMA + tcgen05 GEMM,
+ * against the plain-C oracle on the oracle's own codes: bit-exact */
+static void qgemm_case(int encoding, const char* name) {
+  const int64_t m = 777, n = 200, k = 192;
+  float *x = malloc(m * k * 4), *w = malloc(n * k * 4), *ca = malloc(m * k * 4), *cw = malloc(n * k * 4);
+  float *sw = malloc(n * 4), *bias = malloc(n * 4), *out = malloc(m * n * 4), *ref = malloc(m * n * 4);
+  for (int64_t i = 0; i < m * k; ++i) { const float v = nrand() * 1.5f; x[i] = (v > 0.f ? v : 0.f) + 0.05f; }
+  for (int64_t i = 0; i < n * k; ++i) w[i] = nrand() * 0.05f;
+  for (int64_t j = 0; j < n; ++j) { sw[j] = 0.02f + 0.0003f * (float)j; bias[j] = nrand(); }
+  const float sa = 0.31f, oa = 0.05f;
+  const float g = (float)(1.0 / sqrt((double)(m * k) * 15));
+  orc_fq_forward(x, NULL, ca, m * k, 1, m * k, &sa, &oa, DLMCQ_FORM_AFFINE, 0.f, 15.f, g);
+  orc_fq_forward(w, NULL, cw, n * k, n, k, sw, NULL, DLMCQ_FORM_SYM, -7.f, 7.f, 0.f);
+  orc_code_gemm(ca, cw, m, n, k, orc_grad_scale_value(sa, g), oa, 0.f, sw, n, bias, 1, ref);
+
+  float *d_x = dev_copy(x, m * k), *d_w = dev_copy(w, n * k), *d_sa = dev_copy(&sa, 1), *d_oa = dev_copy(&oa, 1);
+  float *d_sw = dev_copy(sw, n), *d_bias = dev_copy(bias, n), *d_alpha, *d_beta, *d_out;
+  void *d_ca, *d_cw;
+  CK(cudaMalloc(&d_ca, m * k)); CK(cudaMalloc(&d_cw, n * k));
+  CK(cudaMalloc((void**)&d_alpha, n * 4)); CK(cudaMalloc((void**)&d_beta, n * 4)); CK(cudaMalloc((void**)&d_out, m * n * 4));
+  dlmcq_layout la = {1, 1, m * k, DLMCQ_F32}, lw = {1, n, k, DLMCQ_F32};
+  dlmcq_qparams qa = {DLMCQ_FORM_AFFINE, 0, 15, g, d_sa, d_oa}, qw = {DLMCQ_FORM_SYM, -7, 7, 0.f, d_sw, NULL};
+  QK(dlmcq_codes_forward(d_x, d_ca, &la, &qa, encoding, NULL));
+  QK(dlmcq_codes_forward(d_w, d_cw, &lw, &qw, encoding, NULL));
+  QK(dlmcq_qgemm_prepare(d_cw, n, k, encoding, &qa, &qw, n, d_bias, d_alpha, d_beta, NULL));
+  QK(dlmcq_qgemm(d_ca, d_cw, d_alpha, d_beta, d_out, m, n, k, encoding, 0, 1, DLMCQ_F32, NULL));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, d_out, m * n * 4, cudaMemcpyDeviceToHost));
+  report(name, memcmp(out, ref, m * n * 4) == 0);
+  CK(cudaFree(d_x)); CK(cudaFree(d_w)); CK(cudaFree(d_sa)); CK(cudaFree(d_oa)); CK(cudaFree(d_sw)); CK(cudaFree(d_bias));
+  CK(cudaFree(d_ca)); CK(cudaFree(d_cw)); CK(cudaFree(d_alpha)); CK(cudaFree(d_beta)); CK(cudaFree(d_out));
+  free(x); free(w); free(ca); free(cw); free(sw); free(bias); free(out); free(ref);
+}
+
 static void bandwidth(void) {
   const int64_t n = (int64_t)1 << 26;
   float *d_x, *d_dy, *d_y, *d_dx, *d_ds, *d_s, *d_o;
@@ -172,6 +210,8 @@ int main(void) {
   fq_case("QBase A4 per-channel activation [6, 8, 28, 28] (AFFINE, tiled kernels)", DLMCQ_FORM_AFFINE, 0, 15, 6, 8, 784, 1);
   fq_case("QBase A4 per-channel activation [40, 8, 7, 7] (AFFINE, channel-major kernels)", DLMCQ_FORM_AFFINE, 0, 15, 40, 8, 49, 1);
   observer_case();
+  qgemm_case(DLMCQ_QGEMM_I8, "integer-code layer product (tcgen05 kind::i8) [777,192] x [200,192]: bit-exact vs the C oracle");
+  qgemm_case(DLMCQ_QGEMM_E4M3, "integer-code layer product (tcgen05 kind::f8f6f4, e4m3 codes): bit-exact vs the C oracle");
   bandwidth();
   printf("%s: %d check(s) failed\n", failures ? "FAILED" : "ALL PASS", failures);
   return failures ? 1 : 0;

@@ -68,3 +68,17 @@ def test_code_gemm_relu_and_integer_exactness():
     out = R.code_gemm(ca, cw, 1.0, 0.0, 0.0, torch.ones(5))
     assert torch.equal(out, (ca @ cw.t()).float())            # |acc| up to 1.3e8: one RN conversion, nothing else
     assert (R.code_gemm(ca, cw, 1.0, 0.0, 0.0, torch.ones(5), relu=True) >= 0).all()
+
+
+@pytest.mark.parametrize("a_form,w_form", [(AFFINE, AFFINE), (ZP, SYM), (A1, SYM)])
+@pytest.mark.parametrize("per_channel", [True, False])
+def test_plain_c_oracle_equals_the_torch_restatement(a_form, w_form, per_channel):
+    """The second, torch-free statement of the factored product (oracle/fq_oracle.c::orc_code_gemm, what the plain-C
+    ABI consumer checks the device against) agrees with oracle/restate.py::code_gemm bit for bit."""
+    from oracle import c_oracle
+    c_oracle.build()
+    qa, qw, ca, cw, m_a, o_a, z_a, m_w, bias = _setup(a_form, w_form, 8, False, per_channel, seed=5)
+    for relu in (False, True):
+        want = R.code_gemm(ca, cw, m_a, o_a, z_a, m_w, bias, relu=relu)
+        got = c_oracle.code_gemm(ca.numpy(), cw.numpy(), float(m_a), float(o_a), float(z_a), m_w.numpy(), bias.numpy(), relu)
+        assert torch.equal(torch.from_numpy(got), want)
