@@ -256,6 +256,82 @@ def case_resnet_layers():
     return {"layers": len(names), "worst_layer": worst_name, "worst_err_over_output_scale": worst}
 
 
+def case_codes_layouts():
+    """dlmcq_codes_forward == the codes of dlmcq_fq_forward, byte for byte, on every path of the code kernels: fp32 and
+    bf16, vector path with a ragged tail, unaligned views (scalar path), per-channel weights and activations,
+    special values (NaN -> 0, +-inf clamp, -0), both encodings."""
+    from dlmc_quant_b200 import functional as F
+    from dlmc_quant_b200 import qgemm as Q
+    g = torch.Generator().manual_seed(17)
+    checked = 0
+    for dtype in (torch.float32, torch.bfloat16):
+        for enc in (I8, E4M3):
+            for form, lo, hi, off in ((AFFINE, 0, 15, 0.04), (ZP, 0, 15, 3.0), (SYM, -7, 7, None), (A1, -7, 7, -0.01)):
+                x = (torch.randn(4099 + 16 * 37, generator=g) * 2).to(dtype)
+                x[:6] = torch.tensor([float("nan"), float("inf"), -float("inf"), -0.0, 0.0, 1e-30]).to(dtype)
+                xc = x.cuda()
+                s = torch.tensor([0.23]).cuda()
+                o = None if off is None else torch.tensor([off]).cuda()
+                gg = 1e-3 if form == AFFINE else 0.0
+                for view in (xc, xc[1:], xc[:4096]):                      # aligned + ragged, unaligned, aligned exact
+                    view = view if view.data_ptr() % 16 else view.contiguous()
+                    want = F.fq_forward(view, s, o, lo, hi, form, gg, want_codes=True, want_y=False).float().nan_to_num(0.0)
+                    got = Q.codes_forward(view, s, o, lo, hi, form, gg, encoding=enc)
+                    gi = got.view(torch.float8_e4m3fn).float() if enc == E4M3 else (
+                        got.view(torch.int8).float() if lo < 0 else got.float())
+                    assert torch.equal(gi, want), (dtype, enc, form, view.shape)
+                    checked += 1
+            # per-channel: weights [C, K] (ch_axis 0) and activations [B, C, H, W] (ch_axis 1)
+            for shape, ax in (((24, 50), 0), ((3, 8, 5, 5), 1)):
+                t = (torch.randn(*shape, generator=g) * 0.1).to(dtype).cuda()
+                c = shape[ax]
+                sc = (torch.rand(c, generator=g) * 0.02 + 0.01).cuda()
+                want = F.fq_forward(t, sc, None, -7, 7, SYM, 0.0, ch_axis=ax, want_codes=True, want_y=False).float()
+                got = Q.codes_forward(t, sc, None, -7, 7, SYM, 0.0, ch_axis=ax, encoding=enc)
+                gi = got.view(torch.float8_e4m3fn).float() if enc == E4M3 else got.view(torch.int8).float()
+                assert torch.equal(gi, want), (dtype, enc, shape)
+                checked += 1
+    return {"comparisons": checked}
+
+
+def case_cuda_graph():
+    """The switched layers are capturable: after one warm forward (observers, weight codes, alpha / beta cached, kernel
+    attributes set) a forward holds no host synchronisation, so torch.cuda.graph records it; replays on fresh inputs
+    equal the eager code path bit for bit."""
+    import copy
+    from dlmc_quant_b200 import quantize_model
+    from dlmc_quant_b200.qgemm import enable_code_gemm
+    torch.manual_seed(5)
+    nn = torch.nn
+    net = nn.Sequential(nn.Conv2d(32, 64, 1), nn.ReLU(), nn.Conv2d(64, 48, 1, bias=False), nn.ReLU(),
+                        nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(48, 16)).cuda().to(memory_format=torch.channels_last)
+    cfg = {"weight": {"enable": True, "type": "minmax_channel", "args": {"n_bits": 4, "signed": True, "ch_axis": 0}},
+           "input": {"enable": True, "type": "minmax_tensor", "args": {"n_bits": 4, "signed": False}},
+           "exclude_layers": [], "override_options": [], "momentum": 0.1}
+    quantize_model(net, copy.deepcopy(cfg), None)
+    net.eval()
+    xs = [torch.rand(5, 32, 10, 10).cuda().contiguous(memory_format=torch.channels_last) for _ in range(3)]
+    with torch.no_grad():
+        net(xs[0])
+        assert enable_code_gemm(net) == ["0", "2", "6"]
+        eager = [net(x).clone() for x in xs]
+        static_x = xs[0].clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net(static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_y = net(static_x)
+        for x, want in zip(xs, eager):
+            static_x.copy_(x)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(static_y, want), "graph replay differs from the eager code path"
+    return {}
+
+
 def case_errors():
     from dlmc_quant_b200 import qgemm as Q
     from dlmc_quant_b200._lib import DlmcqError
@@ -313,6 +389,8 @@ def build_cases():
     cases.append(("module_i8_conv_nchw_qbase", case_module, dict(kind="conv", family="qbase", encoding=I8, channels_last=False)))
     cases.append(("module_fsptq_fractional_zero_point_keeps_reference_path", case_fractional_zp, {}))
     cases.append(("module_resnet50_every_switched_layer", case_resnet_layers, {}))
+    cases.append(("module_cuda_graph_capture", case_cuda_graph, {}))
+    cases.append(("codes_forward_every_path", case_codes_layouts, {}))
     cases.append(("errors", case_errors, {}))
     return cases
 
