@@ -46,7 +46,7 @@ constexpr int kStgPitch = 36;                                 // floats per row 
 constexpr int kStgBytes = kEpiWarps * 32 * kStgPitch * 4;
 constexpr int kBarBytes = 128;
 constexpr size_t kGemmSmem = 1024 + static_cast<size_t>(kStages) * kStageBytes + kStgBytes + kBarBytes;
-constexpr long long kWatchdogCycles = 4000000000LL;           // ~2 s: a wedged pipeline traps instead of hanging the GPU
+constexpr long long kWatchdogCycles = 30000000000LL;          // ~15 s in ONE barrier wait: a wedged pipeline traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 

@@ -176,12 +176,11 @@ class _CodeGemmState:
         w2 = w.reshape(n, -1)                # 1x1 conv weights [n, k, 1, 1] are [n, k] matrices in either memory format
         w2 = w2 if w2.is_contiguous() else w2.contiguous()
         g_w = 1 / math.sqrt(w.numel() * hi_w) if w_form == FORM_AFFINE else 0.0
-        g_a = 0.0                            # the grad_scale VALUE needs numel of the input: filled per call (AFFINE)
         per_ch = ws.numel() == n and n != 1
         self.w_codes = codes_forward(w2, ws.reshape(-1), None, lo_w, hi_w, w_form, g_w, ch_axis=0 if per_ch else None,
                                      encoding=self.encoding)
         self._wt = (ws.reshape(-1), lo_w, hi_w, w_form, g_w)
-        self._g_a = g_a
+        self._g_a = 0.0                      # the activation's grad_scale factor depends on the input's numel: epilogue()
         self.alpha = self.beta = None
         self._ab_numel = None
         return True
