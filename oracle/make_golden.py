@@ -319,6 +319,81 @@ def golden_fsptq(ns, gen):
     b.save()
 
 
+def golden_qgemm(ns, gen):
+    """Whole-LAYER outputs of the reference's quantised Linear / 1x1 Conv2d modules in eval mode (what
+    `_forward_func(q_input, q_weight)` returns, modules/base.py:140 and FSPTQuant/base.py:111-113), with the qparams
+    the reference's own observers chose: the pin for the integer-code layer product (include/dlmcq.h, dlmcq_qgemm).
+    K is a multiple of 16 everywhere so the same cases run through the TMA kernel on the GPU."""
+    b = Book("qgemm")
+    qnn, FSP = ns.modules, ns.FSPTQuant
+    real_zeros = torch.zeros
+
+    def cpu_zeros(*a, **k):
+        k.pop("device", None)
+        return real_zeros(*a, **k)
+
+    def build(cls, base, qcfg, fsptq=False):
+        if not fsptq:
+            return _build(cls, base, qcfg)
+        torch.zeros = cpu_zeros                   # FSPTQBase.initialize hard-codes device='cuda' (FSPTQuant/base.py:47)
+        try:
+            return _build(cls, base, qcfg)
+        finally:
+            torch.zeros = real_zeros
+
+    def qcfg_of(wtype, itype, wbits, abits, act_signed=False, recon=None):
+        w = {"enable": True, "type": wtype, "args": {"n_bits": wbits, "signed": True}}
+        if "channel" in wtype:
+            w["args"]["ch_axis"] = 0
+        if recon is not None:
+            w["recon_type"] = recon
+        return {"weight": w, "input": {"enable": True, "type": itype, "args": {"n_bits": abits, "signed": act_signed}},
+                "momentum": 0.1}
+
+    def run(case, m, x, base, meta):
+        out = _run_module(m, x, 0, gen, train=False, steps=1)
+        b.add(case, meta, {"x": x, "weight": base.weight, "bias": base.bias if base.bias is not None else torch.zeros(0)}, out)
+
+    # QBase family (modules/base.py): per-tensor weights as the reference allocates them
+    for name, wbits, abits, kind, act_signed in [("w4a4", 4, 4, "act", False), ("w8a8_offset", 8, 8, "shifted", False),
+                                                  ("w4a4_signed_act", 4, 4, "randn", True)]:
+        qcfg = qcfg_of("minmax_tensor", "minmax_tensor", wbits, abits, act_signed)
+        lin = torch.nn.Linear(64, 24)
+        with torch.no_grad():
+            lin.weight.copy_(gen_tensor(gen, lin.weight.shape, "wt"))
+            lin.bias.copy_(gen_tensor(gen, lin.bias.shape, "randn"))
+        run(f"qbase_linear_{name}", build(qnn.QLinear, lin, qcfg), gen_tensor(gen, (10, 64), kind), lin,
+            {"qconfig": qcfg, "kind": "linear", "family": "qbase"})
+        conv = torch.nn.Conv2d(32, 40, 1, bias=(name != "w4a4"))
+        with torch.no_grad():
+            conv.weight.copy_(gen_tensor(gen, conv.weight.shape, "wt"))
+        run(f"qbase_conv1x1_{name}", build(qnn.QConv2d, conv, qcfg), gen_tensor(gen, (3, 32, 6, 5), kind), conv,
+            {"qconfig": qcfg, "kind": "conv", "family": "qbase"})
+    # QBase with a per-output-channel weight scale: only reachable by pre-shaping wt_scale (SURVEY.md a6)
+    qcfg = qcfg_of("minmax_channel", "minmax_tensor", 4, 4)
+    conv = torch.nn.Conv2d(48, 36, 1, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(gen_tensor(gen, conv.weight.shape, "wt") * torch.linspace(0.5, 3, 36).view(36, 1, 1, 1))
+    m = build(qnn.QConv2d, conv, qcfg)
+    m.wt_scale = torch.nn.Parameter(torch.ones(36, 1, 1, 1))
+    run("qbase_conv1x1_pcw_w4a4", m, gen_tensor(gen, (2, 48, 7, 7), "act"), conv,
+        {"qconfig": qcfg, "kind": "conv", "family": "qbase", "per_channel_weight": True})
+    # FSPTQ family (FSPTQuant/base.py): integer zero-point activations, symmetric per-channel weights (+1e-6)
+    for name, wbits, abits in [("w8a8", 8, 8), ("w4a4", 4, 4)]:
+        qcfg = qcfg_of("minmax_channel", "minmax_tensor", wbits, abits, recon="none")
+        lin = torch.nn.Linear(48, 20)
+        with torch.no_grad():
+            lin.weight.copy_(gen_tensor(gen, lin.weight.shape, "wt") * torch.linspace(0.5, 2, 20).view(20, 1))
+        run(f"fsptq_linear_{name}", build(FSP.FSPTQLinear, lin, qcfg, fsptq=True), gen_tensor(gen, (7, 48), "act"), lin,
+            {"qconfig": qcfg, "kind": "linear", "family": "fsptq"})
+        conv = torch.nn.Conv2d(16, 40, 1, bias=True)
+        with torch.no_grad():
+            conv.weight.copy_(gen_tensor(gen, conv.weight.shape, "wt") * torch.linspace(0.5, 3, 40).view(40, 1, 1, 1))
+        run(f"fsptq_conv1x1_{name}", build(FSP.FSPTQConv2d, conv, qcfg, fsptq=True), gen_tensor(gen, (4, 16, 5, 5), "act"),
+            conv, {"qconfig": qcfg, "kind": "conv", "family": "fsptq"})
+    b.save()
+
+
 class _Timeout(Exception):
     pass
 
@@ -472,6 +547,9 @@ def main():
     ns = ref_shim.load()
     torch.manual_seed(SEED)
     torch.set_num_threads(1)     # reduction order of the stored sums is then machine-independent
+    if sys.argv[1:] == ["qgemm"]:                # this book has its own generator: mint it without touching the others
+        golden_qgemm(ns, torch.Generator().manual_seed(SEED + 11))
+        return
     gen = torch.Generator().manual_seed(SEED)
     golden_utils(ns, gen)
     golden_qbase(ns, gen)
@@ -480,6 +558,7 @@ def main():
     golden_fsptq(ns, gen)
     golden_observers(ns, gen)
     golden_reparam(torch.Generator().manual_seed(SEED + 7))
+    golden_qgemm(ns, torch.Generator().manual_seed(SEED + 11))
 
 
 if __name__ == "__main__":

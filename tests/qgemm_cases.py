@@ -256,6 +256,35 @@ def case_resnet_layers():
     return {"layers": len(names), "worst_layer": worst_name, "worst_err_over_output_scale": worst}
 
 
+def case_golden():
+    """tests/golden/qgemm.npz - the eval-mode outputs of the UNMODIFIED reference's QLinear / 1x1 QConv2d / FSPTQ layers:
+    the device pipeline (codes_forward -> qgemm_prepare -> qgemm, both operand encodings where the codes fit) equals the
+    integer oracle bit for bit and the reference's layer output to 1e-5 of sum_k |y_a*y_w| (+ |bias|)."""
+    from dlmc_quant_b200 import qgemm as Q
+    from tests import golden_io
+    from tests.qgemm_golden import Problem
+    worst, runs = 0.0, 0
+    for name, case in sorted(golden_io.load("qgemm").items()):
+        p = Problem(case)
+        ca, cw, m_a, o_a, z_a, m_w = p.oracle()
+        want = R.code_gemm(ca, cw, m_a, o_a, z_a, m_w, p.bias)
+        encs = [I8] + ([E4M3] if max(p.a_hi, -p.a_lo, p.w_hi, -p.w_lo) <= 16 else [])
+        off = p.off_a.cuda()
+        for enc in encs:
+            a_codes = Q.codes_forward(p.x.cuda(), p.s_a.cuda(), off, p.a_lo, p.a_hi, p.a_form, p.g_a, encoding=enc)
+            w_codes = Q.codes_forward(p.w.cuda(), p.s_w.cuda(), None, p.w_lo, p.w_hi, p.w_form, p.g_w,
+                                      ch_axis=0 if p.s_w.numel() > 1 else None, encoding=enc)
+            alpha, beta = Q.qgemm_prepare(w_codes, (p.s_a.cuda(), off, p.a_lo, p.a_hi, p.a_form, p.g_a),
+                                          (p.s_w.cuda(), p.w_lo, p.w_hi, p.w_form, p.g_w),
+                                          None if p.bias is None else p.bias.cuda(), enc)
+            got = Q.qgemm(a_codes, w_codes, alpha, beta, a_signed=p.a_lo < 0, encoding=enc).cpu()
+            assert torch.equal(got, want), f"{name} (encoding {enc}): differs from the integer oracle"
+            err = ((got.double() - p.y.double()).abs() / p.bound().clamp_min(1e-30)).max().item()
+            assert err <= 1e-5, f"{name}: {err:.3e} vs the reference's layer output"
+            worst, runs = max(worst, err), runs + 1
+    return {"fixtures_x_encodings": runs, "worst_rel_err_vs_reference_layer_output": worst}
+
+
 def case_codes_layouts():
     """dlmcq_codes_forward == the codes of dlmcq_fq_forward, byte for byte, on every path of the code kernels: fp32 and
     bf16, vector path with a ragged tail, unaligned views (scalar path), per-channel weights and activations,
@@ -391,6 +420,7 @@ def build_cases():
     cases.append(("module_resnet50_every_switched_layer", case_resnet_layers, {}))
     cases.append(("module_cuda_graph_capture", case_cuda_graph, {}))
     cases.append(("codes_forward_every_path", case_codes_layouts, {}))
+    cases.append(("golden_reference_layer_outputs", case_golden, {}))
     cases.append(("errors", case_errors, {}))
     return cases
 

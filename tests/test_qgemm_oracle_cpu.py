@@ -82,3 +82,28 @@ def test_plain_c_oracle_equals_the_torch_restatement(a_form, w_form, per_channel
         want = R.code_gemm(ca, cw, m_a, o_a, z_a, m_w, bias, relu=relu)
         got = c_oracle.code_gemm(ca.numpy(), cw.numpy(), float(m_a), float(o_a), float(z_a), m_w.numpy(), bias.numpy(), relu)
         assert torch.equal(torch.from_numpy(got), want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pinned against the reference's own layer outputs (tests/golden/qgemm.npz, minted from the unmodified reference)
+# ---------------------------------------------------------------------------------------------------------------
+from tests import golden_io  # noqa: E402
+from tests.qgemm_golden import Problem  # noqa: E402
+
+QGEMM_GOLDEN = golden_io.load("qgemm")
+
+
+@pytest.mark.parametrize("name", sorted(QGEMM_GOLDEN))
+def test_factored_product_equals_the_reference_layer_output(name):
+    """The reference module's eval output (its observers' qparams, its own F.linear / F.conv2d on its own fake-quantised
+    tensors) vs oracle/restate.py::code_gemm on the oracle's codes: <= 1e-5 of sum_k |y_a*y_w| (+|bias|)."""
+    p = Problem(QGEMM_GOLDEN[name])
+    ca, cw, m_a, o_a, z_a, m_w = p.oracle()
+    # the codes dequantise to exactly the tensors the reference fed to _forward_func
+    ya = (ca - z_a) * m_a + o_a if p.a_form == 2 else ca * m_a + o_a
+    assert torch.equal(ya, p.qx) and torch.equal(cw * (m_w.reshape(-1, 1) if m_w.numel() > 1 else m_w), p.qw)
+    assert bool((ca == ca.round()).all()) and bool((cw == cw.round()).all())
+    out = R.code_gemm(ca, cw, m_a, o_a, z_a, m_w, p.bias)
+    err = ((out.double() - p.y.double()).abs() / p.bound().clamp_min(1e-30)).max().item()
+    assert err <= 1e-5, err
+    assert len(QGEMM_GOLDEN) == 11
